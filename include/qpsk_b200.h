@@ -1,0 +1,116 @@
+/*
+ * qpsk_b200.h -- batch C-ABI of the B200-native QPSK receiver (libqpsk_b200.so).
+ *
+ * Plain C: opaque handles, plain pointers and sizes, int status returns (0 = success, negative
+ * = error, text from qpsk_b200_last_error()).  No CPU fallback exists: every entry point that
+ * computes fails with QPSK_B200_ERR_CUDA when no sm_100 device is usable.
+ *
+ * The reference (MonsieurETM/QPSK) handles exactly one channel through file-scope singletons;
+ * this interface is the same pipeline over many independent channels:
+ *
+ *   qpsk_b200_rx_process_*   <->  rx_frame()           qpsk.c:88-218   (static in the reference)
+ *        mixer                    qpsk.c:114-120
+ *        matched filter           rrc_fir()            rrc_fir.c:17-30
+ *        timing histogram/index   qpsk.c:131-180
+ *        decimation + delay       qpsk.c:186-191
+ *        Costas loop              qpsk.c:196-207, costas_loop.c:44-74
+ *        slicer                   qpsk_demod()         qpsk.c:74-79
+ *   qpsk_b200_fir_*          <->  rrc_fir()/rrc_make() rrc_fir.h:16-17
+ *   qpsk_b200_fft_*          <->  fftn()/ifftn()       algorithms/fft.h:46-49 (+ |X|^2 argmax)
+ *   qpsk_b200_bits_*         <->  scramble()/interleave()/crc16()  algorithms/*.h
+ *   qpsk_b200_tx_*           <->  qpsk_packet_mod()/tx_frame()     qpsk.c:225-285
+ *
+ * The single-channel drop-in symbols of the reference headers (rrc_fir, rrc_make, the 22
+ * costas_loop functions, fft/fftn/ifft/ifftn, crc16, interleave, scramble, rx_frame, ...) are
+ * exported by the same library; see include/qpsk_dropin.h and INTEGRATION.md.
+ */
+#ifndef QPSK_B200_H
+#define QPSK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    QPSK_B200_OK = 0,
+    QPSK_B200_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+    QPSK_B200_ERR_CUDA = -2,     /* CUDA runtime or device failure (no fallback) */
+    QPSK_B200_ERR_STATE = -3     /* call sequence error (e.g. output not enabled) */
+};
+
+enum { QPSK_B200_MODE_EXACT = 0,   /* reference arithmetic, bit-exact decisions */
+       QPSK_B200_MODE_FAST = 1 };  /* fused multiply-add FIR (<= 1e-5 relative), not bit-exact */
+enum { QPSK_B200_UB_ALIAS = 0,     /* reproduce the Makefile-build out-of-frame read of qpsk.c:190 */
+       QPSK_B200_UB_CLAMP = 1 };   /* fenced: out-of-frame reads return the last sample of the frame */
+
+enum {                              /* cfg.flags */
+    QPSK_B200_KEEP_FIR = 1,         /* keep the matched-filter output (16 B/sample!) for parity checks */
+    QPSK_B200_KEEP_SYMBOLS = 2      /* keep the derotated symbols (costas_frame) */
+};
+
+typedef struct {
+    float fs;          /* FS      qpsk.h:16   9600 */
+    float rs;          /* RS      qpsk.h:17   2400 (1200 for the 10 m profile) */
+    float center;      /* CENTER  qpsk.h:18   1500 */
+    float rrc_alpha;   /* qpsk.c:308          0.35 */
+    float loop_bw;     /* qpsk.c:302          (float)(TAU/100) */
+    int   ntaps;       /* NTAPS   rrc_fir.h:13 127 */
+    int   frame_size;  /* FRAME_SIZE qpsk.h:23 512 */
+    int   mode;        /* QPSK_B200_MODE_* */
+    int   ub_mode;     /* QPSK_B200_UB_* */
+    int   flags;       /* QPSK_B200_KEEP_* */
+    int   device;      /* CUDA device ordinal */
+} qpsk_b200_rx_config;
+
+typedef struct qpsk_b200_rx qpsk_b200_rx;
+
+/* which array qpsk_b200_rx_read() downloads; all are channel-major on the host side */
+enum {
+    QPSK_B200_OUT_DIBITS = 0,   /* uint8  [C][F*nsym/4]  4 dibits per byte, symbol i at bits 2*(i%4); dibit = bits[0] | bits[1]<<1 */
+    QPSK_B200_OUT_INDEX = 1,    /* int32  [C][F]         timing index per frame */
+    QPSK_B200_OUT_TRACK = 2,    /* float  [C][F][2]      (d_phase, d_freq) after each frame */
+    QPSK_B200_OUT_DEC = 3,      /* float2 [C][F*nsym]    decimated symbols produced by each frame */
+    QPSK_B200_OUT_SYMBOLS = 4,  /* float2 [C][F*nsym]    costas_frame (needs KEEP_SYMBOLS) */
+    QPSK_B200_OUT_FIR = 5,      /* float2 [C][F*N]       matched-filter output (needs KEEP_FIR) */
+    QPSK_B200_OUT_TAPS = 6      /* float  [ntaps] */
+};
+
+const char *qpsk_b200_last_error(void);
+int qpsk_b200_device_count(void);
+
+/* fills the reference's constants (2400 baud profile) */
+void qpsk_b200_rx_default_config(qpsk_b200_rx_config *cfg);
+
+/* nchan independent channels, at most max_frames frames per process call */
+int qpsk_b200_rx_create(const qpsk_b200_rx_config *cfg, int nchan, int max_frames, qpsk_b200_rx **out);
+int qpsk_b200_rx_destroy(qpsk_b200_rx *rx);
+/* stream start for every channel: zero delay lines, loop at rest, fbb_rx_phase = cmplx(0) */
+int qpsk_b200_rx_reset(qpsk_b200_rx *rx);
+
+/* PCM already in HBM: d_pcm is int16 [C][nframes*frame_size], 16-byte aligned.  Asynchronous on
+ * `cuda_stream` (a cudaStream_t, NULL = the context's own stream).  Channel state carries over
+ * to the next call, so a stream may be fed in several calls. */
+int qpsk_b200_rx_process_device(qpsk_b200_rx *rx, const int16_t *d_pcm, int nframes, void *cuda_stream);
+/* PCM in host memory (pinned for best speed): copies in, runs, copies the packed dibits out
+ * (h_dibits may be NULL) and returns when done. */
+int qpsk_b200_rx_process_host(qpsk_b200_rx *rx, const int16_t *h_pcm, int nframes, uint8_t *h_dibits);
+int qpsk_b200_rx_sync(qpsk_b200_rx *rx);
+
+/* download one output of the most recent process call, channel-major, `bytes` = exact size */
+int qpsk_b200_rx_read(qpsk_b200_rx *rx, int what, void *h_dst, size_t bytes);
+size_t qpsk_b200_rx_output_bytes(const qpsk_b200_rx *rx, int what);
+/* device-resident packed dibits of the most recent call, internal layout
+ * uint32 [F][nsym/16][Cpad] (channel-fastest); for consumers that stay on the GPU */
+int qpsk_b200_rx_device_dibits(qpsk_b200_rx *rx, const uint32_t **d_ptr, int *cpad);
+/* kernels launched by this context so far (bench bookkeeping) */
+long long qpsk_b200_rx_launch_count(const qpsk_b200_rx *rx);
+/* device milliseconds of the front-end kernel in the most recent call (CUDA events on its stream) */
+int qpsk_b200_rx_last_kernel_ms(qpsk_b200_rx *rx, float *front_ms, float *costas_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

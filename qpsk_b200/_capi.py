@@ -1,0 +1,61 @@
+"""ctypes binding of libqpsk_b200.so (the C-ABI declared in include/qpsk_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is usable, the
+calls raise.  The library is built in-tree by `make -C qpsk_b200` (see __graft_entry__.build()).
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libqpsk_b200.so")
+
+
+class QpskB200Error(RuntimeError):
+    pass
+
+
+class RxConfig(C.Structure):
+    _fields_ = [("fs", C.c_float), ("rs", C.c_float), ("center", C.c_float), ("rrc_alpha", C.c_float),
+                ("loop_bw", C.c_float), ("ntaps", C.c_int), ("frame_size", C.c_int), ("mode", C.c_int),
+                ("ub_mode", C.c_int), ("flags", C.c_int), ("device", C.c_int)]
+
+
+MODE_EXACT, MODE_FAST = 0, 1
+UB_ALIAS, UB_CLAMP = 0, 1
+KEEP_FIR, KEEP_SYMBOLS = 1, 2
+OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS = range(7)
+
+_lib = None
+
+
+def lib():
+    """Load libqpsk_b200.so; raises QpskB200Error when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise QpskB200Error("%s not found: run `make -C qpsk_b200` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.qpsk_b200_last_error.restype = C.c_char_p
+    L.qpsk_b200_rx_default_config.argtypes = [C.POINTER(RxConfig)]
+    L.qpsk_b200_rx_default_config.restype = None
+    L.qpsk_b200_rx_create.argtypes = [C.POINTER(RxConfig), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.qpsk_b200_rx_destroy.argtypes = [C.c_void_p]
+    L.qpsk_b200_rx_reset.argtypes = [C.c_void_p]
+    L.qpsk_b200_rx_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.qpsk_b200_rx_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.qpsk_b200_rx_sync.argtypes = [C.c_void_p]
+    L.qpsk_b200_rx_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    L.qpsk_b200_rx_output_bytes.argtypes = [C.c_void_p, C.c_int]
+    L.qpsk_b200_rx_output_bytes.restype = C.c_size_t
+    L.qpsk_b200_rx_device_dibits.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]
+    L.qpsk_b200_rx_launch_count.argtypes = [C.c_void_p]
+    L.qpsk_b200_rx_launch_count.restype = C.c_longlong
+    L.qpsk_b200_rx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise QpskB200Error("qpsk_b200 error %d: %s" % (rc, lib().qpsk_b200_last_error().decode()))

@@ -1,0 +1,399 @@
+// qpsk_b200.cu -- C-ABI (include/qpsk_b200.h) over the sm_100a receiver kernels.
+// Build: see qpsk_b200/Makefile (nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+#include "../../include/qpsk_b200.h"
+#include "../host/host_design.h"
+#include "common.cuh"
+#include "rx_front.cuh"
+#include "rx_costas.cuh"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(QPSK_B200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),  \
+                        __FILE__, __LINE__);                                                          \
+    } while (0)
+
+extern "C" const char* qpsk_b200_last_error(void) { return g_err; }
+
+extern "C" int qpsk_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static const double kTau = 2.0 * 3.14159265358979323846;
+
+// ---------------------------------------------------------------------------------------------
+struct qpsk_b200_rx {
+    qpsk_b200_rx_config cfg;
+    int C, Cpad, maxF, N, sps, nsym, nslots, slot_base, lastF;
+    float taps[QPSK_MAX_TAPS];
+    float2 rect, rot45;
+    qpsk_host_loop loop;
+    cudaStream_t stream;
+    cudaEvent_t ev[4];
+    bool timed;
+    long long launches;
+    // device state
+    int16_t* d_pcm_tail;    // [Cpad][128]
+    float2* d_phasor;       // [128 + maxF*N]
+    float2* d_ph_tail;      // [128]
+    float2* d_ph_state;     // [1]
+    float2* d_dec_ring;     // [nslots][nsym][Cpad]
+    int* d_index_t;         // [maxF][Cpad]
+    float2* d_loop_state;   // [Cpad]
+    unsigned* d_dibits_t;   // [maxF][nsym/16][Cpad]
+    float2* d_track_t;      // [maxF][Cpad]
+    float2* d_fir_dbg;      // [C][maxF*N] or null
+    float2* d_costas_dbg;   // [maxF][nsym][Cpad] or null
+    int16_t* d_pcm_stage;   // [C][maxF*N] for the host path (lazy)
+    void* d_scratch;        // transposed download staging (lazy)
+    size_t scratch_bytes;
+};
+
+extern "C" void qpsk_b200_rx_default_config(qpsk_b200_rx_config* cfg) {
+    memset(cfg, 0, sizeof *cfg);
+    cfg->fs = 9600.0f;                        // qpsk.h:16
+    cfg->rs = 2400.0f;                        // qpsk.h:17
+    cfg->center = 1500.0f;                    // qpsk.h:18
+    cfg->rrc_alpha = .35f;                    // qpsk.c:308
+    cfg->loop_bw = (float)(kTau / 100.0f);    // qpsk.c:302
+    cfg->ntaps = 127;                         // rrc_fir.h:13
+    cfg->frame_size = 512;                    // qpsk.h:23
+    cfg->mode = QPSK_B200_MODE_EXACT;
+    cfg->ub_mode = QPSK_B200_UB_ALIAS;
+}
+
+__global__ void save_pcm_tail_kernel(const int16_t* __restrict__ pcm, int16_t* __restrict__ tail, int C, size_t row) {
+    // last 128 samples of every channel row; 16 threads x 16 bytes per channel
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = t >> 4, q = t & 15;
+    if (c >= C) return;
+    const uint4* src = reinterpret_cast<const uint4*>(pcm + (size_t)c * row + row - QPSK_CHUNK) + q;
+    reinterpret_cast<uint4*>(tail + (size_t)c * QPSK_CHUNK)[q] = *src;
+}
+
+static int rx_free(qpsk_b200_rx* rx) {
+    if (!rx) return 0;
+    cudaSetDevice(rx->cfg.device);
+    void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->d_dec_ring, rx->d_index_t,
+                     rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
+                     rx->d_pcm_stage, rx->d_scratch };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (auto& e : rx->ev) if (e) cudaEventDestroy(e);
+    if (rx->stream) cudaStreamDestroy(rx->stream);
+    delete rx;
+    return 0;
+}
+
+extern "C" int qpsk_b200_rx_destroy(qpsk_b200_rx* rx) { return rx_free(rx); }
+
+template <int NTAPS, int SPS, int MODE>
+static cudaError_t launch_front(const RxFrontArgs& a, int grid, cudaStream_t s) {
+    const size_t smem = sizeof(RxFrontSmem<SPS>);
+    cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<NTAPS, SPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    rx_front_kernel<NTAPS, SPS, MODE><<<grid, 256, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, int max_frames, qpsk_b200_rx** out) {
+    if (!cfg || !out) return fail(QPSK_B200_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (nchan < 1 || max_frames < 1) return fail(QPSK_B200_ERR_ARG, "nchan and max_frames must be positive");
+    if (cfg->frame_size != 512) return fail(QPSK_B200_ERR_ARG, "frame_size %d unsupported (FRAME_SIZE is 512, qpsk.h:23)", cfg->frame_size);
+    if (cfg->ntaps != 127) return fail(QPSK_B200_ERR_ARG, "receiver supports ntaps 127 (rrc_fir.h:13); got %d (use qpsk_b200_fir_* for other lengths)", cfg->ntaps);
+    const int sps = (int)((double)cfg->fs / (double)cfg->rs);   // CYCLES, qpsk.h:21
+    if (sps != 4 && sps != 8) return fail(QPSK_B200_ERR_ARG, "samples/symbol %d unsupported (4 = 2400 baud, 8 = 1200 baud)", sps);
+    if (cfg->mode != QPSK_B200_MODE_EXACT && cfg->mode != QPSK_B200_MODE_FAST) return fail(QPSK_B200_ERR_ARG, "bad mode");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(QPSK_B200_ERR_CUDA, "CUDA device %d not present (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(QPSK_B200_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", cfg->device, prop.major, prop.minor);
+
+    qpsk_b200_rx* rx = new (std::nothrow) qpsk_b200_rx();
+    if (!rx) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+    memset(rx, 0, sizeof *rx);
+    rx->cfg = *cfg;
+    rx->C = nchan;
+    rx->Cpad = (nchan + QPSK_GROUP - 1) / QPSK_GROUP * QPSK_GROUP;
+    rx->maxF = max_frames;
+    rx->N = cfg->frame_size;
+    rx->sps = sps;
+    rx->nsym = rx->N / sps;
+    rx->nslots = max_frames + 1;
+    // design-time constants on the host, with the host libm, as the reference computes them
+    qpsk_host_rrc_make(rx->taps, cfg->ntaps, cfg->fs, cfg->rs, cfg->rrc_alpha);           // qpsk.c:308
+    float t2[2];
+    qpsk_host_cis(kTau * (double)cfg->center / (double)cfg->fs, 1, t2);                    // qpsk.c:342
+    rx->rect = make_float2(t2[0], t2[1]);
+    qpsk_host_cis(3.14159265358979323846 / 4.0, 0, t2);                                    // qpsk.c:75
+    rx->rot45 = make_float2(t2[0], t2[1]);
+    qpsk_host_loop_create(&rx->loop, cfg->loop_bw, -1.0f, 1.0f);                           // qpsk.c:302
+
+    const size_t Cp = rx->Cpad, F = max_frames, N = rx->N, S = rx->nsym;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
+    if (cudaStreamCreateWithFlags(&rx->stream, cudaStreamNonBlocking) != cudaSuccess) e = cudaGetLastError();
+    for (auto& ev : rx->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    alloc((void**)&rx->d_pcm_tail, Cp * QPSK_CHUNK * sizeof(int16_t));
+    alloc((void**)&rx->d_phasor, (QPSK_CHUNK + F * N) * sizeof(float2));
+    alloc((void**)&rx->d_ph_tail, QPSK_CHUNK * sizeof(float2));
+    alloc((void**)&rx->d_ph_state, sizeof(float2));
+    alloc((void**)&rx->d_dec_ring, (F + 1) * S * Cp * sizeof(float2));
+    alloc((void**)&rx->d_index_t, F * Cp * sizeof(int));
+    alloc((void**)&rx->d_loop_state, Cp * sizeof(float2));
+    alloc((void**)&rx->d_dibits_t, F * (S / 16) * Cp * sizeof(unsigned));
+    alloc((void**)&rx->d_track_t, F * Cp * sizeof(float2));
+    if (cfg->flags & QPSK_B200_KEEP_FIR) alloc((void**)&rx->d_fir_dbg, (size_t)nchan * F * N * sizeof(float2));
+    if (cfg->flags & QPSK_B200_KEEP_SYMBOLS) alloc((void**)&rx->d_costas_dbg, F * S * Cp * sizeof(float2));
+    if (e != cudaSuccess) {
+        rx_free(rx);
+        return fail(QPSK_B200_ERR_CUDA, "allocating receiver state failed: %s", cudaGetErrorString(e));
+    }
+    int rc = qpsk_b200_rx_reset(rx);
+    if (rc != 0) { rx_free(rx); return rc; }
+    *out = rx;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_rx_reset(qpsk_b200_rx* rx) {
+    if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
+    CU(cudaSetDevice(rx->cfg.device));
+    const size_t Cp = rx->Cpad, S = rx->nsym;
+    cudaStream_t s = rx->stream;
+    CU(cudaMemsetAsync(rx->d_pcm_tail, 0, Cp * QPSK_CHUNK * sizeof(int16_t), s));
+    CU(cudaMemsetAsync(rx->d_dec_ring, 0, (size_t)rx->nslots * S * Cp * sizeof(float2), s));
+    // the carried phasors only ever multiply zero PCM at stream start; keep them finite
+    float2 ones[QPSK_CHUNK];
+    for (auto& v : ones) v = make_float2(1.0f, 0.0f);
+    CU(cudaMemcpyAsync(rx->d_ph_tail, ones, sizeof ones, cudaMemcpyHostToDevice, s));
+    float c0[2];
+    qpsk_host_cis(0.0, 0, c0);                                                             // qpsk.c:341
+    const float2 ph0 = make_float2(c0[0], c0[1]);
+    CU(cudaMemcpyAsync(rx->d_ph_state, &ph0, sizeof ph0, cudaMemcpyHostToDevice, s));
+    // d_phase = d_freq = 0 (costas_loop.c:32-33)
+    CU(cudaMemsetAsync(rx->d_loop_state, 0, Cp * sizeof(float2), s));
+    CU(cudaStreamSynchronize(s));
+    rx->slot_base = 0;
+    rx->lastF = 0;
+    return QPSK_B200_OK;
+}
+
+static int upload_taps(const qpsk_b200_rx* rx, cudaStream_t s) {
+    float2 t2[QPSK_MAX_TAPS];
+    for (int i = 0; i < rx->cfg.ntaps; i++) t2[i] = make_float2(rx->taps[i], rx->taps[i]);
+    CU(cudaMemcpyToSymbolAsync(c_taps2, t2, sizeof(float2) * rx->cfg.ntaps, 0, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));   // t2 is on the stack
+    return 0;
+}
+
+static const qpsk_b200_rx* g_taps_owner = nullptr;
+
+extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pcm, int nframes, void* cuda_stream) {
+    if (!rx || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nframes < 1 || nframes > rx->maxF) return fail(QPSK_B200_ERR_ARG, "nframes %d outside 1..%d", nframes, rx->maxF);
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15) != 0) return fail(QPSK_B200_ERR_ARG, "d_pcm must be 16-byte aligned");
+    CU(cudaSetDevice(rx->cfg.device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rx->stream;
+    if (g_taps_owner != rx) {
+        int rc = upload_taps(rx, s);
+        if (rc) return rc;
+        g_taps_owner = rx;
+    }
+    const int F = nframes, N = rx->N;
+
+    // K0: mixer phasors of this call
+    phasor_table_kernel<<<1, QPSK_CHUNK, 0, s>>>(rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->rect, F, N);
+    CU(cudaGetLastError());
+
+    // K1: mixer + matched filter + timing + decimation
+    RxFrontArgs fa;
+    fa.pcm = d_pcm; fa.pcm_tail = rx->d_pcm_tail; fa.phasor = rx->d_phasor;
+    fa.dec_ring = rx->d_dec_ring; fa.index_t = rx->d_index_t; fa.fir_dbg = rx->d_fir_dbg;
+    fa.C = rx->C; fa.Cpad = rx->Cpad; fa.F = F; fa.N = N;
+    fa.slot_base = rx->slot_base; fa.nslots = rx->nslots; fa.ub_mode = rx->cfg.ub_mode;
+    const int ngroups = rx->Cpad / QPSK_GROUP;
+    // enough CTAs for a few waves over the SMs: split the frames of a channel group when channels are few
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, rx->cfg.device);
+    int fblocks = 1;
+    while (ngroups * fblocks < 4 * nsm && fblocks < F) fblocks *= 2;
+    fa.frames_per_block = (F + fblocks - 1) / fblocks;
+    fblocks = (F + fa.frames_per_block - 1) / fa.frames_per_block;
+    const int grid = ngroups * fblocks;
+    CU(cudaEventRecord(rx->ev[0], s));
+    cudaError_t e;
+    const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
+    if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, grid, s) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, grid, s);
+    else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, grid, s) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, grid, s);
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(rx->ev[1], s));
+
+    // carry the last 128 PCM samples of every channel (the next call's filter history)
+    save_pcm_tail_kernel<<<(rx->C * 16 + 255) / 256, 256, 0, s>>>(d_pcm, rx->d_pcm_tail, rx->C, (size_t)F * N);
+    CU(cudaGetLastError());
+
+    // K3: Costas loop + slicer
+    CostasArgs ca;
+    ca.dec_ring = rx->d_dec_ring; ca.index_t = rx->d_index_t; ca.loop_state = rx->d_loop_state;
+    ca.dibits_t = rx->d_dibits_t; ca.costas_dbg = rx->d_costas_dbg; ca.track_t = rx->d_track_t;
+    ca.C = rx->C; ca.Cpad = rx->Cpad; ca.F = F; ca.nsym = rx->nsym; ca.sps = rx->sps; ca.N = N;
+    ca.slot_base = rx->slot_base; ca.nslots = rx->nslots; ca.ub_mode = rx->cfg.ub_mode;
+    ca.alpha = rx->loop.alpha; ca.beta = rx->loop.beta; ca.max_freq = rx->loop.max_freq; ca.min_freq = rx->loop.min_freq;
+    ca.rot45 = rx->rot45;
+    CU(cudaEventRecord(rx->ev[2], s));
+    costas_kernel<<<(rx->C + 127) / 128, 128, 0, s>>>(ca);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(rx->ev[3], s));
+
+    rx->launches += 4;
+    rx->timed = true;
+    rx->slot_base = (rx->slot_base + F) % rx->nslots;
+    rx->lastF = F;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_rx_sync(qpsk_b200_rx* rx) {
+    if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
+    CU(cudaSetDevice(rx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    return QPSK_B200_OK;
+}
+
+extern "C" long long qpsk_b200_rx_launch_count(const qpsk_b200_rx* rx) { return rx ? rx->launches : 0; }
+
+extern "C" int qpsk_b200_rx_last_kernel_ms(qpsk_b200_rx* rx, float* front_ms, float* costas_ms) {
+    if (!rx || !rx->timed) return fail(QPSK_B200_ERR_STATE, "no process call yet");
+    CU(cudaEventSynchronize(rx->ev[3]));
+    if (front_ms) CU(cudaEventElapsedTime(front_ms, rx->ev[0], rx->ev[1]));
+    if (costas_ms) CU(cudaEventElapsedTime(costas_ms, rx->ev[2], rx->ev[3]));
+    return QPSK_B200_OK;
+}
+
+extern "C" size_t qpsk_b200_rx_output_bytes(const qpsk_b200_rx* rx, int what) {
+    if (!rx) return 0;
+    const size_t C = rx->C, F = rx->lastF, S = rx->nsym, N = rx->N;
+    switch (what) {
+        case QPSK_B200_OUT_DIBITS: return C * F * (S / 4);
+        case QPSK_B200_OUT_INDEX: return C * F * sizeof(int);
+        case QPSK_B200_OUT_TRACK: return C * F * sizeof(float2);
+        case QPSK_B200_OUT_DEC: return C * F * S * sizeof(float2);
+        case QPSK_B200_OUT_SYMBOLS: return C * F * S * sizeof(float2);
+        case QPSK_B200_OUT_FIR: return C * F * N * sizeof(float2);
+        case QPSK_B200_OUT_TAPS: return (size_t)rx->cfg.ntaps * sizeof(float);
+        default: return 0;
+    }
+}
+
+static int ensure_scratch(qpsk_b200_rx* rx, size_t bytes) {
+    if (rx->scratch_bytes >= bytes) return 0;
+    if (rx->d_scratch) { cudaFree(rx->d_scratch); rx->d_scratch = nullptr; rx->scratch_bytes = 0; }
+    CU(cudaMalloc(&rx->d_scratch, bytes));
+    rx->scratch_bytes = bytes;
+    return 0;
+}
+
+template <typename T>
+static int download_transposed(qpsk_b200_rx* rx, const T* d_src, int rows, void* h_dst, cudaStream_t s) {
+    const size_t bytes = (size_t)rx->C * rows * sizeof(T);
+    int rc = ensure_scratch(rx, bytes);
+    if (rc) return rc;
+    dim3 grid((rx->C + 31) / 32, (rows + 31) / 32), block(32, 8);
+    transpose_to_channel_major<T><<<grid, block, 0, s>>>(d_src, (T*)rx->d_scratch, rows, rx->C, rx->Cpad);
+    CU(cudaGetLastError());
+    rx->launches += 1;
+    CU(cudaMemcpyAsync(h_dst, rx->d_scratch, bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return 0;
+}
+
+extern "C" int qpsk_b200_rx_read(qpsk_b200_rx* rx, int what, void* h_dst, size_t bytes) {
+    if (!rx || !h_dst) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (what != QPSK_B200_OUT_TAPS && rx->lastF == 0) return fail(QPSK_B200_ERR_STATE, "no process call yet");
+    const size_t need = qpsk_b200_rx_output_bytes(rx, what);
+    if (need == 0 || bytes != need) return fail(QPSK_B200_ERR_ARG, "output %d needs %zu bytes, got %zu", what, need, bytes);
+    CU(cudaSetDevice(rx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    cudaStream_t s = rx->stream;
+    const int F = rx->lastF, S = rx->nsym;
+    switch (what) {
+        case QPSK_B200_OUT_TAPS: memcpy(h_dst, rx->taps, need); return 0;
+        case QPSK_B200_OUT_DIBITS: return download_transposed<unsigned>(rx, rx->d_dibits_t, F * (S / 16), h_dst, s);
+        case QPSK_B200_OUT_INDEX: return download_transposed<int>(rx, rx->d_index_t, F, h_dst, s);
+        case QPSK_B200_OUT_TRACK: return download_transposed<float2>(rx, rx->d_track_t, F, h_dst, s);
+        case QPSK_B200_OUT_SYMBOLS:
+            if (!rx->d_costas_dbg) return fail(QPSK_B200_ERR_STATE, "symbols were not kept (QPSK_B200_KEEP_SYMBOLS)");
+            return download_transposed<float2>(rx, rx->d_costas_dbg, F * S, h_dst, s);
+        case QPSK_B200_OUT_FIR:
+            if (!rx->d_fir_dbg) return fail(QPSK_B200_ERR_STATE, "filter output was not kept (QPSK_B200_KEEP_FIR)");
+            CU(cudaMemcpy(h_dst, rx->d_fir_dbg, need, cudaMemcpyDeviceToHost));
+            return 0;
+        case QPSK_B200_OUT_DEC: {
+            // frames of the last call live in ring slots (slot_base_before + 1 + f); slot_base already advanced by F
+            const int base_before = ((rx->slot_base - F) % rx->nslots + rx->nslots) % rx->nslots;
+            int rc = ensure_scratch(rx, need + (size_t)F * S * rx->Cpad * sizeof(float2));
+            if (rc) return rc;
+            float2* lin = reinterpret_cast<float2*>(static_cast<char*>(rx->d_scratch) + need);
+            for (int f = 0; f < F; f++) {
+                const int slot = (base_before + 1 + f) % rx->nslots;
+                CU(cudaMemcpyAsync(lin + (size_t)f * S * rx->Cpad, rx->d_dec_ring + (size_t)slot * S * rx->Cpad,
+                                   (size_t)S * rx->Cpad * sizeof(float2), cudaMemcpyDeviceToDevice, s));
+            }
+            dim3 grid((rx->C + 31) / 32, (F * S + 31) / 32), block(32, 8);
+            transpose_to_channel_major<float2><<<grid, block, 0, s>>>(lin, (float2*)rx->d_scratch, F * S, rx->C, rx->Cpad);
+            CU(cudaGetLastError());
+            rx->launches += 1;
+            CU(cudaMemcpyAsync(h_dst, rx->d_scratch, need, cudaMemcpyDeviceToHost, s));
+            CU(cudaStreamSynchronize(s));
+            return 0;
+        }
+        default: return fail(QPSK_B200_ERR_ARG, "unknown output %d", what);
+    }
+}
+
+extern "C" int qpsk_b200_rx_device_dibits(qpsk_b200_rx* rx, const uint32_t** d_ptr, int* cpad) {
+    if (!rx || !d_ptr) return fail(QPSK_B200_ERR_ARG, "null argument");
+    *d_ptr = rx->d_dibits_t;
+    if (cpad) *cpad = rx->Cpad;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_rx_process_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, uint8_t* h_dibits) {
+    if (!rx || !h_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nframes < 1 || nframes > rx->maxF) return fail(QPSK_B200_ERR_ARG, "nframes %d outside 1..%d", nframes, rx->maxF);
+    CU(cudaSetDevice(rx->cfg.device));
+    const size_t bytes = (size_t)rx->C * nframes * rx->N * sizeof(int16_t);
+    if (!rx->d_pcm_stage) CU(cudaMalloc((void**)&rx->d_pcm_stage, (size_t)rx->C * rx->maxF * rx->N * sizeof(int16_t)));
+    CU(cudaMemcpyAsync(rx->d_pcm_stage, h_pcm, bytes, cudaMemcpyHostToDevice, rx->stream));
+    int rc = qpsk_b200_rx_process_device(rx, rx->d_pcm_stage, nframes, rx->stream);
+    if (rc) return rc;
+    if (h_dibits) {
+        rc = download_transposed<unsigned>(rx, rx->d_dibits_t, nframes * (rx->nsym / 16), h_dibits, rx->stream);
+        if (rc) return rc;
+    } else {
+        CU(cudaStreamSynchronize(rx->stream));
+    }
+    return QPSK_B200_OK;
+}

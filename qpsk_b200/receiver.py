@@ -1,0 +1,109 @@
+"""Host-side mirror of the reference receive path over many channels.
+
+`Receiver.rx_frames(pcm)` is rx_frame() of the reference (qpsk.c:88-218) applied to every row of
+`pcm` frame after frame, with the per-channel globals of qpsk.c:36-53 / costas_loop.c:13-23 held
+in HBM between calls.  All compute happens in libqpsk_b200.so on a B200.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+
+class Receiver:
+    def __init__(self, nchan, max_frames, rs=2400.0, mode=capi.MODE_EXACT, ub_mode=capi.UB_ALIAS,
+                 keep_fir=False, keep_symbols=False, device=0, loop_bw=None, center=1500.0):
+        self.L = capi.lib()
+        cfg = capi.RxConfig()
+        self.L.qpsk_b200_rx_default_config(C.byref(cfg))
+        cfg.rs = rs
+        cfg.center = center
+        cfg.mode = mode
+        cfg.ub_mode = ub_mode
+        cfg.flags = (capi.KEEP_FIR if keep_fir else 0) | (capi.KEEP_SYMBOLS if keep_symbols else 0)
+        cfg.device = device
+        if loop_bw is not None:
+            cfg.loop_bw = loop_bw
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        capi.check(self.L.qpsk_b200_rx_create(C.byref(cfg), nchan, max_frames, C.byref(self.h)))
+        self.nchan, self.max_frames = nchan, max_frames
+        self.frame_size = cfg.frame_size
+        self.sps = int(cfg.fs / cfg.rs)
+        self.nsym = self.frame_size // self.sps
+        self.last_frames = 0
+
+    def close(self):
+        if self.h:
+            self.L.qpsk_b200_rx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        capi.check(self.L.qpsk_b200_rx_reset(self.h))
+
+    # -- device-resident path ---------------------------------------------------------------
+    def process_device(self, d_pcm_ptr, nframes, stream=None):
+        """d_pcm_ptr: device address of int16 [C][nframes*frame_size]; asynchronous."""
+        capi.check(self.L.qpsk_b200_rx_process_device(self.h, C.c_void_p(d_pcm_ptr), nframes,
+                                                      C.c_void_p(stream) if stream else None))
+        self.last_frames = nframes
+
+    def sync(self):
+        capi.check(self.L.qpsk_b200_rx_sync(self.h))
+
+    # -- host path (what a user of the reference calls) ---------------------------------------
+    def rx_frames(self, pcm, want_dibits=True):
+        """pcm: int16 ndarray [C, F*frame_size] in host memory.  Returns packed dibits uint8 [C, F*nsym/4]."""
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        assert pcm.ndim == 2 and pcm.shape[0] == self.nchan and pcm.shape[1] % self.frame_size == 0
+        F = pcm.shape[1] // self.frame_size
+        out = np.empty((self.nchan, F * self.nsym // 4), np.uint8) if want_dibits else None
+        capi.check(self.L.qpsk_b200_rx_process_host(self.h, pcm.ctypes.data_as(C.c_void_p), F,
+                                                    out.ctypes.data_as(C.c_void_p) if want_dibits else None))
+        self.last_frames = F
+        return out
+
+    def read(self, what):
+        F, Cn, S, N = self.last_frames, self.nchan, self.nsym, self.frame_size
+        shapes = {
+            capi.OUT_DIBITS: ((Cn, F * S // 4), np.uint8),
+            capi.OUT_INDEX: ((Cn, F), np.int32),
+            capi.OUT_TRACK: ((Cn, F, 2), np.float32),
+            capi.OUT_DEC: ((Cn, F * S), np.complex64),
+            capi.OUT_SYMBOLS: ((Cn, F * S), np.complex64),
+            capi.OUT_FIR: ((Cn, F * N), np.complex64),
+            capi.OUT_TAPS: ((self.cfg.ntaps,), np.float32),
+        }
+        shape, dt = shapes[what]
+        out = np.empty(shape, dt)
+        capi.check(self.L.qpsk_b200_rx_read(self.h, what, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def dibits(self):
+        """Unpacked dibits uint8 [C, F*nsym] (bits[0] | bits[1] << 1 of qpsk_demod, qpsk.c:74-79)."""
+        p = self.read(capi.OUT_DIBITS)
+        return unpack_dibits(p)
+
+    def kernel_ms(self):
+        a, b = C.c_float(), C.c_float()
+        capi.check(self.L.qpsk_b200_rx_last_kernel_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self):
+        return int(self.L.qpsk_b200_rx_launch_count(self.h))
+
+
+def unpack_dibits(packed):
+    """uint8 [..., n] with 4 dibits per byte (symbol i at bits 2*(i%4)) -> uint8 [..., 4n]."""
+    p = np.asarray(packed, np.uint8)
+    out = np.empty(p.shape + (4,), np.uint8)
+    for k in range(4):
+        out[..., k] = (p >> (2 * k)) & 3
+    return out.reshape(p.shape[:-1] + (p.shape[-1] * 4,))
