@@ -262,8 +262,8 @@ class Ref:
 class RefAlg:
     """algorithms/{fft,crc16,interleave,bit-scramble}.c of the unmodified reference."""
 
-    def __init__(self):
-        path = os.path.join(HERE, "_ref", "libref_alg.so")
+    def __init__(self, flavour="alg"):
+        path = os.path.join(HERE, "_ref", "libref_%s.so" % flavour)
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.L = C.CDLL(path)

@@ -462,8 +462,14 @@ static inline float sc_cos_poly(double x2, int negate) {
     const double c = fma(x4, sg * SC_C2, c1);
     return (float)fma(x6, c2, c);
 }
+static inline int sc_tiny(float y) {          /* abstop12(y) < abstop12(0x1p-12f): sinf returns y, cosf returns 1 */
+    uint32_t u;
+    memcpy(&u, &y, sizeof u);
+    return ((u >> 20) & 0x7ff) < 0x398;
+}
 float orc_glibc_sinf(float y) {
     int n;
+    if (sc_tiny(y)) return y;
     const double x = sc_reduce((double)y, &n);
     const double x2 = x * x;
     if ((n & 1) == 0) return sc_sin_poly(((n & 3) == 1 || (n & 3) == 2) ? -x : x, x2);
@@ -471,8 +477,25 @@ float orc_glibc_sinf(float y) {
 }
 float orc_glibc_cosf(float y) {
     int n;
+    if (sc_tiny(y)) return 1.0f;
     const double x = sc_reduce((double)y, &n);
     const double x2 = x * x;
     if (n & 1) return sc_sin_poly(((n & 3) == 1 || (n & 3) == 2) ? -x : x, x2);
     return sc_cos_poly(x2, (n & 2) != 0);
+}
+
+/* mismatch count of the restated sinf/cosf against the host libm over the float bit patterns
+ * lo..hi (both signs), every `stride`-th one */
+long orc_glibc_check(uint32_t lo, uint32_t hi, uint32_t stride) {
+    long bad = 0;
+    for (uint64_t b = lo; b <= hi; b += stride) {
+        for (uint32_t sign = 0; sign < 2; sign++) {
+            uint32_t u = (uint32_t)b | (sign << 31);
+            float y;
+            memcpy(&y, &u, sizeof y);
+            float s0 = sinf(y), c0 = cosf(y), s1 = orc_glibc_sinf(y), c1 = orc_glibc_cosf(y);
+            if (memcmp(&s0, &s1, 4) != 0 || memcmp(&c0, &c1, 4) != 0) bad++;
+        }
+    }
+    return bad;
 }

@@ -125,6 +125,7 @@ uint16_t orc_crc16(const uint8_t *data, int length);
 /* ---- glibc 2.39 sinf/cosf (x86-64 FMA ifunc variant), restated: the device NCO follows this */
 float orc_glibc_sinf(float y);
 float orc_glibc_cosf(float y);
+long  orc_glibc_check(uint32_t lo_bits, uint32_t hi_bits, uint32_t stride);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,8 @@ __device__ __forceinline__ void sincosf_glibc(float y, float& s_out, float& c_ou
     // sinf: even n -> sine poly, odd n -> cosine poly; cosf the other way round
     s_out = (n & 1) ? cv : sv;
     c_out = (n & 1) ? sv : cv;
+    // |y| < 2^-12 (abstop12 test of s_sinf.c / s_cosf.c): sinf returns y itself (keeps -0), cosf returns 1
+    if (((__float_as_uint(y) >> 20) & 0x7ffu) < 0x398u) { s_out = y; c_out = 1.0f; }
 }
 
 #define QPSK_CHUNK 128          // samples per time tile of the front-end kernel

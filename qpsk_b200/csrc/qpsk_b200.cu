@@ -41,9 +41,14 @@ extern "C" int qpsk_b200_device_count(void) {
 
 static const double kTau = 2.0 * 3.14159265358979323846;
 
+// constant-bank taps belong to the context that uploaded them last; ids are never reused
+static long long g_taps_owner = -1;
+static long long g_next_id = 0;
+
 // ---------------------------------------------------------------------------------------------
 struct qpsk_b200_rx {
     qpsk_b200_rx_config cfg;
+    long long id;
     int C, Cpad, maxF, N, sps, nsym, nslots, slot_base, lastF;
     float taps[QPSK_MAX_TAPS];
     float2 rect, rot45;
@@ -136,6 +141,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (!rx) return fail(QPSK_B200_ERR_ARG, "out of host memory");
     memset(rx, 0, sizeof *rx);
     rx->cfg = *cfg;
+    rx->id = g_next_id++;
     rx->C = nchan;
     rx->Cpad = (nchan + QPSK_GROUP - 1) / QPSK_GROUP * QPSK_GROUP;
     rx->maxF = max_frames;
@@ -209,7 +215,6 @@ static int upload_taps(const qpsk_b200_rx* rx, cudaStream_t s) {
     return 0;
 }
 
-static const qpsk_b200_rx* g_taps_owner = nullptr;
 
 extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pcm, int nframes, void* cuda_stream) {
     if (!rx || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
@@ -217,10 +222,10 @@ extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pc
     if ((reinterpret_cast<uintptr_t>(d_pcm) & 15) != 0) return fail(QPSK_B200_ERR_ARG, "d_pcm must be 16-byte aligned");
     CU(cudaSetDevice(rx->cfg.device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rx->stream;
-    if (g_taps_owner != rx) {
+    if (g_taps_owner != rx->id) {
         int rc = upload_taps(rx, s);
         if (rc) return rc;
-        g_taps_owner = rx;
+        g_taps_owner = rx->id;
     }
     const int F = nframes, N = rx->N;
 

@@ -1,0 +1,167 @@
+"""Parity of the CUDA receive path (through the C-ABI, libqpsk_b200.so) against the CPU oracle
+and the committed reference golden vectors.  Bit-exact in exact mode: matched-filter output,
+timing index, decimated symbols, Costas symbols, phase/frequency tracks and decided dibits."""
+import numpy as np
+import pytest
+
+from conftest import bits_equal
+from synth import make_pcm
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(pcm, rs, **kw):
+    import qpsk_b200
+    from qpsk_b200 import capi
+    C, n = pcm.shape
+    F = n // 512
+    rx = qpsk_b200.Receiver(C, kw.pop("max_frames", F), rs=rs, keep_fir=True, keep_symbols=True, **kw)
+    packed = rx.rx_frames(pcm)
+    out = {"fir": rx.read(capi.OUT_FIR), "index": rx.read(capi.OUT_INDEX), "dec": rx.read(capi.OUT_DEC),
+           "costas": rx.read(capi.OUT_SYMBOLS), "dibit": qpsk_b200.unpack_dibits(packed),
+           "track": rx.read(capi.OUT_TRACK), "taps": rx.read(capi.OUT_TAPS), "packed": packed}
+    out["phase"], out["freq"] = np.ascontiguousarray(out["track"][..., 0]), np.ascontiguousarray(out["track"][..., 1])
+    return rx, out
+
+
+def assert_all_stages(got, want, keys=("fir", "index", "dec", "costas", "dibit", "phase", "freq")):
+    for k in keys:
+        assert bits_equal(got[k], want[k]), "%s differs in %d of %d elements" % (k, int(np.sum(got[k] != want[k])), want[k].size)
+
+
+@pytest.mark.parametrize("name,rs", [("rx_2400", 2400.0), ("rx_1200", 1200.0)])
+def test_reference_golden_vectors(golden, name, rs):
+    g = golden[name]
+    rx, out = run_gpu(g["pcm"], rs)
+    assert bits_equal(out["taps"], g["taps"])
+    assert_all_stages(out, g, keys=("fir", "dec", "costas", "dibit", "phase", "freq"))
+    rx.close()
+
+
+@pytest.mark.parametrize("rs,nchan,nframes,esn0", [
+    (2400.0, 1, 5, None),        # the reference's own shape: one channel (config 0)
+    (2400.0, 31, 7, 20.0),       # ragged: fewer channels than one CTA group
+    (2400.0, 33, 6, 20.0),       # ragged: one channel into the second group
+    (2400.0, 200, 16, 20.0),     # high SNR, 2400 baud with the aliasing read
+    (1200.0, 64, 24, 20.0),      # config 1 profile (10 m, 1200 baud) scaled down
+    (1200.0, 100, 3, 6.0),       # low SNR
+    (2400.0, 96, 1, 12.0),       # a single frame
+])
+def test_all_stages_bit_exact_vs_oracle(oracle_lib, rs, nchan, nframes, esn0):
+    o = oracle_lib.Oracle(rs=rs)
+    pcm, _ = make_pcm(nchan, nframes, rs=rs, seed=nchan * 7 + nframes, esn0_db=esn0, oracle=o)
+    want = o.rx_run(pcm)
+    rx, got = run_gpu(pcm, rs)
+    assert_all_stages(got, want)
+    rx.close()
+
+
+def test_streaming_calls_carry_state(oracle_lib):
+    """A stream fed in several calls (ragged frame counts) equals one call: filter history, mixer
+    phasor, decimation delay and loop state all carry over."""
+    import qpsk_b200
+    o = oracle_lib.Oracle()
+    pcm, _ = make_pcm(40, 20, seed=5, esn0_db=15.0, oracle=o)
+    want = o.rx_run(pcm)["dibit"]
+    rx = qpsk_b200.Receiver(40, 8)
+    parts, f = [], 0
+    for nf in (3, 8, 1, 8):
+        parts.append(qpsk_b200.unpack_dibits(rx.rx_frames(pcm[:, f * 512:(f + nf) * 512])))
+        f += nf
+    assert np.array_equal(np.concatenate(parts, axis=1), want)
+    rx.reset()                                 # reset = stream start
+    again = qpsk_b200.unpack_dibits(rx.rx_frames(pcm[:, :8 * 512]))
+    assert np.array_equal(again, want[:, :8 * 128])
+    rx.close()
+
+
+def test_frame_split_grid_equals_unsplit(oracle_lib):
+    """Few channels x many frames: the front-end kernel splits the frames of a channel group over
+    several CTAs (halo recomputed from the PCM); results must not depend on the split."""
+    o = oracle_lib.Oracle(rs=1200.0)
+    pcm, _ = make_pcm(8, 96, rs=1200.0, seed=21, esn0_db=20.0, oracle=o)
+    want = o.rx_run(pcm)
+    rx, got = run_gpu(pcm, 1200.0)
+    assert_all_stages(got, want)
+    rx.close()
+
+
+def test_clamp_mode_matches_oracle_clamp(oracle_lib):
+    from qpsk_b200 import capi
+    o = oracle_lib.Oracle(ub_mode=1)
+    pcm, _ = make_pcm(16, 10, seed=31, esn0_db=20.0, oracle=o)
+    want = o.rx_run(pcm)
+    rx, got = run_gpu(pcm, 2400.0, ub_mode=capi.UB_CLAMP)
+    assert_all_stages(got, want)
+    rx.close()
+
+
+def test_silence_and_full_scale(oracle_lib):
+    o = oracle_lib.Oracle()
+    pcm = np.zeros((3, 4 * 512), np.int16)
+    pcm[1] = 32767
+    pcm[2] = -32768
+    pcm[2, ::2] = 32767
+    want = o.rx_run(pcm)
+    rx, got = run_gpu(pcm, 2400.0)
+    assert_all_stages(got, want)
+    rx.close()
+
+
+def test_fast_mode_is_close_but_not_required_exact(oracle_lib):
+    """Fused-multiply-add FIR: matched-filter output within 1e-5 of the reference (max-norm relative)."""
+    from qpsk_b200 import capi
+    o = oracle_lib.Oracle()
+    pcm, _ = make_pcm(32, 6, seed=41, esn0_db=20.0, oracle=o)
+    want = o.rx_run(pcm)
+    rx, got = run_gpu(pcm, 2400.0, mode=capi.MODE_FAST)
+    err = np.max(np.abs(got["fir"] - want["fir"]), axis=1) / np.max(np.abs(want["fir"]), axis=1)
+    assert err.max() <= 1e-5        # north_star tolerance for the FIR in FP32
+    rx.close()
+
+
+def test_nco_matches_host_libm():
+    """The device NCO (glibc sinf/cosf restated in FP64) against the host libm the reference links:
+    drive the loop with constant symbols so the phase sweeps [-TAU, TAU] and compare the derotated
+    symbols with numpy float32 arithmetic around libm's sinf/cosf."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.sinf.restype = libm.cosf.restype = ctypes.c_float
+    libm.sinf.argtypes = libm.cosf.argtypes = [ctypes.c_float]
+    pcm = np.zeros((1, 30 * 512), np.int16)
+    pcm[0] = (8000 * np.cos(2 * np.pi * 1537.0 / 9600.0 * np.arange(pcm.shape[1]))).astype(np.int16)
+    rx, got = run_gpu(pcm, 2400.0)
+    dec, sym, track = got["dec"][0], got["costas"][0], got["track"][0]
+    # frame f's loop consumes frame f-1's symbols starting from the phase left by frame f-1
+    checked = 0
+    for f in range(2, 30):
+        ph = np.float32(track[f - 1, 0])
+        d = dec[(f - 1) * 128]
+        c, s = np.float32(libm.cosf(float(ph))), np.float32(libm.sinf(float(ph)))
+        re = np.float32(np.float32(d.real * c) - np.float32(d.imag * -s))
+        im = np.float32(np.float32(d.real * -s) + np.float32(d.imag * c))
+        assert sym[f * 128] == np.complex64(complex(re, im))
+        checked += 1
+    assert checked == 28
+    rx.close()
+
+
+def test_bad_arguments_fail_loudly():
+    import ctypes as C
+    from qpsk_b200 import capi
+    L = capi.lib()
+    cfg = capi.RxConfig()
+    L.qpsk_b200_rx_default_config(C.byref(cfg))
+    h = C.c_void_p()
+    cfg.ntaps = 63
+    assert L.qpsk_b200_rx_create(C.byref(cfg), 4, 4, C.byref(h)) == -1 and b"ntaps" in L.qpsk_b200_last_error()
+    cfg.ntaps, cfg.rs = 127, 4800.0
+    assert L.qpsk_b200_rx_create(C.byref(cfg), 4, 4, C.byref(h)) == -1
+    cfg.rs, cfg.device = 2400.0, 99
+    assert L.qpsk_b200_rx_create(C.byref(cfg), 4, 4, C.byref(h)) == -2
+    cfg.device = 0
+    assert L.qpsk_b200_rx_create(C.byref(cfg), 4, 4, C.byref(h)) == 0
+    assert L.qpsk_b200_rx_process_device(h, None, 1, None) == -1
+    buf = np.zeros(16, np.uint8)
+    assert L.qpsk_b200_rx_read(h, capi.OUT_DIBITS, buf.ctypes.data_as(C.c_void_p), 16) == -3   # nothing processed yet
+    L.qpsk_b200_rx_destroy(h)
