@@ -110,6 +110,27 @@ long long qpsk_b200_rx_launch_count(const qpsk_b200_rx *rx);
 /* device milliseconds of the front-end kernel in the most recent call (CUDA events on its stream) */
 int qpsk_b200_rx_last_kernel_ms(qpsk_b200_rx *rx, float *front_ms, float *costas_ms);
 
+/* ------------------------------------------------------------------------------------------
+ * Channel-batched rrc_fir()/rrc_make()  (rrc_fir.h:16-17, rrc_fir.c:17-76)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct qpsk_b200_fir qpsk_b200_fir;
+
+/* rrc_make(fs, rs, alpha) for any NTAPS: taps[ntaps] on the host, bit-identical to the reference */
+int qpsk_b200_rrc_make(float *taps, int ntaps, float fs, float rs, float alpha);
+/* ntaps in {127, 256}; taps[ntaps] as produced by qpsk_b200_rrc_make (any real taps work) */
+int qpsk_b200_fir_create(const float *taps, int ntaps, int nchan, int mode, int device, qpsk_b200_fir **out);
+int qpsk_b200_fir_destroy(qpsk_b200_fir *f);
+/* zero every channel's delay line (the reference's `memory[]` starts as zero-initialised globals) */
+int qpsk_b200_fir_reset(qpsk_b200_fir *f);
+/* rrc_fir(memory, sample, length) for every channel: d_samples is complex float [C][nsamples]
+ * (re,im interleaved) in HBM, filtered in place; the delay lines persist between calls */
+int qpsk_b200_fir_process_device(qpsk_b200_fir *f, float *d_samples, int nsamples, void *cuda_stream);
+int qpsk_b200_fir_process_host(qpsk_b200_fir *f, float *h_samples, int nsamples);
+/* read / write the delay lines, complex float [C][ntaps], oldest input first (== rrc_fir's memory[]) */
+int qpsk_b200_fir_get_memory(qpsk_b200_fir *f, float *h_memory);
+int qpsk_b200_fir_set_memory(qpsk_b200_fir *f, const float *h_memory);
+int qpsk_b200_fir_last_kernel_ms(qpsk_b200_fir *f, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

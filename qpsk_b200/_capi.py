@@ -52,6 +52,7 @@ def lib():
     L.qpsk_b200_rx_launch_count.argtypes = [C.c_void_p]
     L.qpsk_b200_rx_launch_count.restype = C.c_longlong
     L.qpsk_b200_rx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    _bind_fir(L)
     _lib = L
     return L
 
@@ -59,3 +60,15 @@ def lib():
 def check(rc):
     if rc != 0:
         raise QpskB200Error("qpsk_b200 error %d: %s" % (rc, lib().qpsk_b200_last_error().decode()))
+
+
+def _bind_fir(L):
+    L.qpsk_b200_rrc_make.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
+    L.qpsk_b200_fir_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.qpsk_b200_fir_destroy.argtypes = [C.c_void_p]
+    L.qpsk_b200_fir_reset.argtypes = [C.c_void_p]
+    L.qpsk_b200_fir_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.qpsk_b200_fir_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.qpsk_b200_fir_get_memory.argtypes = [C.c_void_p, C.c_void_p]
+    L.qpsk_b200_fir_set_memory.argtypes = [C.c_void_p, C.c_void_p]
+    L.qpsk_b200_fir_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]

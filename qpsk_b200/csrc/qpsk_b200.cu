@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "rx_front.cuh"
 #include "rx_costas.cuh"
+#include "fir.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -400,5 +401,154 @@ extern "C" int qpsk_b200_rx_process_host(qpsk_b200_rx* rx, const int16_t* h_pcm,
     } else {
         CU(cudaStreamSynchronize(rx->stream));
     }
+    return QPSK_B200_OK;
+}
+
+// =============================================================================================
+// channel-batched rrc_fir
+// =============================================================================================
+struct qpsk_b200_fir {
+    long long id;
+    int ntaps, C, mode, device;
+    float taps[QPSK_MAX_TAPS];
+    float2* d_state;      // [C][ntaps]
+    float2* d_stage;      // host-path staging (lazy)
+    size_t stage_elems;
+    cudaStream_t stream;
+    cudaEvent_t ev[2];
+    bool timed;
+};
+
+extern "C" int qpsk_b200_rrc_make(float* taps, int ntaps, float fs, float rs, float alpha) {
+    if (!taps || ntaps < 1 || ntaps > QPSK_MAX_TAPS) return fail(QPSK_B200_ERR_ARG, "ntaps must be 1..%d", QPSK_MAX_TAPS);
+    qpsk_host_rrc_make(taps, ntaps, fs, rs, alpha);
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fir_destroy(qpsk_b200_fir* f) {
+    if (!f) return 0;
+    cudaSetDevice(f->device);
+    if (f->d_state) cudaFree(f->d_state);
+    if (f->d_stage) cudaFree(f->d_stage);
+    for (auto& e : f->ev) if (e) cudaEventDestroy(e);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+    return 0;
+}
+
+static int check_device(int device) {
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(QPSK_B200_ERR_CUDA, "CUDA device %d not present (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(QPSK_B200_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    return 0;
+}
+
+extern "C" int qpsk_b200_fir_create(const float* taps, int ntaps, int nchan, int mode, int device, qpsk_b200_fir** out) {
+    if (!taps || !out) return fail(QPSK_B200_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (ntaps != 127 && ntaps != 256) return fail(QPSK_B200_ERR_ARG, "ntaps %d unsupported: kernels are instantiated for 127 (rrc_fir.h:13) and 256 (long-tap profile)", ntaps);
+    if (nchan < 1) return fail(QPSK_B200_ERR_ARG, "nchan must be positive");
+    if (mode != QPSK_B200_MODE_EXACT && mode != QPSK_B200_MODE_FAST) return fail(QPSK_B200_ERR_ARG, "bad mode");
+    int rc = check_device(device);
+    if (rc) return rc;
+    qpsk_b200_fir* f = new (std::nothrow) qpsk_b200_fir();
+    if (!f) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+    memset(f, 0, sizeof *f);
+    f->id = g_next_id++;
+    f->ntaps = ntaps; f->C = nchan; f->mode = mode; f->device = device;
+    memcpy(f->taps, taps, sizeof(float) * ntaps);
+    cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    for (auto& ev : f->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_state, (size_t)nchan * ntaps * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemset(f->d_state, 0, (size_t)nchan * ntaps * sizeof(float2));
+    if (e != cudaSuccess) { qpsk_b200_fir_destroy(f); return fail(QPSK_B200_ERR_CUDA, "allocating FIR state failed: %s", cudaGetErrorString(e)); }
+    *out = f;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fir_reset(qpsk_b200_fir* f) {
+    if (!f) return fail(QPSK_B200_ERR_ARG, "null filter");
+    CU(cudaSetDevice(f->device));
+    CU(cudaMemsetAsync(f->d_state, 0, (size_t)f->C * f->ntaps * sizeof(float2), f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+    return QPSK_B200_OK;
+}
+
+template <int NTAPS, int MODE>
+static cudaError_t launch_fir(const FirArgs& a, cudaStream_t s) {
+    const size_t smem = sizeof(FirSmem<NTAPS>);
+    cudaError_t e = cudaFuncSetAttribute(fir_kernel<NTAPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fir_kernel<NTAPS, MODE><<<(a.C + QPSK_GROUP - 1) / QPSK_GROUP, 256, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+extern "C" int qpsk_b200_fir_process_device(qpsk_b200_fir* f, float* d_samples, int nsamples, void* cuda_stream) {
+    if (!f || !d_samples) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nsamples < 1) return fail(QPSK_B200_ERR_ARG, "nsamples must be positive");
+    CU(cudaSetDevice(f->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : f->stream;
+    if (g_taps_owner != f->id) {
+        float2 t2[QPSK_MAX_TAPS];
+        for (int i = 0; i < f->ntaps; i++) t2[i] = make_float2(f->taps[i], f->taps[i]);
+        CU(cudaMemcpyToSymbolAsync(c_taps2, t2, sizeof(float2) * f->ntaps, 0, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        g_taps_owner = f->id;
+    }
+    FirArgs a;
+    a.data = reinterpret_cast<float2*>(d_samples); a.state = f->d_state; a.C = f->C; a.T = nsamples;
+    CU(cudaEventRecord(f->ev[0], s));
+    cudaError_t e;
+    const bool fast = f->mode == QPSK_B200_MODE_FAST;
+    if (f->ntaps == 127) e = fast ? launch_fir<127, QPSK_MODE_FAST>(a, s) : launch_fir<127, QPSK_MODE_EXACT>(a, s);
+    else                 e = fast ? launch_fir<256, QPSK_MODE_FAST>(a, s) : launch_fir<256, QPSK_MODE_EXACT>(a, s);
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "FIR kernel launch failed: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(f->ev[1], s));
+    f->timed = true;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fir_process_host(qpsk_b200_fir* f, float* h_samples, int nsamples) {
+    if (!f || !h_samples) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nsamples < 1) return fail(QPSK_B200_ERR_ARG, "nsamples must be positive");
+    CU(cudaSetDevice(f->device));
+    const size_t elems = (size_t)f->C * nsamples;
+    if (f->stage_elems < elems) {
+        if (f->d_stage) { cudaFree(f->d_stage); f->d_stage = nullptr; f->stage_elems = 0; }
+        CU(cudaMalloc((void**)&f->d_stage, elems * sizeof(float2)));
+        f->stage_elems = elems;
+    }
+    CU(cudaMemcpyAsync(f->d_stage, h_samples, elems * sizeof(float2), cudaMemcpyHostToDevice, f->stream));
+    int rc = qpsk_b200_fir_process_device(f, reinterpret_cast<float*>(f->d_stage), nsamples, f->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_samples, f->d_stage, elems * sizeof(float2), cudaMemcpyDeviceToHost, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fir_get_memory(qpsk_b200_fir* f, float* h_memory) {
+    if (!f || !h_memory) return fail(QPSK_B200_ERR_ARG, "null argument");
+    CU(cudaSetDevice(f->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h_memory, f->d_state, (size_t)f->C * f->ntaps * sizeof(float2), cudaMemcpyDeviceToHost));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fir_set_memory(qpsk_b200_fir* f, const float* h_memory) {
+    if (!f || !h_memory) return fail(QPSK_B200_ERR_ARG, "null argument");
+    CU(cudaSetDevice(f->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(f->d_state, h_memory, (size_t)f->C * f->ntaps * sizeof(float2), cudaMemcpyHostToDevice));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fir_last_kernel_ms(qpsk_b200_fir* f, float* ms) {
+    if (!f || !ms || !f->timed) return fail(QPSK_B200_ERR_STATE, "no process call yet");
+    CU(cudaEventSynchronize(f->ev[1]));
+    CU(cudaEventElapsedTime(ms, f->ev[0], f->ev[1]));
     return QPSK_B200_OK;
 }
