@@ -131,6 +131,25 @@ int qpsk_b200_fir_get_memory(qpsk_b200_fir *f, float *h_memory);
 int qpsk_b200_fir_set_memory(qpsk_b200_fir *f, const float *h_memory);
 int qpsk_b200_fir_last_kernel_ms(qpsk_b200_fir *f, float *ms);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched FFT + |X|^2 argmax  (algorithms/fft.h:46-49; fft.c:98-136)
+ * FP32 on the GPU (the reference is complex double): agrees within 1e-5 max-norm relative.
+ * Forward is scaled by 1/n and the inverse is unscaled, as in the reference.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct qpsk_b200_fft qpsk_b200_fft;
+
+/* n: a power of two, 2..8192 */
+int qpsk_b200_fft_create(int n, int device, qpsk_b200_fft **out);
+int qpsk_b200_fft_destroy(qpsk_b200_fft *f);
+/* estimator: d_in complex float [nbursts][n] in HBM -> d_bin int32 [nbursts] (first strict maximum
+ * of |X[k]|^2, k = 0..n-1) and d_mag2 float [nbursts] (may be NULL).  Forward transform. */
+int qpsk_b200_fft_argmax_device(qpsk_b200_fft *f, const float *d_in, int nbursts, int32_t *d_bin, float *d_mag2, void *cuda_stream);
+int qpsk_b200_fft_argmax_host(qpsk_b200_fft *f, const float *h_in, int nbursts, int32_t *h_bin, float *h_mag2);
+/* fftn (inverse = 0) / ifftn (inverse = 1) over nbursts transforms; d_out may equal d_in */
+int qpsk_b200_fft_transform_device(qpsk_b200_fft *f, const float *d_in, float *d_out, int nbursts, int inverse, void *cuda_stream);
+int qpsk_b200_fft_transform_host(qpsk_b200_fft *f, const float *h_in, float *h_out, int nbursts, int inverse);
+int qpsk_b200_fft_last_kernel_ms(qpsk_b200_fft *f, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,7 @@ def lib():
     L.qpsk_b200_rx_launch_count.restype = C.c_longlong
     L.qpsk_b200_rx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _bind_fir(L)
+    _bind_fft(L)
     _lib = L
     return L
 
@@ -72,3 +73,13 @@ def _bind_fir(L):
     L.qpsk_b200_fir_get_memory.argtypes = [C.c_void_p, C.c_void_p]
     L.qpsk_b200_fir_set_memory.argtypes = [C.c_void_p, C.c_void_p]
     L.qpsk_b200_fir_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+
+
+def _bind_fft(L):
+    L.qpsk_b200_fft_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.qpsk_b200_fft_destroy.argtypes = [C.c_void_p]
+    L.qpsk_b200_fft_argmax_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.qpsk_b200_fft_argmax_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.qpsk_b200_fft_transform_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.qpsk_b200_fft_transform_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.qpsk_b200_fft_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]

@@ -13,6 +13,7 @@
 #include "rx_front.cuh"
 #include "rx_costas.cuh"
 #include "fir.cuh"
+#include "fft.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -548,6 +549,172 @@ extern "C" int qpsk_b200_fir_set_memory(qpsk_b200_fir* f, const float* h_memory)
 
 extern "C" int qpsk_b200_fir_last_kernel_ms(qpsk_b200_fir* f, float* ms) {
     if (!f || !ms || !f->timed) return fail(QPSK_B200_ERR_STATE, "no process call yet");
+    CU(cudaEventSynchronize(f->ev[1]));
+    CU(cudaEventElapsedTime(ms, f->ev[0], f->ev[1]));
+    return QPSK_B200_OK;
+}
+
+// =============================================================================================
+// batched FFT + argmax
+// =============================================================================================
+struct qpsk_b200_fft {
+    int n, log2n, device, nsm;
+    float2* d_tw;
+    void* d_stage;  size_t stage_bytes;
+    int* d_bin;     float* d_mag2;  size_t out_cap;
+    cudaStream_t stream;
+    cudaEvent_t ev[2];
+    bool timed;
+};
+
+extern "C" int qpsk_b200_fft_destroy(qpsk_b200_fft* f) {
+    if (!f) return 0;
+    cudaSetDevice(f->device);
+    if (f->d_tw) cudaFree(f->d_tw);
+    if (f->d_stage) cudaFree(f->d_stage);
+    if (f->d_bin) cudaFree(f->d_bin);
+    if (f->d_mag2) cudaFree(f->d_mag2);
+    for (auto& e : f->ev) if (e) cudaEventDestroy(e);
+    if (f->stream) cudaStreamDestroy(f->stream);
+    delete f;
+    return 0;
+}
+
+extern "C" int qpsk_b200_fft_create(int n, int device, qpsk_b200_fft** out) {
+    if (!out) return fail(QPSK_B200_ERR_ARG, "null argument");
+    *out = nullptr;
+    int lg = 0;
+    while ((1 << lg) < n) lg++;
+    if (n < 2 || n > 8192 || (1 << lg) != n) return fail(QPSK_B200_ERR_ARG, "fft length %d unsupported: powers of two 2..8192", n);
+    int rc = check_device(device);
+    if (rc) return rc;
+    qpsk_b200_fft* f = new (std::nothrow) qpsk_b200_fft();
+    if (!f) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+    memset(f, 0, sizeof *f);
+    f->n = n; f->log2n = lg; f->device = device;
+    cudaDeviceGetAttribute(&f->nsm, cudaDevAttrMultiProcessorCount, device);
+    // twiddles exp(-2 pi i t / n), t < n/2, evaluated in double on the host (fft.c:55-56) and rounded once
+    const int ntw = n / 2 > 0 ? n / 2 : 1;
+    float2* tw = new float2[ntw];
+    for (int t = 0; t < ntw; t++) {
+        const double ang = kTau * (double)t / (double)n;
+        tw[t] = make_float2((float)cos(ang), (float)(-sin(ang)));
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    for (auto& ev : f->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_tw, sizeof(float2) * ntw);
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_tw, tw, sizeof(float2) * ntw, cudaMemcpyHostToDevice);
+    delete[] tw;
+    if (e != cudaSuccess) { qpsk_b200_fft_destroy(f); return fail(QPSK_B200_ERR_CUDA, "allocating FFT state failed: %s", cudaGetErrorString(e)); }
+    *out = f;
+    return QPSK_B200_OK;
+}
+
+template <int LOG2N>
+static cudaError_t launch_fft_n(const FftArgs& a, int nsm, cudaStream_t s) {
+    using Cfg = FftCfg<LOG2N>;
+    cudaError_t e = cudaFuncSetAttribute(fft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_kernel<LOG2N>, Cfg::THREADS, Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const int passes = (a.nbursts + Cfg::FPB - 1) / Cfg::FPB;
+    int grid = nsm * per_sm;                      // persistent: a multiple of the SM count
+    if (grid > passes) grid = passes;
+    fft_kernel<LOG2N><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(a);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_fft(int log2n, const FftArgs& a, int nsm, cudaStream_t s) {
+    switch (log2n) {
+        case 1: return launch_fft_n<1>(a, nsm, s);   case 2: return launch_fft_n<2>(a, nsm, s);
+        case 3: return launch_fft_n<3>(a, nsm, s);   case 4: return launch_fft_n<4>(a, nsm, s);
+        case 5: return launch_fft_n<5>(a, nsm, s);   case 6: return launch_fft_n<6>(a, nsm, s);
+        case 7: return launch_fft_n<7>(a, nsm, s);   case 8: return launch_fft_n<8>(a, nsm, s);
+        case 9: return launch_fft_n<9>(a, nsm, s);   case 10: return launch_fft_n<10>(a, nsm, s);
+        case 11: return launch_fft_n<11>(a, nsm, s); case 12: return launch_fft_n<12>(a, nsm, s);
+        case 13: return launch_fft_n<13>(a, nsm, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+static int fft_run(qpsk_b200_fft* f, const float* d_in, float* d_out, int nbursts, int inverse, int32_t* d_bin, float* d_mag2, cudaStream_t s) {
+    FftArgs a;
+    a.in = reinterpret_cast<const float2*>(d_in); a.spectrum = reinterpret_cast<float2*>(d_out);
+    a.bin = d_bin; a.mag2 = d_mag2; a.tw = f->d_tw; a.nbursts = nbursts;
+    a.im_sign = inverse ? -1.0f : 1.0f;
+    a.scale = inverse ? 1.0f : 1.0f / (float)f->n;           // fft.c:105-107 vs fft.c:130-136
+    CU(cudaEventRecord(f->ev[0], s));
+    cudaError_t e = launch_fft(f->log2n, a, f->nsm, s);
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "FFT kernel launch failed: %s", cudaGetErrorString(e));
+    CU(cudaEventRecord(f->ev[1], s));
+    f->timed = true;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fft_argmax_device(qpsk_b200_fft* f, const float* d_in, int nbursts, int32_t* d_bin, float* d_mag2, void* cuda_stream) {
+    if (!f || !d_in || !d_bin) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nbursts < 1) return fail(QPSK_B200_ERR_ARG, "nbursts must be positive");
+    CU(cudaSetDevice(f->device));
+    return fft_run(f, d_in, nullptr, nbursts, 0, d_bin, d_mag2, cuda_stream ? (cudaStream_t)cuda_stream : f->stream);
+}
+
+extern "C" int qpsk_b200_fft_transform_device(qpsk_b200_fft* f, const float* d_in, float* d_out, int nbursts, int inverse, void* cuda_stream) {
+    if (!f || !d_in || !d_out) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nbursts < 1) return fail(QPSK_B200_ERR_ARG, "nbursts must be positive");
+    CU(cudaSetDevice(f->device));
+    return fft_run(f, d_in, d_out, nbursts, inverse, nullptr, nullptr, cuda_stream ? (cudaStream_t)cuda_stream : f->stream);
+}
+
+static int fft_stage_in(qpsk_b200_fft* f, const float* h_in, int nbursts) {
+    const size_t bytes = (size_t)nbursts * f->n * sizeof(float2);
+    if (f->stage_bytes < bytes) {
+        if (f->d_stage) { cudaFree(f->d_stage); f->d_stage = nullptr; f->stage_bytes = 0; }
+        CU(cudaMalloc(&f->d_stage, bytes));
+        f->stage_bytes = bytes;
+    }
+    CU(cudaMemcpyAsync(f->d_stage, h_in, bytes, cudaMemcpyHostToDevice, f->stream));
+    return 0;
+}
+
+extern "C" int qpsk_b200_fft_argmax_host(qpsk_b200_fft* f, const float* h_in, int nbursts, int32_t* h_bin, float* h_mag2) {
+    if (!f || !h_in || !h_bin) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nbursts < 1) return fail(QPSK_B200_ERR_ARG, "nbursts must be positive");
+    CU(cudaSetDevice(f->device));
+    int rc = fft_stage_in(f, h_in, nbursts);
+    if (rc) return rc;
+    if (f->out_cap < (size_t)nbursts) {
+        if (f->d_bin) cudaFree(f->d_bin);
+        if (f->d_mag2) cudaFree(f->d_mag2);
+        f->d_bin = nullptr; f->d_mag2 = nullptr; f->out_cap = 0;
+        CU(cudaMalloc((void**)&f->d_bin, sizeof(int) * nbursts));
+        CU(cudaMalloc((void**)&f->d_mag2, sizeof(float) * nbursts));
+        f->out_cap = nbursts;
+    }
+    rc = fft_run(f, reinterpret_cast<const float*>(f->d_stage), nullptr, nbursts, 0, f->d_bin, f->d_mag2, f->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_bin, f->d_bin, sizeof(int) * nbursts, cudaMemcpyDeviceToHost, f->stream));
+    if (h_mag2) CU(cudaMemcpyAsync(h_mag2, f->d_mag2, sizeof(float) * nbursts, cudaMemcpyDeviceToHost, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fft_transform_host(qpsk_b200_fft* f, const float* h_in, float* h_out, int nbursts, int inverse) {
+    if (!f || !h_in || !h_out) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nbursts < 1) return fail(QPSK_B200_ERR_ARG, "nbursts must be positive");
+    CU(cudaSetDevice(f->device));
+    int rc = fft_stage_in(f, h_in, nbursts);
+    if (rc) return rc;
+    rc = fft_run(f, reinterpret_cast<const float*>(f->d_stage), reinterpret_cast<float*>(f->d_stage), nbursts, inverse, nullptr, nullptr, f->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_out, f->d_stage, (size_t)nbursts * f->n * sizeof(float2), cudaMemcpyDeviceToHost, f->stream));
+    CU(cudaStreamSynchronize(f->stream));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_fft_last_kernel_ms(qpsk_b200_fft* f, float* ms) {
+    if (!f || !ms || !f->timed) return fail(QPSK_B200_ERR_STATE, "no transform yet");
     CU(cudaEventSynchronize(f->ev[1]));
     CU(cudaEventElapsedTime(ms, f->ev[0], f->ev[1]));
     return QPSK_B200_OK;
