@@ -48,7 +48,8 @@ enum { QPSK_B200_UB_ALIAS = 0,     /* reproduce the Makefile-build out-of-frame 
 
 enum {                              /* cfg.flags */
     QPSK_B200_KEEP_FIR = 1,         /* keep the matched-filter output (16 B/sample!) for parity checks */
-    QPSK_B200_KEEP_SYMBOLS = 2      /* keep the derotated symbols (costas_frame) */
+    QPSK_B200_KEEP_SYMBOLS = 2,     /* keep the derotated symbols (costas_frame) */
+    QPSK_B200_DECODE_FRAMES = 4     /* run descramble -> de-interleave -> CRC16 on every frame's dibits */
 };
 
 typedef struct {
@@ -75,7 +76,9 @@ enum {
     QPSK_B200_OUT_DEC = 3,      /* float2 [C][F*nsym]    decimated symbols produced by each frame */
     QPSK_B200_OUT_SYMBOLS = 4,  /* float2 [C][F*nsym]    costas_frame (needs KEEP_SYMBOLS) */
     QPSK_B200_OUT_FIR = 5,      /* float2 [C][F*N]       matched-filter output (needs KEEP_FIR) */
-    QPSK_B200_OUT_TAPS = 6      /* float  [ntaps] */
+    QPSK_B200_OUT_TAPS = 6,     /* float  [ntaps] */
+    QPSK_B200_OUT_FRAMES = 7,   /* uint8  [C][F*nbytes]  de-scrambled, de-interleaved frames: payload | crc16 hi | lo (needs DECODE_FRAMES) */
+    QPSK_B200_OUT_CRC_OK = 8    /* uint8  [C][F]         1 where the frame's CRC16 matched (needs DECODE_FRAMES) */
 };
 
 const char *qpsk_b200_last_error(void);
@@ -149,6 +152,29 @@ int qpsk_b200_fft_argmax_host(qpsk_b200_fft *f, const float *h_in, int nbursts, 
 int qpsk_b200_fft_transform_device(qpsk_b200_fft *f, const float *d_in, float *d_out, int nbursts, int inverse, void *cuda_stream);
 int qpsk_b200_fft_transform_host(qpsk_b200_fft *f, const float *h_in, float *h_out, int nbursts, int inverse);
 int qpsk_b200_fft_last_kernel_ms(qpsk_b200_fft *f, float *ms);
+
+/* ------------------------------------------------------------------------------------------
+ * Bit stages  (algorithms/bit-scramble.h:29-30, interleave.h:13, crc16.h:10), batched over frames.
+ * Host-buffer entry points; rows are frames.  The *_rx_* form runs on the slicer output in HBM.
+ *
+ * Frame format used by DECODE_FRAMES / qpsk_b200_frames_encode (this project's composition; the
+ * reference never chains its bit stages): frame = payload[nbytes-2] | crc16(payload) hi | lo ->
+ * interleave(INTERLEAVE) -> dibits LSB first -> scramble with the register reset to SEED per
+ * frame; nbytes = FRAME_SIZE/CYCLES/4 (32 at 2400 baud, 16 at 1200 baud), one frame per rx_frame.
+ * ---------------------------------------------------------------------------------------- */
+/* crc16() of every row: h_data uint8 [nframes][nbytes] -> h_crc uint16 [nframes] */
+int qpsk_b200_bits_crc16(const uint8_t *h_data, int nbytes, int nframes, uint16_t *h_crc, int device);
+/* interleave(row, nbytes, dir) of every row in place; dir 0 = INTERLEAVE, 1 = DEINTERLEAVE; nbytes < 8192 */
+int qpsk_b200_bits_interleave(uint8_t *h_data, int nbytes, int nframes, int dir, int device);
+/* scramble() over every row of dibits (one dibit per byte, low two bits), register = SEED at the start of each row */
+int qpsk_b200_bits_scramble(uint8_t *h_dibits, int ndibits, int nframes, int device);
+/* payload uint8 [C][F][nbytes] (last two bytes of each frame ignored) -> packed dibits uint8 [C][F*nbytes]
+ * in the layout QPSK_B200_OUT_DIBITS uses; nbytes in {16, 32} */
+int qpsk_b200_frames_encode(const uint8_t *h_payload, int nbytes, int nchan, int nframes, uint8_t *h_dibits, int device);
+/* inverse of the above on host buffers: packed dibits -> frames uint8 [C][F][nbytes] and CRC verdicts uint8 [C][F] */
+int qpsk_b200_frames_decode(const uint8_t *h_dibits, int nbytes, int nchan, int nframes, uint8_t *h_frames, uint8_t *h_crc_ok, int device);
+/* counters accumulated by DECODE_FRAMES since create/reset: frames examined and CRC passes */
+int qpsk_b200_rx_crc_counters(qpsk_b200_rx *rx, unsigned long long *frames, unsigned long long *passes);
 
 #ifdef __cplusplus
 }

@@ -174,6 +174,21 @@ class Oracle:
             d[i] = one.value
         return d, r.value
 
+    def frame_encode(self, payload, nbytes):
+        """payload uint8 [nbytes-2] -> scrambled, interleaved dibits uint8 [4*nbytes] (unpinned composition)."""
+        payload = np.ascontiguousarray(payload, np.uint8)
+        assert len(payload) == nbytes - 2
+        out = np.zeros(4 * nbytes, np.uint8)
+        self.L.orc_frame_encode(payload.ctypes.data_as(C.c_void_p), nbytes, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def frame_decode(self, dibits, nbytes):
+        dibits = np.ascontiguousarray(dibits, np.uint8)
+        assert len(dibits) == 4 * nbytes
+        frame = np.zeros(nbytes, np.uint8)
+        ok = self.L.orc_frame_decode(dibits.ctypes.data_as(C.c_void_p), nbytes, frame.ctypes.data_as(C.c_void_p))
+        return frame, bool(ok)
+
     def fftn(self, x, inverse=False):
         x = np.ascontiguousarray(x, np.complex128)
         out = np.zeros_like(x)

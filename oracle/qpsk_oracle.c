@@ -499,3 +499,45 @@ long orc_glibc_check(uint32_t lo, uint32_t hi, uint32_t stride) {
     }
     return bad;
 }
+
+/* ======================================================================================
+ * Frame format -- PARITY UNPINNED: the reference never chains its bit stages (algorithms/ is
+ * not even linked), so this composition is this project's own, built
+ * only from the pinned primitives above:
+ *
+ *   frame[nbytes] = payload[nbytes-2] | crc16(payload) high byte | low byte
+ *   interleave(frame, nbytes, INTERLEAVE)                       (interleave.c:43-78)
+ *   dibit k = bit 2k | bit 2k+1 << 1, bits taken LSB first      (bit-scramble.c:57-69 bit order)
+ *   scramble every dibit, register reset to SEED per frame      (bit-scramble.c:11)
+ *
+ * and the inverse on the receive side.  One frame = the dibits of one rx_frame call
+ * (FRAME_SIZE / CYCLES symbols = 32 bytes at 2400 baud, 16 bytes at 1200 baud).
+ * ==================================================================================== */
+void orc_frame_encode(const uint8_t *payload, int nbytes, uint8_t *dibits /* [4*nbytes] */) {
+    uint8_t frame[nbytes];
+    memcpy(frame, payload, (size_t)nbytes - 2);
+    const uint16_t crc = orc_crc16(payload, nbytes - 2);
+    frame[nbytes - 2] = (uint8_t)(crc >> 8);
+    frame[nbytes - 1] = (uint8_t)(crc & 0xff);
+    orc_interleave(frame, nbytes, 0);
+    uint16_t reg = ORC_SCRAMBLE_SEED;
+    for (int k = 0; k < 4 * nbytes; k++) {
+        uint8_t d = (uint8_t)((frame[k / 4] >> (2 * (k % 4))) & 3);
+        orc_scramble_dibit(&reg, &d);
+        dibits[k] = d;
+    }
+}
+
+/* returns 1 when the CRC matches; frame[nbytes] receives payload | crc */
+int orc_frame_decode(const uint8_t *dibits, int nbytes, uint8_t *frame) {
+    uint16_t reg = ORC_SCRAMBLE_SEED;
+    memset(frame, 0, (size_t)nbytes);
+    for (int k = 0; k < 4 * nbytes; k++) {
+        uint8_t d = (uint8_t)(dibits[k] & 3);
+        orc_scramble_dibit(&reg, &d);
+        frame[k / 4] |= (uint8_t)(d << (2 * (k % 4)));
+    }
+    orc_interleave(frame, nbytes, 1);
+    const uint16_t crc = orc_crc16(frame, nbytes - 2);
+    return frame[nbytes - 2] == (uint8_t)(crc >> 8) && frame[nbytes - 1] == (uint8_t)(crc & 0xff);
+}

@@ -122,6 +122,10 @@ void     orc_interleave(uint8_t *inout, int nbytes, int dir /* 0 = interleave, 1
 int      orc_interleave_prime(int nbytes);
 uint16_t orc_crc16(const uint8_t *data, int length);
 
+/* ---- frame format (parity unpinned composition of the pinned bit stages; see qpsk_oracle.c) */
+void orc_frame_encode(const uint8_t *payload, int nbytes, uint8_t *dibits);
+int  orc_frame_decode(const uint8_t *dibits, int nbytes, uint8_t *frame);
+
 /* ---- glibc 2.39 sinf/cosf (x86-64 FMA ifunc variant), restated: the device NCO follows this */
 float orc_glibc_sinf(float y);
 float orc_glibc_cosf(float y);

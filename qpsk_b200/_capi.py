@@ -22,8 +22,8 @@ class RxConfig(C.Structure):
 
 MODE_EXACT, MODE_FAST = 0, 1
 UB_ALIAS, UB_CLAMP = 0, 1
-KEEP_FIR, KEEP_SYMBOLS = 1, 2
-OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS = range(7)
+KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES = 1, 2, 4
+OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK = range(9)
 
 _lib = None
 
@@ -54,6 +54,7 @@ def lib():
     L.qpsk_b200_rx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _bind_fir(L)
     _bind_fft(L)
+    _bind_bits(L)
     _lib = L
     return L
 
@@ -83,3 +84,12 @@ def _bind_fft(L):
     L.qpsk_b200_fft_transform_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.qpsk_b200_fft_transform_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.qpsk_b200_fft_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+
+
+def _bind_bits(L):
+    L.qpsk_b200_bits_crc16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.qpsk_b200_bits_interleave.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.qpsk_b200_bits_scramble.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.qpsk_b200_frames_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.qpsk_b200_frames_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.qpsk_b200_rx_crc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]

@@ -14,6 +14,7 @@
 #include "rx_costas.cuh"
 #include "fir.cuh"
 #include "fft.cuh"
+#include "bits.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -71,6 +72,9 @@ struct qpsk_b200_rx {
     float2* d_track_t;      // [maxF][Cpad]
     float2* d_fir_dbg;      // [C][maxF*N] or null
     float2* d_costas_dbg;   // [maxF][nsym][Cpad] or null
+    unsigned* d_frames_t;   // [maxF][W][Cpad] decoded frames (DECODE_FRAMES)
+    uint8_t* d_crc_ok_t;    // [maxF][Cpad]
+    unsigned long long* d_counters;   // [2]
     int16_t* d_pcm_stage;   // [C][maxF*N] for the host path (lazy)
     void* d_scratch;        // transposed download staging (lazy)
     size_t scratch_bytes;
@@ -103,6 +107,7 @@ static int rx_free(qpsk_b200_rx* rx) {
     cudaSetDevice(rx->cfg.device);
     void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
+                     rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters,
                      rx->d_pcm_stage, rx->d_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev) if (e) cudaEventDestroy(e);
@@ -176,6 +181,11 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     alloc((void**)&rx->d_track_t, F * Cp * sizeof(float2));
     if (cfg->flags & QPSK_B200_KEEP_FIR) alloc((void**)&rx->d_fir_dbg, (size_t)nchan * F * N * sizeof(float2));
     if (cfg->flags & QPSK_B200_KEEP_SYMBOLS) alloc((void**)&rx->d_costas_dbg, F * S * Cp * sizeof(float2));
+    if (cfg->flags & QPSK_B200_DECODE_FRAMES) {
+        alloc((void**)&rx->d_frames_t, F * (S / 16) * Cp * sizeof(unsigned));
+        alloc((void**)&rx->d_crc_ok_t, F * Cp);
+        alloc((void**)&rx->d_counters, 2 * sizeof(unsigned long long));
+    }
     if (e != cudaSuccess) {
         rx_free(rx);
         return fail(QPSK_B200_ERR_CUDA, "allocating receiver state failed: %s", cudaGetErrorString(e));
@@ -203,6 +213,7 @@ extern "C" int qpsk_b200_rx_reset(qpsk_b200_rx* rx) {
     CU(cudaMemcpyAsync(rx->d_ph_state, &ph0, sizeof ph0, cudaMemcpyHostToDevice, s));
     // d_phase = d_freq = 0 (costas_loop.c:32-33)
     CU(cudaMemsetAsync(rx->d_loop_state, 0, Cp * sizeof(float2), s));
+    if (rx->d_counters) CU(cudaMemsetAsync(rx->d_counters, 0, 2 * sizeof(unsigned long long), s));
     CU(cudaStreamSynchronize(s));
     rx->slot_base = 0;
     rx->lastF = 0;
@@ -217,6 +228,35 @@ static int upload_taps(const qpsk_b200_rx* rx, cudaStream_t s) {
     return 0;
 }
 
+
+
+// ---- bit-stage helpers shared by the receiver and the standalone entry points -----------------
+static long long g_keystream_nbytes = -1;
+
+static int upload_keystream(int nbytes, cudaStream_t s) {
+    if (g_keystream_nbytes == nbytes) return 0;
+    unsigned words[16] = { 0 };
+    uint16_t reg = (uint16_t)QPSK_SCRAMBLE_SEED;                 // bit-scramble.c:46-55, reset per frame
+    for (int bit = 0; bit < nbytes * 8; bit++) words[bit >> 5] |= lfsr_step(reg) << (bit & 31);
+    CU(cudaMemcpyToSymbolAsync(c_keystream_words, words, sizeof words, 0, cudaMemcpyHostToDevice, s));
+    CU(cudaStreamSynchronize(s));
+    g_keystream_nbytes = nbytes;
+    return 0;
+}
+
+static int launch_frame_decode(int nbytes, const unsigned* dibits_t, unsigned* frames_t, uint8_t* crc_ok_t,
+                               unsigned long long* counters, int C, int Cpad, int F, cudaStream_t s) {
+    if (nbytes != 16 && nbytes != 32) return fail(QPSK_B200_ERR_ARG, "frame decode supports 16- and 32-byte frames, got %d", nbytes);
+    int rc = upload_keystream(nbytes, s);
+    if (rc) return rc;
+    FrameDecodeArgs a;
+    a.dibits_t = dibits_t; a.frames_t = frames_t; a.crc_ok_t = crc_ok_t; a.counters = counters; a.C = C; a.Cpad = Cpad; a.F = F;
+    dim3 grid((C + 127) / 128, F);
+    if (nbytes == 32) frame_decode_kernel<32><<<grid, 128, 0, s>>>(a);
+    else frame_decode_kernel<16><<<grid, 128, 0, s>>>(a);
+    CU(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pcm, int nframes, void* cuda_stream) {
     if (!rx || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
@@ -275,6 +315,12 @@ extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pc
     CU(cudaGetLastError());
     CU(cudaEventRecord(rx->ev[3], s));
 
+    if (rx->d_frames_t) {   // K4: descramble -> de-interleave -> CRC16 per frame
+        int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t, rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters, rx->C, rx->Cpad, F, s);
+        if (rc) return rc;
+        rx->launches += 1;
+    }
+
     rx->launches += 4;
     rx->timed = true;
     rx->slot_base = (rx->slot_base + F) % rx->nslots;
@@ -310,6 +356,8 @@ extern "C" size_t qpsk_b200_rx_output_bytes(const qpsk_b200_rx* rx, int what) {
         case QPSK_B200_OUT_SYMBOLS: return C * F * S * sizeof(float2);
         case QPSK_B200_OUT_FIR: return C * F * N * sizeof(float2);
         case QPSK_B200_OUT_TAPS: return (size_t)rx->cfg.ntaps * sizeof(float);
+        case QPSK_B200_OUT_FRAMES: return C * F * (S / 4);
+        case QPSK_B200_OUT_CRC_OK: return C * F;
         default: return 0;
     }
 }
@@ -350,6 +398,12 @@ extern "C" int qpsk_b200_rx_read(qpsk_b200_rx* rx, int what, void* h_dst, size_t
         case QPSK_B200_OUT_DIBITS: return download_transposed<unsigned>(rx, rx->d_dibits_t, F * (S / 16), h_dst, s);
         case QPSK_B200_OUT_INDEX: return download_transposed<int>(rx, rx->d_index_t, F, h_dst, s);
         case QPSK_B200_OUT_TRACK: return download_transposed<float2>(rx, rx->d_track_t, F, h_dst, s);
+        case QPSK_B200_OUT_FRAMES:
+            if (!rx->d_frames_t) return fail(QPSK_B200_ERR_STATE, "frames were not decoded (QPSK_B200_DECODE_FRAMES)");
+            return download_transposed<unsigned>(rx, rx->d_frames_t, F * (S / 16), h_dst, s);
+        case QPSK_B200_OUT_CRC_OK:
+            if (!rx->d_crc_ok_t) return fail(QPSK_B200_ERR_STATE, "frames were not decoded (QPSK_B200_DECODE_FRAMES)");
+            return download_transposed<uint8_t>(rx, rx->d_crc_ok_t, F, h_dst, s);
         case QPSK_B200_OUT_SYMBOLS:
             if (!rx->d_costas_dbg) return fail(QPSK_B200_ERR_STATE, "symbols were not kept (QPSK_B200_KEEP_SYMBOLS)");
             return download_transposed<float2>(rx, rx->d_costas_dbg, F * S, h_dst, s);
@@ -718,4 +772,148 @@ extern "C" int qpsk_b200_fft_last_kernel_ms(qpsk_b200_fft* f, float* ms) {
     CU(cudaEventSynchronize(f->ev[1]));
     CU(cudaEventElapsedTime(ms, f->ev[0], f->ev[1]));
     return QPSK_B200_OK;
+}
+
+// =============================================================================================
+// bit stages: standalone entry points on host buffers
+// =============================================================================================
+extern "C" int qpsk_b200_rx_crc_counters(qpsk_b200_rx* rx, unsigned long long* frames, unsigned long long* passes) {
+    if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
+    if (!rx->d_counters) return fail(QPSK_B200_ERR_STATE, "frames are not decoded (QPSK_B200_DECODE_FRAMES)");
+    CU(cudaSetDevice(rx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    unsigned long long h[2];
+    CU(cudaMemcpy(h, rx->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    if (frames) *frames = h[0];
+    if (passes) *passes = h[1];
+    return QPSK_B200_OK;
+}
+
+struct DevBuf {      // scoped device allocation for the one-shot entry points
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+extern "C" int qpsk_b200_bits_crc16(const uint8_t* h_data, int nbytes, int nframes, uint16_t* h_crc, int device) {
+    if (!h_crc || nframes < 1 || nbytes < 0 || (nbytes > 0 && !h_data)) return fail(QPSK_B200_ERR_ARG, "bad argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    DevBuf d, c;
+    const size_t bytes = (size_t)nbytes * nframes;
+    CU(cudaMalloc(&d.p, bytes ? bytes : 1));
+    CU(cudaMalloc(&c.p, sizeof(uint16_t) * nframes));
+    if (bytes) CU(cudaMemcpy(d.p, h_data, bytes, cudaMemcpyHostToDevice));
+    crc16_rows_kernel<<<(nframes + 127) / 128, 128>>>((const uint8_t*)d.p, nbytes, nframes, (uint16_t*)c.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(h_crc, c.p, sizeof(uint16_t) * nframes, cudaMemcpyDeviceToHost));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_bits_interleave(uint8_t* h_data, int nbytes, int nframes, int dir, int device) {
+    if (!h_data || nframes < 1 || nbytes < 1) return fail(QPSK_B200_ERR_ARG, "bad argument");
+    if (nbytes >= 8192) return fail(QPSK_B200_ERR_ARG, "nbytes %d: the reference's uint16_t bit count wraps at 8192 bytes (interleave.c:49)", nbytes);
+    if (dir != 0 && dir != 1) return fail(QPSK_B200_ERR_ARG, "dir must be 0 (INTERLEAVE) or 1 (DEINTERLEAVE)");
+    int rc = check_device(device);
+    if (rc) return rc;
+    DevBuf d;
+    const size_t bytes = (size_t)nbytes * nframes;
+    CU(cudaMalloc(&d.p, bytes));
+    CU(cudaMemcpy(d.p, h_data, bytes, cudaMemcpyHostToDevice));
+    const int b = interleave_prime(nbytes * 8);
+    const int warps = 8;
+    const size_t smem = (size_t)warps * ((nbytes + 3) / 4) * sizeof(unsigned);
+    CU(cudaFuncSetAttribute(interleave_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    interleave_rows_kernel<<<(nframes + warps - 1) / warps, warps * 32, smem>>>((uint8_t*)d.p, nbytes, nframes, b, dir);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(h_data, d.p, bytes, cudaMemcpyDeviceToHost));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_bits_scramble(uint8_t* h_dibits, int ndibits, int nframes, int device) {
+    if (!h_dibits || nframes < 1 || ndibits < 1) return fail(QPSK_B200_ERR_ARG, "bad argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    // the keystream does not depend on the data: evaluate the LFSR once per call, XOR on the device
+    uint8_t* ks = new (std::nothrow) uint8_t[ndibits];
+    if (!ks) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+    uint16_t reg = (uint16_t)QPSK_SCRAMBLE_SEED;
+    for (int k = 0; k < ndibits; k++) { const unsigned b0 = lfsr_step(reg); const unsigned b1 = lfsr_step(reg); ks[k] = (uint8_t)(b0 | (b1 << 1)); }
+    DevBuf d, k;
+    const size_t total = (size_t)ndibits * nframes;
+    cudaError_t e = cudaMalloc(&d.p, total);
+    if (e == cudaSuccess) e = cudaMalloc(&k.p, ndibits);
+    if (e == cudaSuccess) e = cudaMemcpy(d.p, h_dibits, total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(k.p, ks, ndibits, cudaMemcpyHostToDevice);
+    delete[] ks;
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "scramble staging failed: %s", cudaGetErrorString(e));
+    scramble_rows_kernel<<<(unsigned)((total + 255) / 256), 256>>>((uint8_t*)d.p, (const uint8_t*)k.p, ndibits, total);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(h_dibits, d.p, total, cudaMemcpyDeviceToHost));
+    return QPSK_B200_OK;
+}
+
+// [C][rows] channel-major words -> [rows][Cpad] channel-fastest (the upload twin of transpose_to_channel_major)
+__global__ void transpose_from_channel_major(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int rows, int C, int Cpad) {
+    __shared__ unsigned tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < C) tile[j][threadIdx.x] = src[(size_t)c * rows + r];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < C) dst[(size_t)r * Cpad + c] = tile[threadIdx.x][j];
+    }
+}
+
+static int frames_codec(const uint8_t* h_in, int nbytes, int nchan, int nframes, uint8_t* h_out, uint8_t* h_crc_ok, int device, bool encode) {
+    if (!h_in || !h_out || nchan < 1 || nframes < 1) return fail(QPSK_B200_ERR_ARG, "bad argument");
+    if (nbytes != 16 && nbytes != 32) return fail(QPSK_B200_ERR_ARG, "frame codec supports 16- and 32-byte frames, got %d", nbytes);
+    int rc = check_device(device);
+    if (rc) return rc;
+    const int W = nbytes / 4, rows = nframes * W, Cpad = (nchan + 31) / 32 * 32;
+    const size_t words = (size_t)rows * Cpad, bytes_cm = (size_t)nchan * rows * 4;
+    DevBuf cm, a, b, ok, cnt, okcm;
+    CU(cudaMalloc(&cm.p, bytes_cm));
+    CU(cudaMalloc(&a.p, words * 4));
+    CU(cudaMalloc(&b.p, words * 4));
+    CU(cudaMemcpy(cm.p, h_in, bytes_cm, cudaMemcpyHostToDevice));
+    dim3 tgrid((nchan + 31) / 32, (rows + 31) / 32), tblock(32, 8);
+    transpose_from_channel_major<<<tgrid, tblock>>>((const unsigned*)cm.p, (unsigned*)a.p, rows, nchan, Cpad);
+    CU(cudaGetLastError());
+    rc = upload_keystream(nbytes, 0);
+    if (rc) return rc;
+    if (encode) {
+        FrameEncodeArgs ea;
+        ea.payload_t = (const unsigned*)a.p; ea.dibits_t = (unsigned*)b.p; ea.C = nchan; ea.Cpad = Cpad; ea.F = nframes;
+        dim3 grid((nchan + 127) / 128, nframes);
+        if (nbytes == 32) frame_encode_kernel<32><<<grid, 128>>>(ea); else frame_encode_kernel<16><<<grid, 128>>>(ea);
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMalloc(&ok.p, (size_t)nframes * Cpad));
+        CU(cudaMalloc(&cnt.p, 2 * sizeof(unsigned long long)));
+        CU(cudaMemset(cnt.p, 0, 2 * sizeof(unsigned long long)));
+        rc = launch_frame_decode(nbytes, (const unsigned*)a.p, (unsigned*)b.p, (uint8_t*)ok.p, (unsigned long long*)cnt.p, nchan, Cpad, nframes, 0);
+        if (rc) return rc;
+    }
+    transpose_to_channel_major<unsigned><<<tgrid, tblock>>>((const unsigned*)b.p, (unsigned*)cm.p, rows, nchan, Cpad);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(h_out, cm.p, bytes_cm, cudaMemcpyDeviceToHost));
+    if (!encode && h_crc_ok) {
+        CU(cudaMalloc(&okcm.p, (size_t)nchan * nframes));
+        dim3 g2((nchan + 31) / 32, (nframes + 31) / 32);
+        transpose_to_channel_major<uint8_t><<<g2, tblock>>>((const uint8_t*)ok.p, (uint8_t*)okcm.p, nframes, nchan, Cpad);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(h_crc_ok, okcm.p, (size_t)nchan * nframes, cudaMemcpyDeviceToHost));
+    }
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_frames_encode(const uint8_t* h_payload, int nbytes, int nchan, int nframes, uint8_t* h_dibits, int device) {
+    return frames_codec(h_payload, nbytes, nchan, nframes, h_dibits, nullptr, device, true);
+}
+
+extern "C" int qpsk_b200_frames_decode(const uint8_t* h_dibits, int nbytes, int nchan, int nframes, uint8_t* h_frames, uint8_t* h_crc_ok, int device) {
+    return frames_codec(h_dibits, nbytes, nchan, nframes, h_frames, h_crc_ok, device, false);
 }

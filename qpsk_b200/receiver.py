@@ -13,7 +13,7 @@ from . import _capi as capi
 
 class Receiver:
     def __init__(self, nchan, max_frames, rs=2400.0, mode=capi.MODE_EXACT, ub_mode=capi.UB_ALIAS,
-                 keep_fir=False, keep_symbols=False, device=0, loop_bw=None, center=1500.0):
+                 keep_fir=False, keep_symbols=False, decode_frames=False, device=0, loop_bw=None, center=1500.0):
         self.L = capi.lib()
         cfg = capi.RxConfig()
         self.L.qpsk_b200_rx_default_config(C.byref(cfg))
@@ -21,7 +21,8 @@ class Receiver:
         cfg.center = center
         cfg.mode = mode
         cfg.ub_mode = ub_mode
-        cfg.flags = (capi.KEEP_FIR if keep_fir else 0) | (capi.KEEP_SYMBOLS if keep_symbols else 0)
+        cfg.flags = ((capi.KEEP_FIR if keep_fir else 0) | (capi.KEEP_SYMBOLS if keep_symbols else 0)
+                     | (capi.DECODE_FRAMES if decode_frames else 0))
         cfg.device = device
         if loop_bw is not None:
             cfg.loop_bw = loop_bw
@@ -80,6 +81,8 @@ class Receiver:
             capi.OUT_SYMBOLS: ((Cn, F * S), np.complex64),
             capi.OUT_FIR: ((Cn, F * N), np.complex64),
             capi.OUT_TAPS: ((self.cfg.ntaps,), np.float32),
+            capi.OUT_FRAMES: ((Cn, F, S // 4), np.uint8),
+            capi.OUT_CRC_OK: ((Cn, F), np.uint8),
         }
         shape, dt = shapes[what]
         out = np.empty(shape, dt)
@@ -90,6 +93,11 @@ class Receiver:
         """Unpacked dibits uint8 [C, F*nsym] (bits[0] | bits[1] << 1 of qpsk_demod, qpsk.c:74-79)."""
         p = self.read(capi.OUT_DIBITS)
         return unpack_dibits(p)
+
+    def crc_counters(self):
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        capi.check(self.L.qpsk_b200_rx_crc_counters(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def kernel_ms(self):
         a, b = C.c_float(), C.c_float()
