@@ -176,6 +176,24 @@ int qpsk_b200_frames_decode(const uint8_t *h_dibits, int nbytes, int nchan, int 
 /* counters accumulated by DECODE_FRAMES since create/reset: frames examined and CRC passes */
 int qpsk_b200_rx_crc_counters(qpsk_b200_rx *rx, unsigned long long *frames, unsigned long long *passes);
 
+/* ------------------------------------------------------------------------------------------
+ * Batched transmit path  (qpsk_packet_mod / tx_frame / qpsk_mod, qpsk.c:58-63, 225-285)
+ * Bit-exact PCM.  Also the on-device synthetic-signal generator for the receiver benchmarks.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct qpsk_b200_tx qpsk_b200_tx;
+
+/* carrier_hz[nchan]: each channel's fbb_tx_rect = cmplx(TAU * carrier / FS) (qpsk.c:320 uses CENTER + 50).
+ * packet_symbols: symbols per qpsk_packet_mod call (qpsk.c:329 uses FRAME_SIZE/2 = 256); the up-mix
+ * phasor is renormalised at every packet end (qpsk.c:253).  rs selects 2400 (sps 4) or 1200 (sps 8). */
+int qpsk_b200_tx_create(float fs, float rs, float rrc_alpha, const float *carrier_hz, int nchan, int packet_symbols,
+                        int device, qpsk_b200_tx **out);
+int qpsk_b200_tx_destroy(qpsk_b200_tx *tx);
+int qpsk_b200_tx_reset(qpsk_b200_tx *tx);
+/* symbols: uint8 [C][nsym], constellation index per symbol = (tx_bits[2k] << 1) | tx_bits[2k+1] (qpsk.c:270,278-279);
+ * pcm: int16 [C][nsym*sps].  nsym must be a multiple of 128/sps.  Device pointers, asynchronous. */
+int qpsk_b200_tx_process_device(qpsk_b200_tx *tx, const uint8_t *d_symbols, int nsym, int16_t *d_pcm, void *cuda_stream);
+int qpsk_b200_tx_process_host(qpsk_b200_tx *tx, const uint8_t *h_symbols, int nsym, int16_t *h_pcm);
+
 #ifdef __cplusplus
 }
 #endif

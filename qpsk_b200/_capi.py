@@ -55,6 +55,7 @@ def lib():
     _bind_fir(L)
     _bind_fft(L)
     _bind_bits(L)
+    _bind_tx(L)
     _lib = L
     return L
 
@@ -93,3 +94,11 @@ def _bind_bits(L):
     L.qpsk_b200_frames_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.qpsk_b200_frames_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.qpsk_b200_rx_crc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+
+
+def _bind_tx(L):
+    L.qpsk_b200_tx_create.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.qpsk_b200_tx_destroy.argtypes = [C.c_void_p]
+    L.qpsk_b200_tx_reset.argtypes = [C.c_void_p]
+    L.qpsk_b200_tx_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.qpsk_b200_tx_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

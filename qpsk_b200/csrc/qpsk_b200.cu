@@ -15,6 +15,7 @@
 #include "fir.cuh"
 #include "fft.cuh"
 #include "bits.cuh"
+#include "tx.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -916,4 +917,131 @@ extern "C" int qpsk_b200_frames_encode(const uint8_t* h_payload, int nbytes, int
 
 extern "C" int qpsk_b200_frames_decode(const uint8_t* h_dibits, int nbytes, int nchan, int nframes, uint8_t* h_frames, uint8_t* h_crc_ok, int device) {
     return frames_codec(h_dibits, nbytes, nchan, nframes, h_frames, h_crc_ok, device, false);
+}
+
+// =============================================================================================
+// batched transmit path
+// =============================================================================================
+struct qpsk_b200_tx {
+    long long id;
+    int C, Cpad, sps, ntaps, packet_samples, sample_pos, device;
+    float taps[QPSK_MAX_TAPS];
+    float2* d_phase;     // [Cpad]
+    float2* d_rect;      // [Cpad]
+    float2* d_hist;      // [Cpad][128/sps]
+    uint8_t* d_sym_stage;  int16_t* d_pcm_stage;  size_t stage_syms;
+    cudaStream_t stream;
+};
+
+extern "C" int qpsk_b200_tx_destroy(qpsk_b200_tx* tx) {
+    if (!tx) return 0;
+    cudaSetDevice(tx->device);
+    void* ptrs[] = { tx->d_phase, tx->d_rect, tx->d_hist, tx->d_sym_stage, tx->d_pcm_stage };
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (tx->stream) cudaStreamDestroy(tx->stream);
+    delete tx;
+    return 0;
+}
+
+extern "C" int qpsk_b200_tx_reset(qpsk_b200_tx* tx) {
+    if (!tx) return fail(QPSK_B200_ERR_ARG, "null transmitter");
+    CU(cudaSetDevice(tx->device));
+    float c0[2];
+    qpsk_host_cis(0.0, 0, c0);                                                  // qpsk.c:316 fbb_tx_phase = cmplx(0)
+    float2* ph = new float2[tx->Cpad];
+    for (int i = 0; i < tx->Cpad; i++) ph[i] = make_float2(c0[0], c0[1]);
+    cudaError_t e = cudaMemcpy(tx->d_phase, ph, sizeof(float2) * tx->Cpad, cudaMemcpyHostToDevice);
+    delete[] ph;
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "tx reset failed: %s", cudaGetErrorString(e));
+    CU(cudaMemset(tx->d_hist, 0, sizeof(float2) * tx->Cpad * (QPSK_CHUNK / tx->sps)));
+    tx->sample_pos = 0;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_tx_create(float fs, float rs, float rrc_alpha, const float* carrier_hz, int nchan, int packet_symbols,
+                                   int device, qpsk_b200_tx** out) {
+    if (!carrier_hz || !out) return fail(QPSK_B200_ERR_ARG, "null argument");
+    *out = nullptr;
+    const int sps = (int)((double)fs / (double)rs);
+    if (sps != 4 && sps != 8) return fail(QPSK_B200_ERR_ARG, "samples/symbol %d unsupported (4 or 8)", sps);
+    if (nchan < 1 || packet_symbols < 1 || (packet_symbols * sps) % QPSK_CHUNK != 0)
+        return fail(QPSK_B200_ERR_ARG, "packet_symbols*sps must be a positive multiple of %d", QPSK_CHUNK);
+    int rc = check_device(device);
+    if (rc) return rc;
+    qpsk_b200_tx* tx = new (std::nothrow) qpsk_b200_tx();
+    if (!tx) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+    memset(tx, 0, sizeof *tx);
+    tx->id = g_next_id++;
+    tx->C = nchan; tx->Cpad = (nchan + 31) / 32 * 32; tx->sps = sps; tx->ntaps = 127; tx->device = device;
+    tx->packet_samples = packet_symbols * sps;
+    qpsk_host_rrc_make(tx->taps, tx->ntaps, fs, rs, rrc_alpha);                 // qpsk.c:308
+    float2* rect = new float2[tx->Cpad];
+    for (int i = 0; i < tx->Cpad; i++) {
+        float t2[2];
+        qpsk_host_cis(kTau * (double)carrier_hz[i < nchan ? i : nchan - 1] / (double)fs, 0, t2);   // qpsk.c:320
+        rect[i] = make_float2(t2[0], t2[1]);
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&tx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&tx->d_phase, sizeof(float2) * tx->Cpad);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&tx->d_rect, sizeof(float2) * tx->Cpad);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&tx->d_hist, sizeof(float2) * tx->Cpad * (QPSK_CHUNK / sps));
+    if (e == cudaSuccess) e = cudaMemcpy(tx->d_rect, rect, sizeof(float2) * tx->Cpad, cudaMemcpyHostToDevice);
+    delete[] rect;
+    if (e != cudaSuccess) { qpsk_b200_tx_destroy(tx); return fail(QPSK_B200_ERR_CUDA, "allocating transmitter state failed: %s", cudaGetErrorString(e)); }
+    rc = qpsk_b200_tx_reset(tx);
+    if (rc) { qpsk_b200_tx_destroy(tx); return rc; }
+    *out = tx;
+    return QPSK_B200_OK;
+}
+
+template <int SPS>
+static cudaError_t launch_tx(const TxArgs& a, cudaStream_t s) {
+    const size_t smem = sizeof(TxSmem<SPS>);
+    cudaError_t e = cudaFuncSetAttribute(tx_kernel<127, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tx_kernel<127, SPS><<<a.Cpad / QPSK_GROUP, 256, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+extern "C" int qpsk_b200_tx_process_device(qpsk_b200_tx* tx, const uint8_t* d_symbols, int nsym, int16_t* d_pcm, void* cuda_stream) {
+    if (!tx || !d_symbols || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
+    const int ts = QPSK_CHUNK / tx->sps;
+    if (nsym < ts || nsym % ts != 0) return fail(QPSK_B200_ERR_ARG, "nsym %d must be a positive multiple of %d", nsym, ts);
+    CU(cudaSetDevice(tx->device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : tx->stream;
+    if (g_taps_owner != tx->id) {
+        float2 t2[QPSK_MAX_TAPS];
+        for (int i = 0; i < tx->ntaps; i++) t2[i] = make_float2(tx->taps[i], tx->taps[i]);
+        CU(cudaMemcpyToSymbolAsync(c_taps2, t2, sizeof(float2) * tx->ntaps, 0, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));
+        g_taps_owner = tx->id;
+    }
+    TxArgs a;
+    a.symbols = d_symbols; a.pcm = d_pcm; a.phase_state = tx->d_phase; a.rect = tx->d_rect; a.sym_hist = tx->d_hist;
+    a.C = tx->C; a.Cpad = tx->Cpad; a.nsym = nsym; a.packet_samples = tx->packet_samples; a.sample_pos = tx->sample_pos;
+    cudaError_t e = tx->sps == 4 ? launch_tx<4>(a, s) : launch_tx<8>(a, s);
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "tx kernel launch failed: %s", cudaGetErrorString(e));
+    tx->sample_pos = (tx->sample_pos + nsym * tx->sps) % tx->packet_samples;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_tx_process_host(qpsk_b200_tx* tx, const uint8_t* h_symbols, int nsym, int16_t* h_pcm) {
+    if (!tx || !h_symbols || !h_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nsym < 1) return fail(QPSK_B200_ERR_ARG, "nsym must be positive");
+    CU(cudaSetDevice(tx->device));
+    const size_t syms = (size_t)tx->C * nsym;
+    if (tx->stage_syms < syms) {
+        if (tx->d_sym_stage) cudaFree(tx->d_sym_stage);
+        if (tx->d_pcm_stage) cudaFree(tx->d_pcm_stage);
+        tx->d_sym_stage = nullptr; tx->d_pcm_stage = nullptr; tx->stage_syms = 0;
+        CU(cudaMalloc((void**)&tx->d_sym_stage, syms));
+        CU(cudaMalloc((void**)&tx->d_pcm_stage, syms * tx->sps * sizeof(int16_t)));
+        tx->stage_syms = syms;
+    }
+    CU(cudaMemcpyAsync(tx->d_sym_stage, h_symbols, syms, cudaMemcpyHostToDevice, tx->stream));
+    int rc = qpsk_b200_tx_process_device(tx, tx->d_sym_stage, nsym, tx->d_pcm_stage, tx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_pcm, tx->d_pcm_stage, syms * tx->sps * sizeof(int16_t), cudaMemcpyDeviceToHost, tx->stream));
+    CU(cudaStreamSynchronize(tx->stream));
+    return QPSK_B200_OK;
 }

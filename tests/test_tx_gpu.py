@@ -1,0 +1,69 @@
+"""Batched transmit path against the oracle's restatement of qpsk_packet_mod/tx_frame (pinned to the
+reference by tests/test_oracle_golden.py) and the reference golden PCM: bit-exact int16."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reference_golden_pcm(golden):
+    import qpsk_b200
+    g = golden["rx_2400"]
+    tx = qpsk_b200.Transmitter([1550.0])
+    pcm = tx.modulate(qpsk_b200.bits_to_symbols(g["bits"]).reshape(1, -1))
+    assert np.array_equal(pcm[0], g["pcm"][0])
+    assert pcm[0, :8].tolist() == [4, -5, -3, 5, 3, 0, 5, 5] and pcm[0, 300:304].tolist() == [-8227, -7540, 10105, 13816]
+    tx.close()
+
+
+@pytest.mark.parametrize("rs,nchan,npackets", [(2400.0, 37, 3), (1200.0, 64, 2), (2400.0, 1, 5)])
+def test_pcm_bit_exact_vs_oracle_with_streaming(oracle_lib, rs, nchan, npackets):
+    import qpsk_b200
+    o = oracle_lib.Oracle(rs=rs)
+    rng = np.random.default_rng(int(rs) + nchan)
+    carriers = (1500.0 + rng.uniform(-75, 75, nchan)).astype(np.float32)
+    bits = rng.integers(0, 2, (nchan, npackets, 512), dtype=np.int32)
+    want = np.zeros((nchan, npackets * 256 * o.sps), np.int16)
+    for c in range(nchan):
+        st = o.new_tx(float(carriers[c]))
+        want[c] = np.concatenate([o.packet_mod(st, bits[c, k]) for k in range(npackets)])
+    tx = qpsk_b200.Transmitter(carriers, rs=rs)
+    syms = qpsk_b200.bits_to_symbols(bits.reshape(nchan, -1))
+    whole = tx.modulate(syms)
+    assert np.array_equal(whole, want)
+    # the same stream in ragged calls: filter history, phasor and packet position carry over
+    tx.reset()
+    step = 128 // o.sps
+    cuts = [0, step, 5 * step, 256, syms.shape[1]]
+    parts = [tx.modulate(syms[:, a:b]) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    assert np.array_equal(np.concatenate(parts, axis=1), want)
+    tx.close()
+
+
+def test_tx_then_rx_loopback_is_what_the_reference_does(oracle_lib):
+    """The reference's experiment (qpsk.c:289-359) on the GPU end to end: modulate at CENTER+50 Hz,
+    receive, and compare the decisions with the oracle receiving the oracle's PCM."""
+    import qpsk_b200
+    o = oracle_lib.Oracle()
+    rng = np.random.default_rng(50)
+    bits = rng.integers(0, 2, (4, 8 * 512), dtype=np.int32)
+    tx = qpsk_b200.Transmitter([1550.0] * 4)
+    pcm = tx.modulate(qpsk_b200.bits_to_symbols(bits))
+    rx = qpsk_b200.Receiver(4, pcm.shape[1] // 512)
+    got = qpsk_b200.unpack_dibits(rx.rx_frames(pcm))
+    want = o.rx_run(pcm, want=("dibit", "freq"))
+    assert np.array_equal(got, want["dibit"])
+    hz = want["freq"][:, -1] * 2400.0 / (2 * np.pi)
+    assert np.all(np.abs(hz - 50.0) < 2.0)          # the loop acquires the +50 Hz offset (f = 0.1309 rad/sym)
+    tx.close(); rx.close()
+
+
+def test_tx_rejects_ragged_symbol_counts():
+    import ctypes as C
+    import qpsk_b200
+    from qpsk_b200 import capi
+    tx = qpsk_b200.Transmitter([1500.0])
+    s = np.zeros((1, 33), np.uint8)
+    pcm = np.zeros((1, 33 * 4), np.int16)
+    assert capi.lib().qpsk_b200_tx_process_host(tx.h, s.ctypes.data_as(C.c_void_p), 33, pcm.ctypes.data_as(C.c_void_p)) == -1
+    tx.close()
