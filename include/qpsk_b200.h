@@ -17,7 +17,7 @@
  *        slicer                   qpsk_demod()         qpsk.c:74-79
  *   qpsk_b200_fir_*          <->  rrc_fir()/rrc_make() rrc_fir.h:16-17
  *   qpsk_b200_fft_*          <->  fftn()/ifftn()       algorithms/fft.h:46-49 (+ |X|^2 argmax)
- *   qpsk_b200_bits_*         <->  scramble()/interleave()/crc16()  algorithms/*.h
+ *   qpsk_b200_bits_*         <->  scramble()/interleave()/crc16()  algorithms/{bit-scramble,interleave,crc16}.h
  *   qpsk_b200_tx_*           <->  qpsk_packet_mod()/tx_frame()     qpsk.c:225-285
  *
  * The single-channel drop-in symbols of the reference headers (rrc_fir, rrc_make, the 22
@@ -101,6 +101,11 @@ int qpsk_b200_rx_process_device(qpsk_b200_rx *rx, const int16_t *d_pcm, int nfra
  * (h_dibits may be NULL) and returns when done. */
 int qpsk_b200_rx_process_host(qpsk_b200_rx *rx, const int16_t *h_pcm, int nframes, uint8_t *h_dibits);
 int qpsk_b200_rx_sync(qpsk_b200_rx *rx);
+/* the loop's gains and limits (set_alpha/set_beta/set_min_freq/set_max_freq of costas_loop.h:26-32), all channels */
+int qpsk_b200_rx_set_loop(qpsk_b200_rx *rx, float alpha, float beta, float min_freq, float max_freq);
+/* per-channel (d_phase, d_freq) pairs, float [C][2] (set_phase/set_frequency/get_phase/get_frequency) */
+int qpsk_b200_rx_get_loop_state(qpsk_b200_rx *rx, float *h_phase_freq);
+int qpsk_b200_rx_set_loop_state(qpsk_b200_rx *rx, const float *h_phase_freq);
 
 /* download one output of the most recent process call, channel-major, `bytes` = exact size */
 int qpsk_b200_rx_read(qpsk_b200_rx *rx, int what, void *h_dst, size_t bytes);
@@ -193,6 +198,10 @@ int qpsk_b200_tx_reset(qpsk_b200_tx *tx);
  * pcm: int16 [C][nsym*sps].  nsym must be a multiple of 128/sps.  Device pointers, asynchronous. */
 int qpsk_b200_tx_process_device(qpsk_b200_tx *tx, const uint8_t *d_symbols, int nsym, int16_t *d_pcm, void *cuda_stream);
 int qpsk_b200_tx_process_host(qpsk_b200_tx *tx, const uint8_t *h_symbols, int nsym, int16_t *h_pcm);
+/* end the current tx_frame call now: renormalise fbb_tx_phase (qpsk.c:253) and restart the packet position */
+int qpsk_b200_tx_end_packet(qpsk_b200_tx *tx);
+/* tx_frame(samples, symbol, length) itself: arbitrary complex symbols, float [C][nsym][2] in host memory */
+int qpsk_b200_tx_symbols_host(qpsk_b200_tx *tx, const float *h_symbols, int nsym, int16_t *h_pcm);
 
 #ifdef __cplusplus
 }

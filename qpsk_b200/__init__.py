@@ -8,5 +8,5 @@ from ._capi import QpskB200Error  # noqa: F401
 from .receiver import Receiver, unpack_dibits  # noqa: F401
 from .fir import Fir, rrc_make  # noqa: F401
 from .fft import Fft  # noqa: F401
-from . import bits  # noqa: F401
+from . import bits, shard  # noqa: F401
 from .transmitter import Transmitter, bits_to_symbols  # noqa: F401

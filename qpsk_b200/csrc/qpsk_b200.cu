@@ -329,6 +329,28 @@ extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pc
     return QPSK_B200_OK;
 }
 
+extern "C" int qpsk_b200_rx_set_loop(qpsk_b200_rx* rx, float alpha, float beta, float min_freq, float max_freq) {
+    if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
+    rx->loop.alpha = alpha; rx->loop.beta = beta; rx->loop.min_freq = min_freq; rx->loop.max_freq = max_freq;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_rx_get_loop_state(qpsk_b200_rx* rx, float* h_phase_freq) {
+    if (!rx || !h_phase_freq) return fail(QPSK_B200_ERR_ARG, "null argument");
+    CU(cudaSetDevice(rx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h_phase_freq, rx->d_loop_state, (size_t)rx->C * sizeof(float2), cudaMemcpyDeviceToHost));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_rx_set_loop_state(qpsk_b200_rx* rx, const float* h_phase_freq) {
+    if (!rx || !h_phase_freq) return fail(QPSK_B200_ERR_ARG, "null argument");
+    CU(cudaSetDevice(rx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(rx->d_loop_state, h_phase_freq, (size_t)rx->C * sizeof(float2), cudaMemcpyHostToDevice));
+    return QPSK_B200_OK;
+}
+
 extern "C" int qpsk_b200_rx_sync(qpsk_b200_rx* rx) {
     if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
     CU(cudaSetDevice(rx->cfg.device));
@@ -1003,8 +1025,8 @@ static cudaError_t launch_tx(const TxArgs& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-extern "C" int qpsk_b200_tx_process_device(qpsk_b200_tx* tx, const uint8_t* d_symbols, int nsym, int16_t* d_pcm, void* cuda_stream) {
-    if (!tx || !d_symbols || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
+static int tx_run(qpsk_b200_tx* tx, const uint8_t* d_symbols, const float2* d_symbols_cf, int nsym, int16_t* d_pcm, void* cuda_stream) {
+    if (!tx || (!d_symbols && !d_symbols_cf) || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
     const int ts = QPSK_CHUNK / tx->sps;
     if (nsym < ts || nsym % ts != 0) return fail(QPSK_B200_ERR_ARG, "nsym %d must be a positive multiple of %d", nsym, ts);
     CU(cudaSetDevice(tx->device));
@@ -1017,11 +1039,31 @@ extern "C" int qpsk_b200_tx_process_device(qpsk_b200_tx* tx, const uint8_t* d_sy
         g_taps_owner = tx->id;
     }
     TxArgs a;
-    a.symbols = d_symbols; a.pcm = d_pcm; a.phase_state = tx->d_phase; a.rect = tx->d_rect; a.sym_hist = tx->d_hist;
+    a.symbols = d_symbols; a.symbols_cf = d_symbols_cf; a.pcm = d_pcm; a.phase_state = tx->d_phase; a.rect = tx->d_rect; a.sym_hist = tx->d_hist;
     a.C = tx->C; a.Cpad = tx->Cpad; a.nsym = nsym; a.packet_samples = tx->packet_samples; a.sample_pos = tx->sample_pos;
     cudaError_t e = tx->sps == 4 ? launch_tx<4>(a, s) : launch_tx<8>(a, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "tx kernel launch failed: %s", cudaGetErrorString(e));
     tx->sample_pos = (tx->sample_pos + nsym * tx->sps) % tx->packet_samples;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_tx_process_device(qpsk_b200_tx* tx, const uint8_t* d_symbols, int nsym, int16_t* d_pcm, void* cuda_stream) {
+    return tx_run(tx, d_symbols, nullptr, nsym, d_pcm, cuda_stream);
+}
+
+extern "C" int qpsk_b200_tx_symbols_host(qpsk_b200_tx* tx, const float* h_symbols, int nsym, int16_t* h_pcm) {
+    if (!tx || !h_symbols || !h_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nsym < 1) return fail(QPSK_B200_ERR_ARG, "nsym must be positive");
+    CU(cudaSetDevice(tx->device));
+    const size_t syms = (size_t)tx->C * nsym;
+    DevBuf ds, dp;
+    CU(cudaMalloc(&ds.p, syms * sizeof(float2)));
+    CU(cudaMalloc(&dp.p, syms * tx->sps * sizeof(int16_t)));
+    CU(cudaMemcpyAsync(ds.p, h_symbols, syms * sizeof(float2), cudaMemcpyHostToDevice, tx->stream));
+    int rc = tx_run(tx, nullptr, (const float2*)ds.p, nsym, (int16_t*)dp.p, tx->stream);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_pcm, dp.p, syms * tx->sps * sizeof(int16_t), cudaMemcpyDeviceToHost, tx->stream));
+    CU(cudaStreamSynchronize(tx->stream));
     return QPSK_B200_OK;
 }
 
@@ -1043,5 +1085,26 @@ extern "C" int qpsk_b200_tx_process_host(qpsk_b200_tx* tx, const uint8_t* h_symb
     if (rc) return rc;
     CU(cudaMemcpyAsync(h_pcm, tx->d_pcm_stage, syms * tx->sps * sizeof(int16_t), cudaMemcpyDeviceToHost, tx->stream));
     CU(cudaStreamSynchronize(tx->stream));
+    return QPSK_B200_OK;
+}
+
+__global__ void tx_normalise_kernel(float2* __restrict__ phase, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float2 ph = phase[c];
+    const double dr = (double)ph.x, di = (double)ph.y;                 // qpsk.c:253 with glibc hypotf semantics
+    const float mag = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(di, di))));
+    phase[c] = make_float2(__fdiv_rn(ph.x, mag), __fdiv_rn(ph.y, mag));
+}
+
+extern "C" int qpsk_b200_tx_end_packet(qpsk_b200_tx* tx) {
+    if (!tx) return fail(QPSK_B200_ERR_ARG, "null transmitter");
+    CU(cudaSetDevice(tx->device));
+    if (tx->sample_pos != 0) {     // not already normalised by a packet boundary inside the last call
+        tx_normalise_kernel<<<(tx->Cpad + 127) / 128, 128, 0, tx->stream>>>(tx->d_phase, tx->Cpad);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(tx->stream));
+        tx->sample_pos = 0;
+    }
     return QPSK_B200_OK;
 }

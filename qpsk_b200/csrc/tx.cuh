@@ -13,6 +13,7 @@
 
 struct TxArgs {
     const uint8_t* symbols;   // [C][nsym] constellation index per symbol: (tx_bits[2k] << 1) | tx_bits[2k+1]
+    const float2* symbols_cf; // or, when non-null, arbitrary complex symbols [C][nsym] (tx_frame's own argument)
     int16_t* pcm;             // [C][nsym*SPS]
     float2* phase_state;      // [Cpad] fbb_tx_phase
     const float2* rect;       // [Cpad] fbb_tx_rect = cmplx(TAU * carrier / FS)
@@ -66,7 +67,8 @@ __global__ void __launch_bounds__(256, 1) tx_kernel(const TxArgs a) {
         for (int e = 0; e < SPT; e++) {
             const int i = w * SPT + e;
             srow[i] = srow[TS + i];
-            srow[TS + i] = point(symrow[(size_t)k * TS + i] & 3u);
+            if (a.symbols_cf != nullptr) srow[TS + i] = reinterpret_cast<const u64*>(a.symbols_cf)[(size_t)chl * a.nsym + (size_t)k * TS + i];
+            else srow[TS + i] = point(symrow[(size_t)k * TS + i] & 3u);
         }
         __syncthreads();
 
