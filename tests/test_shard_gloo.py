@@ -32,7 +32,7 @@ def _worker(rank, world, port, pcm_path, out_dir):
     start, count = partition(pcm.shape[0], world, rank)
     o = oracle.Oracle()
     out = o.rx_run(pcm[start:start + count], want=("dibit", "freq"))
-    stats = reduce_stats([out["dibit"].size, float(np.abs(out["freq"][:, -1]).sum()), count])
+    stats = reduce_stats([out["dibit"].size, float(np.abs(out["freq"][:, -1].astype(np.float64)).sum()), count])
     worst = max_over_ranks(10.0 + rank)
     np.save(os.path.join(out_dir, "dibit_%d.npy" % rank), out["dibit"])
     if rank == 0:
@@ -55,4 +55,4 @@ def test_two_rank_sharding_matches_single_rank(oracle_lib, tmp_path):
     assert np.array_equal(both, single["dibit"])
     stats = np.load(tmp_path / "stats.npy")
     assert stats[0] == single["dibit"].size and stats[2] == 5 and stats[3] == 11.0
-    assert stats[1] == pytest.approx(float(np.abs(single["freq"][:, -1]).sum()), rel=1e-12)
+    assert stats[1] == pytest.approx(float(np.abs(single["freq"][:, -1].astype(np.float64)).sum()), rel=1e-12)
