@@ -49,7 +49,9 @@ enum { QPSK_B200_UB_ALIAS = 0,     /* reproduce the Makefile-build out-of-frame 
 enum {                              /* cfg.flags */
     QPSK_B200_KEEP_FIR = 1,         /* keep the matched-filter output (16 B/sample!) for parity checks */
     QPSK_B200_KEEP_SYMBOLS = 2,     /* keep the derotated symbols (costas_frame) */
-    QPSK_B200_DECODE_FRAMES = 4     /* run descramble -> de-interleave -> CRC16 on every frame's dibits */
+    QPSK_B200_DECODE_FRAMES = 4,    /* run descramble -> de-interleave -> CRC16 on every frame's dibits */
+    QPSK_B200_NO_FUSE = 8           /* always run the Costas loop as its own kernel (it is fused into the front end
+                                       whenever a CTA owns whole streams, i.e. when channels are plentiful) */
 };
 
 typedef struct {

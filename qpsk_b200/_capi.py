@@ -22,7 +22,7 @@ class RxConfig(C.Structure):
 
 MODE_EXACT, MODE_FAST = 0, 1
 UB_ALIAS, UB_CLAMP = 0, 1
-KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES = 1, 2, 4
+KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE = 1, 2, 4, 8
 OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK = range(9)
 
 _lib = None

@@ -59,7 +59,7 @@ struct qpsk_b200_rx {
     qpsk_host_loop loop;
     cudaStream_t stream;
     cudaEvent_t ev[4];
-    bool timed;
+    bool timed, last_fused, no_fuse;
     long long launches;
     // device state
     int16_t* d_pcm_tail;    // [Cpad][128]
@@ -124,7 +124,7 @@ static cudaError_t launch_front(const RxFrontArgs& a, int grid, cudaStream_t s) 
     const size_t smem = sizeof(RxFrontSmem<SPS>);
     cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<NTAPS, SPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    rx_front_kernel<NTAPS, SPS, MODE><<<grid, 256, smem, s>>>(a);
+    rx_front_kernel<NTAPS, SPS, MODE><<<grid, QPSK_FRONT_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -149,6 +149,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (!rx) return fail(QPSK_B200_ERR_ARG, "out of host memory");
     memset(rx, 0, sizeof *rx);
     rx->cfg = *cfg;
+    rx->no_fuse = (cfg->flags & QPSK_B200_NO_FUSE) != 0;
     rx->id = g_next_id++;
     rx->C = nchan;
     rx->Cpad = (nchan + QPSK_GROUP - 1) / QPSK_GROUP * QPSK_GROUP;
@@ -291,6 +292,19 @@ extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pc
     fa.frames_per_block = (F + fblocks - 1) / fblocks;
     fblocks = (F + fa.frames_per_block - 1) / fa.frames_per_block;
     const int grid = ngroups * fblocks;
+
+    // K3 arguments: the Costas loop + slicer, fused into K1 when every CTA owns whole streams
+    CostasArgs ca;
+    ca.dec_ring = rx->d_dec_ring; ca.index_t = rx->d_index_t; ca.loop_state = rx->d_loop_state;
+    ca.dibits_t = rx->d_dibits_t; ca.costas_dbg = rx->d_costas_dbg; ca.track_t = rx->d_track_t;
+    ca.C = rx->C; ca.Cpad = rx->Cpad; ca.F = F; ca.nsym = rx->nsym; ca.sps = rx->sps; ca.N = N;
+    ca.slot_base = rx->slot_base; ca.nslots = rx->nslots; ca.ub_mode = rx->cfg.ub_mode;
+    ca.alpha = rx->loop.alpha; ca.beta = rx->loop.beta; ca.max_freq = rx->loop.max_freq; ca.min_freq = rx->loop.min_freq;
+    ca.rot45 = rx->rot45;
+    const bool fused = (fblocks == 1) && !rx->no_fuse;
+    fa.fuse_costas = fused ? 1 : 0;
+    fa.costas = ca;
+
     CU(cudaEventRecord(rx->ev[0], s));
     cudaError_t e;
     const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
@@ -303,18 +317,14 @@ extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pc
     save_pcm_tail_kernel<<<(rx->C * 16 + 255) / 256, 256, 0, s>>>(d_pcm, rx->d_pcm_tail, rx->C, (size_t)F * N);
     CU(cudaGetLastError());
 
-    // K3: Costas loop + slicer
-    CostasArgs ca;
-    ca.dec_ring = rx->d_dec_ring; ca.index_t = rx->d_index_t; ca.loop_state = rx->d_loop_state;
-    ca.dibits_t = rx->d_dibits_t; ca.costas_dbg = rx->d_costas_dbg; ca.track_t = rx->d_track_t;
-    ca.C = rx->C; ca.Cpad = rx->Cpad; ca.F = F; ca.nsym = rx->nsym; ca.sps = rx->sps; ca.N = N;
-    ca.slot_base = rx->slot_base; ca.nslots = rx->nslots; ca.ub_mode = rx->cfg.ub_mode;
-    ca.alpha = rx->loop.alpha; ca.beta = rx->loop.beta; ca.max_freq = rx->loop.max_freq; ca.min_freq = rx->loop.min_freq;
-    ca.rot45 = rx->rot45;
     CU(cudaEventRecord(rx->ev[2], s));
-    costas_kernel<<<(rx->C + 127) / 128, 128, 0, s>>>(ca);
-    CU(cudaGetLastError());
+    if (!fused) {
+        costas_kernel<<<(rx->C + 127) / 128, 128, 0, s>>>(ca);
+        CU(cudaGetLastError());
+        rx->launches += 1;
+    }
     CU(cudaEventRecord(rx->ev[3], s));
+    rx->last_fused = fused;
 
     if (rx->d_frames_t) {   // K4: descramble -> de-interleave -> CRC16 per frame
         int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t, rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters, rx->C, rx->Cpad, F, s);
@@ -322,7 +332,7 @@ extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pc
         rx->launches += 1;
     }
 
-    rx->launches += 4;
+    rx->launches += 3;
     rx->timed = true;
     rx->slot_base = (rx->slot_base + F) % rx->nslots;
     rx->lastF = F;

@@ -22,55 +22,90 @@ struct CostasArgs {
     float2 rot45;            // cmplx(ROTATE45) from the host libm, qpsk.c:75
 };
 
+struct CostasParams {
+    float alpha, beta, max_freq, min_freq;
+    float2 rot45;
+};
+
+// one symbol of the loop: derotate, detect, update, wrap, clamp, slice.  Returns bits[0] | bits[1] << 1.
+__device__ __forceinline__ unsigned costas_symbol(const float2 d, float& phase, float& freq, const CostasParams& p, float2& y) {
+    float s, co;
+    sincosf_glibc(phase, s, co);                               // cmplxconj(get_phase()), qpsk.h:36
+    y = cmul_exact(d, make_float2(co, -s));                    // qpsk.c:197
+    // costas_loop.c:44-47: sign(I)*Q - sign(Q)*I with 0 -> -1
+    const float e = __fsub_rn((y.x > 0.0f ? y.y : -y.y), (y.y > 0.0f ? y.x : -y.x));
+    freq = __fadd_rn(freq, __fmul_rn(p.beta, e));              // costas_loop.c:57
+    phase = __fadd_rn(__fadd_rn(phase, freq), __fmul_rn(p.alpha, e));   // :58
+    // costas_loop.c:61-67: compares and subtracts in double against TAU
+    while ((double)phase > 6.283185307179586) phase = __double2float_rn(__dsub_rn((double)phase, 6.283185307179586));
+    while ((double)phase < -6.283185307179586) phase = __double2float_rn(__dadd_rn((double)phase, 6.283185307179586));
+    if (freq > p.max_freq) freq = p.max_freq;                  // :69-74
+    else if (freq < p.min_freq) freq = p.min_freq;
+    const float2 r = cmul_exact(y, p.rot45);                   // qpsk.c:74-79
+    return (r.x < 0.0f ? 1u : 0u) | (r.y < 0.0f ? 2u : 0u);
+}
+
+// One rx_frame call's worth of loop iterations for channel c (qpsk.c:196-212): consumes ring slot
+// (slot_base + f), after patching the last symbol of the frame this call produced (slot + 1).
+// CG loads bypass L1
+// for the fused kernel, where other warps of the same CTA have just written the ring.
+template <bool CG>
+__device__ __forceinline__ void costas_run_frame(const CostasArgs& a, const CostasParams& p, int f, int c, float& phase, float& freq) {
+    const size_t slot_elems = (size_t)a.nsym * a.Cpad;
+    const float2* cur = a.dec_ring + (size_t)((a.slot_base + f) % a.nslots) * slot_elems + c;
+    auto ld = [](const float2* q) -> float2 { return CG ? __ldcg(q) : *q; };
+    // Out-of-frame read of qpsk.c:190 (sps 4, index >= 4): in the Makefile build input_frame[512+k] is
+    // decimated_frame[k], which at that point already holds symbol k of the frame consumed now.
+    if (a.ub_mode == 0) {
+        const int idx = CG ? __ldcg(&a.index_t[(size_t)f * a.Cpad + c]) : a.index_t[(size_t)f * a.Cpad + c];
+        const int j = (a.nsym - 1) * a.sps + idx - a.N;
+        if (j >= 0) {
+            float2* nxt = a.dec_ring + (size_t)((a.slot_base + f + 1) % a.nslots) * slot_elems + c;
+            nxt[(size_t)(a.nsym - 1) * a.Cpad] = ld(cur + (size_t)j * a.Cpad);
+        }
+    }
+    // symbols are fetched four ahead of the recurrence; the loop stays rolled (four inlined symbol
+    // steps, ~9 KB) so that the Costas warp does not evict the filter loop from the instruction cache
+    const int groups = a.nsym / 4;
+    float2 d[4], dn[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) d[k] = ld(cur + (size_t)k * a.Cpad);
+    unsigned bits = 0u;
+#pragma unroll 1
+    for (int gq = 0; gq < groups; gq++) {
+        if (gq + 1 < groups) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) dn[k] = ld(cur + (size_t)((gq + 1) * 4 + k) * a.Cpad);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float2 y;
+            bits |= costas_symbol(d[k], phase, freq, p, y) << (2 * ((gq & 3) * 4 + k));
+            if (a.costas_dbg != nullptr) a.costas_dbg[((size_t)f * a.nsym + gq * 4 + k) * a.Cpad + c] = y;
+        }
+        if ((gq & 3) == 3) {                                   // 16 dibits per output word
+            a.dibits_t[((size_t)f * (a.nsym / 16) + (gq >> 2)) * a.Cpad + c] = bits;
+            bits = 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[k] = dn[k];
+    }
+    a.track_t[(size_t)f * a.Cpad + c] = make_float2(phase, freq);
+}
+
+__device__ __forceinline__ CostasParams costas_params(const CostasArgs& a) {
+    CostasParams p;
+    p.alpha = a.alpha; p.beta = a.beta; p.max_freq = a.max_freq; p.min_freq = a.min_freq; p.rot45 = a.rot45;
+    return p;
+}
+
 __global__ void __launch_bounds__(128) costas_kernel(const CostasArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.C) return;
-    float2 st = a.loop_state[c];
+    const CostasParams p = costas_params(a);
+    const float2 st = a.loop_state[c];
     float phase = st.x, freq = st.y;
-    const size_t slot_elems = (size_t)a.nsym * a.Cpad;
-    const int words = a.nsym / 16;
-
-    for (int f = 0; f < a.F; f++) {
-        const float2* cur = a.dec_ring + (size_t)((a.slot_base + f) % a.nslots) * slot_elems + c;
-        // Out-of-frame read of qpsk.c:190 (sps 4, index >= 4): in the Makefile build
-        // input_frame[512+k] is decimated_frame[k], which at that point already holds symbol k of
-        // the frame consumed now.  Patch the last symbol of the frame produced by this call.
-        if (a.ub_mode == 0) {
-            const int idx = a.index_t[(size_t)f * a.Cpad + c];
-            const int j = (a.nsym - 1) * a.sps + idx - a.N;
-            if (j >= 0) {
-                float2* nxt = a.dec_ring + (size_t)((a.slot_base + f + 1) % a.nslots) * slot_elems + c;
-                nxt[(size_t)(a.nsym - 1) * a.Cpad] = cur[(size_t)j * a.Cpad];
-            }
-        }
-        for (int wd = 0; wd < words; wd++) {
-            unsigned bits = 0u;
-#pragma unroll 4
-            for (int k = 0; k < 16; k++) {
-                const int i = wd * 16 + k;
-                const float2 d = cur[(size_t)i * a.Cpad];
-                float s, co;
-                sincosf_glibc(phase, s, co);                       // cmplxconj(get_phase()), qpsk.h:36
-                const float2 y = cmul_exact(d, make_float2(co, -s)); // qpsk.c:197
-                if (a.costas_dbg != nullptr)
-                    a.costas_dbg[((size_t)f * a.nsym + i) * a.Cpad + c] = y;
-                // costas_loop.c:44-47: sign(I)*Q - sign(Q)*I with 0 -> -1
-                const float e = __fsub_rn((y.x > 0.0f ? y.y : -y.y), (y.y > 0.0f ? y.x : -y.x));
-                freq = __fadd_rn(freq, __fmul_rn(a.beta, e));       // costas_loop.c:57
-                phase = __fadd_rn(__fadd_rn(phase, freq), __fmul_rn(a.alpha, e));   // :58
-                // costas_loop.c:61-67: compares and subtracts in double against TAU
-                while ((double)phase > 6.283185307179586) phase = __double2float_rn(__dsub_rn((double)phase, 6.283185307179586));
-                while ((double)phase < -6.283185307179586) phase = __double2float_rn(__dadd_rn((double)phase, 6.283185307179586));
-                if (freq > a.max_freq) freq = a.max_freq;           // :69-74
-                else if (freq < a.min_freq) freq = a.min_freq;
-                // qpsk.c:74-79
-                const float2 r = cmul_exact(y, a.rot45);
-                bits |= ((r.x < 0.0f ? 1u : 0u) | (r.y < 0.0f ? 2u : 0u)) << (2 * k);
-            }
-            a.dibits_t[((size_t)f * words + wd) * a.Cpad + c] = bits;
-        }
-        a.track_t[(size_t)f * a.Cpad + c] = make_float2(phase, freq);
-    }
+    for (int f = 0; f < a.F; f++) costas_run_frame<false>(a, p, f, c, phase, freq);
     a.loop_state[c] = make_float2(phase, freq);
 }
 

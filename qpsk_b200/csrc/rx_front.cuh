@@ -11,6 +11,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "rx_costas.cuh"
 
 enum { QPSK_MODE_EXACT = 0, QPSK_MODE_FAST = 1 };
 enum { QPSK_UB_ALIAS = 0, QPSK_UB_CLAMP = 1 };
@@ -56,22 +57,52 @@ __global__ void phasor_table_kernel(float2* __restrict__ table, float2* __restri
 // d - r, so walking d upwards accumulates every output oldest-tap-first from +0, exactly the
 // order of rrc_fir.c:22-26.
 // --------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void fir_tap(u64& acc, const u64 xv, const int i) {
+    const u64 cc = *reinterpret_cast<const u64*>(&c_taps2[i]);
+    if (MODE == QPSK_MODE_EXACT) acc = add2(acc, mul2_exact(xv, cc));
+    else acc = fma2(xv, cc, acc);
+}
+
+// The walk over d has a triangular head (d < R-1: only outputs 0..d are reached), a steady part
+// where every output takes a tap, and a triangular tail.  The steady part is a rolled loop of R
+// steps per trip: accumulators stay put, the sample address is base + immediate and the tap index
+// is (uniform loop base) + immediate, so nothing rotates and the body (R*R tap updates, ~8 KB of
+// code at R = 16) stays resident in the instruction cache -- the fully unrolled 70 KB version spent
+// 9 % of its issue slots waiting for instruction fetch (profiles/r01_rx_front_v2).
 template <int NTAPS, int R, int MODE>
 __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[R]) {
+    constexpr int STEADY = NTAPS - R + 1;            // d = R-1 .. NTAPS-1
+    constexpr int TRIPS = STEADY / R, REM = STEADY % R;
 #pragma unroll
-    for (int r = 0; r < R; r++) acc[r] = 0ull;   // (+0, +0)
+    for (int r = 0; r < R; r++) acc[r] = 0ull;       // (+0, +0)
 #pragma unroll
-    for (int d = 0; d < NTAPS - 1 + R; d++) {
+    for (int d = 0; d < R - 1; d++) {                // head
         const u64 xv = x[d];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int i = d - r;
-            if (i >= 0 && i < NTAPS) {
-                const u64 cc = *reinterpret_cast<const u64*>(&c_taps2[i]);
-                if (MODE == QPSK_MODE_EXACT) acc[r] = add2(acc[r], mul2_exact(xv, cc));
-                else acc[r] = fma2(xv, cc, acc[r]);
-            }
+        for (int r = 0; r <= d; r++) fir_tap<MODE>(acc[r], xv, d - r);
+    }
+#pragma unroll 1
+    for (int m = 0; m < TRIPS; m++) {                // steady, rolled
+        const int d0 = R - 1 + m * R;
+#pragma unroll
+        for (int e = 0; e < R; e++) {
+            const u64 xv = x[d0 + e];
+#pragma unroll
+            for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, d0 + e - r);
         }
+    }
+#pragma unroll
+    for (int d = R - 1 + TRIPS * R; d < R - 1 + TRIPS * R + REM; d++) {   // steady remainder
+        const u64 xv = x[d];
+#pragma unroll
+        for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, d - r);
+    }
+#pragma unroll
+    for (int d = NTAPS; d < NTAPS - 1 + R; d++) {    // tail
+        const u64 xv = x[d];
+#pragma unroll
+        for (int r = d - (NTAPS - 1); r < R; r++) fir_tap<MODE>(acc[r], xv, d - r);
     }
 }
 
@@ -86,6 +117,8 @@ struct RxFrontArgs {
     int frames_per_block;      // frames handled by one CTA
     int slot_base, nslots;     // frame f goes to ring slot (slot_base + 1 + f) % nslots
     int ub_mode;
+    int fuse_costas;           // 1: this CTA owns every frame of its channels, so its Costas warp runs the loop too
+    CostasArgs costas;         // used when fuse_costas
 };
 
 template <int SPS>
@@ -95,9 +128,21 @@ struct RxFrontSmem {
     u64 x[QPSK_GROUP][XS];        // [0,128) previous tile (halo), [128,256) current tile
     u64 out[QPSK_GROUP][OS];      // matched-filter output of the current frame
     float2 ph[2][QPSK_CHUNK];     // mixer phasors of the current / next tile
+    short pcm[QPSK_GROUP][QPSK_CHUNK + 8];   // cp.async landing zone for the next tile's PCM (row stride 272 B: conflict-free 16 B reads)
     u64 hist[2][QPSK_GROUP];      // 7 x 8-bit amplitude-bin counters for I and for Q
     int index[QPSK_GROUP];
+    volatile int frames_decimated; // frames whose symbols are in the ring (producer: timing warps, consumer: Costas warp)
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // mix 16 PCM samples with their phasors and store them as the current tile: qpsk.c:117
 __device__ __forceinline__ void mix_store(u64* __restrict__ xrow_cur, const uint4& p0, const uint4& p1,
@@ -112,11 +157,28 @@ __device__ __forceinline__ void mix_store(u64* __restrict__ xrow_cur, const uint
     }
 }
 
+// named barriers (id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+enum { BAR_ROWS = 1,      // FIR warps: sample rows of the tile are in shared memory
+       BAR_FIR_DONE = 2,  // FIR warps: every strip has finished reading the rows
+       BAR_FULL0 = 3,     // +t: matched-filter outputs of tile t of the frame are in sm.out (FIR arrive, timing sync)
+       BAR_FREE = 7,      // sm.out of the previous frame has been consumed (timing arrive, FIR sync)
+       BAR_AUX = 8 };     // the two timing warps among themselves
+#define QPSK_FIR_THREADS 256
+#define QPSK_AUX_THREADS 64
+#define QPSK_FRONT_THREADS 352   // 8 FIR warps + 2 timing/decimation warps + 1 Costas warp
+
+// Warp-specialised front end.  Warps 0-7 mix and filter (the FP32-pipe-bound part); warps 8-9
+// follow one tile behind with the amplitude histograms, the index and the decimation; warp 10 runs
+// the Costas loop of the previous frame when the CTA owns whole streams.  The auxiliary warps live
+// in the issue slots the packed-FP32 filter leaves free, so the filter never waits for them.
 template <int NTAPS, int SPS, int MODE>
-__global__ void __launch_bounds__(256, 1) rx_front_kernel(const RxFrontArgs a) {
+__global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const RxFrontArgs a) {
     static_assert(NTAPS - 1 <= QPSK_CHUNK - 2, "halo must fit in one previous tile");
     constexpr int R = 16;
-    constexpr int NSYM_MAX = 512 / SPS;
+    constexpr int NSYM = 512 / SPS, TILE_SYMS = QPSK_CHUNK / SPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RxFrontSmem<SPS>& sm = *reinterpret_cast<RxFrontSmem<SPS>*>(smem_raw);
 
@@ -129,122 +191,159 @@ __global__ void __launch_bounds__(256, 1) rx_front_kernel(const RxFrontArgs a) {
     const int ch = g * QPSK_GROUP + lane;
     const bool live = ch < a.C;
     const int chl = live ? ch : a.C - 1;            // padded lanes recompute the last channel, stores are masked
-    const int N = a.N, nsym = N / SPS;
-    const int tiles_per_frame = N / QPSK_CHUNK;
-    const size_t row = (size_t)a.F * N;
-    const int16_t* pcm_row = a.pcm + (size_t)chl * row;
-    const int strip = w * R;                         // this thread's 16 samples inside a tile
-
-    u64* xrow = &sm.x[lane][0];
-    u64* xcur = xrow + QPSK_CHUNK + strip;
-
-    // ---- prologue: the tile before frame f0 becomes the halo
-    {
-        const int16_t* src = (f0 == 0) ? a.pcm_tail + (size_t)chl * QPSK_CHUNK + strip
-                                       : pcm_row + (size_t)f0 * N - QPSK_CHUNK + strip;
-        const uint4 p0 = *reinterpret_cast<const uint4*>(src);
-        const uint4 p1 = *reinterpret_cast<const uint4*>(src + 8);
-        const float2* ph = a.phasor + (size_t)f0 * N + strip;    // table index QPSK_CHUNK + (f0*N - 128 + strip + e)
-        float2 phr[16];
-#pragma unroll
-        for (int e = 0; e < 16; e++) phr[e] = ph[e];
-        mix_store(xcur, p0, p1, phr);
-    }
-    uint4 n0, n1;   // PCM of the next tile, prefetched across the FIR loop
-    {
-        const int16_t* src = pcm_row + (size_t)f0 * N + strip;
-        n0 = *reinterpret_cast<const uint4*>(src);
-        n1 = *reinterpret_cast<const uint4*>(src + 8);
-    }
-    if (threadIdx.x < QPSK_CHUNK) sm.ph[0][threadIdx.x] = a.phasor[QPSK_CHUNK + (size_t)f0 * N + threadIdx.x];
+    const int N = a.N;
+    constexpr int tiles_per_frame = 512 / QPSK_CHUNK;
+    const int nframes = f1 - f0;
+    if (threadIdx.x == 0) sm.frames_decimated = 0;
     __syncthreads();
 
-    const int ntiles = (f1 - f0) * tiles_per_frame;
-    for (int k = 0; k < ntiles; k++) {
-        const size_t tbase = (size_t)f0 * N + (size_t)k * QPSK_CHUNK;   // first sample of this tile in the launch
-        // ---- shift own strip: current -> halo, then mix the prefetched PCM in as the new current tile
+    if (w < 8) {
+        // =================================== FIR warps ===================================
+        const size_t row = (size_t)a.F * N;
+        const int16_t* pcm_row = a.pcm + (size_t)chl * row;
+        const int strip = w * R;                     // this thread's 16 samples inside a tile
+        u64* xrow = &sm.x[lane][0];
+        u64* xcur = xrow + QPSK_CHUNK + strip;
+
+        // prologue: the tile before frame f0 becomes the halo
+        {
+            const int16_t* src = (f0 == 0) ? a.pcm_tail + (size_t)chl * QPSK_CHUNK + strip
+                                           : pcm_row + (size_t)f0 * N - QPSK_CHUNK + strip;
+            const uint4 p0 = *reinterpret_cast<const uint4*>(src);
+            const uint4 p1 = *reinterpret_cast<const uint4*>(src + 8);
+            const float2* ph = a.phasor + (size_t)f0 * N + strip;    // table index QPSK_CHUNK + (f0*N - 128 + strip + e)
+            float2 phr[16];
 #pragma unroll
-        for (int e = 0; e < R; e++) xrow[strip + e] = xcur[e];
-        mix_store(xcur, n0, n1, &sm.ph[k & 1][strip]);
-        __syncthreads();
-
-        // ---- prefetch the next tile's PCM and phasors while the FIR runs
-        float2 phn = make_float2(0.f, 0.f);
-        if (k + 1 < ntiles) {
-            const int16_t* src = pcm_row + tbase + QPSK_CHUNK + strip;
-            n0 = *reinterpret_cast<const uint4*>(src);
-            n1 = *reinterpret_cast<const uint4*>(src + 8);
-            if (threadIdx.x < QPSK_CHUNK) phn = a.phasor[QPSK_CHUNK + tbase + QPSK_CHUNK + threadIdx.x];
+            for (int e = 0; e < 16; e++) phr[e] = ph[e];
+            mix_store(xcur, p0, p1, phr);
         }
+        // PCM and phasors of the next tile travel HBM -> shared memory by cp.async while the filter runs
+        short* stage = &sm.pcm[lane][strip];
+        {
+            const int16_t* src = pcm_row + (size_t)f0 * N + strip;
+            cp_async16(stage, src);
+            cp_async16(stage + 8, src + 8);
+            if (threadIdx.x < QPSK_CHUNK) cp_async8(&sm.ph[0][threadIdx.x], &a.phasor[QPSK_CHUNK + (size_t)f0 * N + threadIdx.x]);
+        }
+        cp_async_wait_all();
+        bar_sync(BAR_FIR_DONE, QPSK_FIR_THREADS);
 
-        // ---- matched filter: rrc_fir.c:22-28
-        u64 acc[R];
-        fir_strip<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
-        const int tf = (k % tiles_per_frame) * QPSK_CHUNK + strip;     // sample index inside the frame
-        u64* orow = &sm.out[lane][tf];
+        const int ntiles = nframes * tiles_per_frame;
+        for (int k = 0; k < ntiles; k++) {
+            const size_t tbase = (size_t)f0 * N + (size_t)k * QPSK_CHUNK;   // first sample of this tile in the launch
+            // shift own strip: current -> halo, then mix the staged PCM in as the new current tile
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            float yr, yi;
-            unpack2(acc[r], yr, yi);
-            orow[r] = pack2(gain_exact(yr), gain_exact(yi));
-        }
-        if (a.fir_dbg != nullptr && live) {
-            u64* dst = reinterpret_cast<u64*>(a.fir_dbg) + (size_t)ch * row + tbase + strip;
+            for (int e = 0; e < R; e++) xrow[strip + e] = xcur[e];
+            {
+                const uint4 n0 = *reinterpret_cast<const uint4*>(stage);
+                const uint4 n1 = *reinterpret_cast<const uint4*>(stage + 8);
+                mix_store(xcur, n0, n1, &sm.ph[k & 1][strip]);
+            }
+            bar_sync(BAR_ROWS, QPSK_FIR_THREADS);
+
+            if (k + 1 < ntiles) {
+                const int16_t* src = pcm_row + tbase + QPSK_CHUNK + strip;
+                cp_async16(stage, src);
+                cp_async16(stage + 8, src + 8);
+                if (threadIdx.x < QPSK_CHUNK) cp_async8(&sm.ph[(k + 1) & 1][threadIdx.x], &a.phasor[QPSK_CHUNK + tbase + QPSK_CHUNK + threadIdx.x]);
+            }
+
+            // matched filter: rrc_fir.c:22-28
+            u64 acc[R];
+            fir_strip<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
+            const int t = k % tiles_per_frame;
+            // sm.out still holds the previous frame until the timing warps have decimated it
+            if (t == 0 && k > 0) bar_sync(BAR_FREE, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+            // raw sums go to shared memory; the output gain (a double multiply behind two conversions on the
+            // narrow XU pipe) is applied by the timing warps, off the filter's critical path
+            u64* orow = &sm.out[lane][t * QPSK_CHUNK + strip];
 #pragma unroll
-            for (int r = 0; r < R; r++) dst[r] = orow[r];
+            for (int r = 0; r < R; r++) orow[r] = acc[r];
+            bar_arrive(BAR_FULL0 + t, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+            cp_async_wait_all();                       // next tile's PCM and phasors have landed
+            bar_sync(BAR_FIR_DONE, QPSK_FIR_THREADS);
         }
-        if (threadIdx.x < QPSK_CHUNK) sm.ph[(k + 1) & 1][threadIdx.x] = phn;
-        __syncthreads();
-
-        if ((k + 1) % tiles_per_frame != 0) continue;
-
-        // ---- frame complete: amplitude histograms, qpsk.c:131-167.  Warp 0 = I, warp 1 = Q, lane = channel.
-        const int f = f0 + k / tiles_per_frame;
-        if (w < 2) {
-            const float* o = reinterpret_cast<const float*>(&sm.out[lane][0]) + w;
+    } else if (w < 10) {
+        // ============================ timing + decimation warps ============================
+        // warp 8 = I, warp 9 = Q, lane = channel: amplitude histograms of qpsk.c:131-167, one tile behind the filter
+        const int comp = w - 8;
+        const int nsym = N / SPS;
+        for (int fr = 0; fr < nframes; fr++) {
+            const int f = f0 + fr;
             float av = 0.0f, mx = 0.0f;
             u64 hist = 0ull;
-#pragma unroll 4
-            for (int s = 0; s < NSYM_MAX; s++) {
+            for (int t = 0; t < tiles_per_frame; t++) {
+                bar_sync(BAR_FULL0 + t, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+                float* ow = reinterpret_cast<float*>(&sm.out[lane][0]) + comp;
+#pragma unroll 2
+                for (int s = t * TILE_SYMS; s < (t + 1) * TILE_SYMS; s++) {
 #pragma unroll
-                for (int j = 0; j < SPS; j++) av = __fadd_rn(av, fabsf(o[2 * (s * SPS + j)]));
-                av = __fmul_rn(av, 1.0f / SPS);              // av /= CYCLES, exact for a power of two
-                if (av > mx) mx = av;
-                const float hv = __fmul_rn(mx, 0.125f);      // max / 8.0f
-                int bin = 0;                                   // first k in 1..7 with av <= hv*k (hv*k is monotone in k)
+                    for (int j = 0; j < SPS; j++) {
+                        const float y = gain_exact(ow[2 * (s * SPS + j)]);      // rrc_fir.c:28, this warp's component
+                        ow[2 * (s * SPS + j)] = y;                                 // the decimation reads it back
+                        av = __fadd_rn(av, fabsf(y));
+                    }
+                    av = __fmul_rn(av, 1.0f / SPS);              // av /= CYCLES, exact for a power of two
+                    if (av > mx) mx = av;
+                    const float hv = __fmul_rn(mx, 0.125f);      // max / 8.0f
+                    int bin = 0;                                   // first k in 1..7 with av <= hv*k (hv*k is monotone in k)
 #pragma unroll
-                for (int kk = 7; kk >= 1; kk--) bin = (av <= __fmul_rn(hv, (float)kk)) ? kk : bin;
-                hist += 1ull << (8 * bin);                     // byte 0 collects "no bin"; counts <= 128 fit a byte
+                    for (int kk = 7; kk >= 1; kk--) bin = (av <= __fmul_rn(hv, (float)kk)) ? kk : bin;
+                    hist += 1ull << (8 * bin);                     // byte 0 collects "no bin"; counts <= 128 fit a byte
+                }
             }
-            sm.hist[w][lane] = hist;
-        }
-        __syncthreads();
-        if (w == 0) {                                          // qpsk.c:173-180 first strict maximum
-            const u64 hi = sm.hist[0][lane], hq = sm.hist[1][lane];
-            int hmax = 0, index = 0;
+            sm.hist[comp][lane] = hist;
+            bar_sync(BAR_AUX, QPSK_AUX_THREADS);
+            int index = 0;
+            {                                                      // qpsk.c:173-180 first strict maximum
+                const u64 hi = sm.hist[0][lane], hq = sm.hist[1][lane];
+                int hmax = 0;
 #pragma unroll
-            for (int kk = 1; kk < 8; kk++) {
-                const int h = (int)((hi >> (8 * kk)) & 0xff) + (int)((hq >> (8 * kk)) & 0xff);
-                if (h > hmax) { hmax = h; index = kk; }
+                for (int kk = 1; kk < 8; kk++) {
+                    const int h = (int)((hi >> (8 * kk)) & 0xff) + (int)((hq >> (8 * kk)) & 0xff);
+                    if (h > hmax) { hmax = h; index = kk; }
+                }
             }
-            sm.index[lane] = index;
-            if (live) a.index_t[(size_t)f * a.Cpad + ch] = index;
-        }
-        __syncthreads();
-        // ---- decimate, qpsk.c:186-191: symbol i = sample i*SPS + index, stored channel-fastest
-        {
-            const int index = sm.index[lane];
-            const int slot = (a.slot_base + 1 + f) % a.nslots;
-            u64* dst = reinterpret_cast<u64*>(a.dec_ring) + (size_t)slot * nsym * a.Cpad + ch;
-            for (int i = w; i < nsym; i += 8) {
-                const int j = i * SPS + index;
-                u64 v;
-                if (j < N) v = sm.out[lane][j];
-                else if (a.ub_mode == QPSK_UB_CLAMP) v = sm.out[lane][N - 1];
-                else v = 0ull;   // aliasing read of decimated_frame[j-N]: patched by the Costas kernel
-                if (live) dst[(size_t)i * a.Cpad] = v;
+            if (comp == 0 && live) a.index_t[(size_t)f * a.Cpad + ch] = index;
+            if (a.fir_dbg != nullptr && live) {                    // parity tap: the whole filtered frame
+                u64* dst = reinterpret_cast<u64*>(a.fir_dbg) + (size_t)ch * ((size_t)a.F * N) + (size_t)f * N;
+                for (int i = comp; i < N; i += 2) dst[i] = sm.out[lane][i];
+            }
+            // decimate, qpsk.c:186-191: symbol i = sample i*SPS + index, stored channel-fastest
+            {
+                const int slot = (a.slot_base + 1 + f) % a.nslots;
+                u64* dst = reinterpret_cast<u64*>(a.dec_ring) + (size_t)slot * nsym * a.Cpad + ch;
+                for (int i = comp; i < NSYM; i += 2) {
+                    const int j = i * SPS + index;
+                    u64 v;
+                    if (j < N) v = sm.out[lane][j];
+                    else if (a.ub_mode == QPSK_UB_CLAMP) v = sm.out[lane][N - 1];
+                    else v = 0ull;   // aliasing read of decimated_frame[j-N]: patched by the Costas stage
+                    if (live) dst[(size_t)i * a.Cpad] = v;
+                }
+            }
+            if (fr + 1 < nframes) bar_arrive(BAR_FREE, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+            if (a.fuse_costas) {
+                __threadfence();                                   // ring + index writes before the flag
+                bar_sync(BAR_AUX, QPSK_AUX_THREADS);
+                if (threadIdx.x == 8 * 32) sm.frames_decimated = fr + 1;
+            } else {
+                bar_sync(BAR_AUX, QPSK_AUX_THREADS);               // sm.hist is rewritten next frame
             }
         }
-        __syncthreads();
+    } else {
+        // ================================== Costas warp ==================================
+        if (!a.fuse_costas || !live) return;
+        const CostasParams p = costas_params(a.costas);
+        const float2 st = a.costas.loop_state[ch];
+        float phase = st.x, freq = st.y;
+        for (int fr = 0; fr < nframes; fr++) {
+            // call f consumes the frame decimated one call earlier (already in the ring) and patches the
+            // frame produced by this call, so it must wait until that one has been decimated
+            while (sm.frames_decimated < fr + 1) __nanosleep(200);
+            __threadfence();
+            costas_run_frame<true>(a.costas, p, f0 + fr, ch, phase, freq);
+        }
+        a.costas.loop_state[ch] = make_float2(phase, freq);
     }
 }
