@@ -110,6 +110,7 @@ struct FrameDecodeArgs {
     uint8_t* crc_ok_t;          // [F][Cpad]
     unsigned long long* counters;   // [0] frames examined, [1] CRC passes
     int C, Cpad, F;
+    int c0;                     // first channel of this launch; C is its end
 };
 
 template <int NBYTES, int DIR>
@@ -129,7 +130,7 @@ __device__ __forceinline__ void permute_frame(const unsigned (&in)[NBYTES / 4], 
 template <int NBYTES>
 __global__ void __launch_bounds__(128) frame_decode_kernel(const FrameDecodeArgs a) {
     constexpr int W = NBYTES / 4;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
     unsigned ok = 0;
     if (c < a.C) {

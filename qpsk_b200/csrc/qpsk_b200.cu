@@ -76,7 +76,11 @@ struct qpsk_b200_rx {
     unsigned* d_frames_t;   // [maxF][W][Cpad] decoded frames (DECODE_FRAMES)
     uint8_t* d_crc_ok_t;    // [maxF][Cpad]
     unsigned long long* d_counters;   // [2]
-    int16_t* d_pcm_stage;   // [C][maxF*N] for the host path (lazy)
+    int16_t* d_pcm_stage2[2];   // host path: double-buffered PCM slices (lazy)
+    unsigned* d_out_stage2[2];  // host path: double-buffered transposed dibit slices
+    size_t stage_slice_bytes;
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
     void* d_scratch;        // transposed download staging (lazy)
     size_t scratch_bytes;
 };
@@ -109,9 +113,16 @@ static int rx_free(qpsk_b200_rx* rx) {
     void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
                      rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters,
-                     rx->d_pcm_stage, rx->d_scratch };
+                     rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev) if (e) cudaEventDestroy(e);
+    for (int b = 0; b < 2; b++) {
+        if (rx->ev_in[b]) cudaEventDestroy(rx->ev_in[b]);
+        if (rx->ev_cmp[b]) cudaEventDestroy(rx->ev_cmp[b]);
+        if (rx->ev_out[b]) cudaEventDestroy(rx->ev_out[b]);
+    }
+    if (rx->s_in) cudaStreamDestroy(rx->s_in);
+    if (rx->s_out) cudaStreamDestroy(rx->s_out);
     if (rx->stream) cudaStreamDestroy(rx->stream);
     delete rx;
     return 0;
@@ -247,43 +258,42 @@ static int upload_keystream(int nbytes, cudaStream_t s) {
 }
 
 static int launch_frame_decode(int nbytes, const unsigned* dibits_t, unsigned* frames_t, uint8_t* crc_ok_t,
-                               unsigned long long* counters, int C, int Cpad, int F, cudaStream_t s) {
+                               unsigned long long* counters, int c0, int C, int Cpad, int F, cudaStream_t s) {
     if (nbytes != 16 && nbytes != 32) return fail(QPSK_B200_ERR_ARG, "frame decode supports 16- and 32-byte frames, got %d", nbytes);
     int rc = upload_keystream(nbytes, s);
     if (rc) return rc;
     FrameDecodeArgs a;
-    a.dibits_t = dibits_t; a.frames_t = frames_t; a.crc_ok_t = crc_ok_t; a.counters = counters; a.C = C; a.Cpad = Cpad; a.F = F;
-    dim3 grid((C + 127) / 128, F);
+    a.dibits_t = dibits_t; a.frames_t = frames_t; a.crc_ok_t = crc_ok_t; a.counters = counters; a.C = C; a.Cpad = Cpad; a.F = F; a.c0 = c0;
+    dim3 grid((C - c0 + 127) / 128, F);
     if (nbytes == 32) frame_decode_kernel<32><<<grid, 128, 0, s>>>(a);
     else frame_decode_kernel<16><<<grid, 128, 0, s>>>(a);
     CU(cudaGetLastError());
     return 0;
 }
 
-extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pcm, int nframes, void* cuda_stream) {
-    if (!rx || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
-    if (nframes < 1 || nframes > rx->maxF) return fail(QPSK_B200_ERR_ARG, "nframes %d outside 1..%d", nframes, rx->maxF);
-    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15) != 0) return fail(QPSK_B200_ERR_ARG, "d_pcm must be 16-byte aligned");
-    CU(cudaSetDevice(rx->cfg.device));
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rx->stream;
+// ---- one process call = begin (taps, phasor table) + one or more channel slices + end ----------
+static int rx_begin_call(qpsk_b200_rx* rx, int F, cudaStream_t s) {
     if (g_taps_owner != rx->id) {
         int rc = upload_taps(rx, s);
         if (rc) return rc;
         g_taps_owner = rx->id;
     }
-    const int F = nframes, N = rx->N;
-
     // K0: mixer phasors of this call
-    phasor_table_kernel<<<1, QPSK_CHUNK, 0, s>>>(rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->rect, F, N);
+    phasor_table_kernel<<<1, QPSK_CHUNK, 0, s>>>(rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->rect, F, rx->N);
     CU(cudaGetLastError());
+    rx->launches += 1;
+    return 0;
+}
 
-    // K1: mixer + matched filter + timing + decimation
+// channels [c0, c0 + nc) of the call; d_pcm holds exactly those rows.  c0 must be a multiple of 32.
+static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, int F, cudaStream_t s, bool timed) {
+    const int N = rx->N;
     RxFrontArgs fa;
     fa.pcm = d_pcm; fa.pcm_tail = rx->d_pcm_tail; fa.phasor = rx->d_phasor;
     fa.dec_ring = rx->d_dec_ring; fa.index_t = rx->d_index_t; fa.fir_dbg = rx->d_fir_dbg;
-    fa.C = rx->C; fa.Cpad = rx->Cpad; fa.F = F; fa.N = N;
+    fa.C = rx->C; fa.Cpad = rx->Cpad; fa.F = F; fa.N = N; fa.chan_base = c0; fa.chan_count = nc;
     fa.slot_base = rx->slot_base; fa.nslots = rx->nslots; fa.ub_mode = rx->cfg.ub_mode;
-    const int ngroups = rx->Cpad / QPSK_GROUP;
+    const int ngroups = (nc + QPSK_GROUP - 1) / QPSK_GROUP;
     // enough CTAs for a few waves over the SMs: split the frames of a channel group when channels are few
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, rx->cfg.device);
@@ -298,6 +308,7 @@ extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pc
     ca.dec_ring = rx->d_dec_ring; ca.index_t = rx->d_index_t; ca.loop_state = rx->d_loop_state;
     ca.dibits_t = rx->d_dibits_t; ca.costas_dbg = rx->d_costas_dbg; ca.track_t = rx->d_track_t;
     ca.C = rx->C; ca.Cpad = rx->Cpad; ca.F = F; ca.nsym = rx->nsym; ca.sps = rx->sps; ca.N = N;
+    ca.c0 = c0; ca.c1 = (c0 + nc < rx->C) ? c0 + nc : rx->C;
     ca.slot_base = rx->slot_base; ca.nslots = rx->nslots; ca.ub_mode = rx->cfg.ub_mode;
     ca.alpha = rx->loop.alpha; ca.beta = rx->loop.beta; ca.max_freq = rx->loop.max_freq; ca.min_freq = rx->loop.min_freq;
     ca.rot45 = rx->rot45;
@@ -305,37 +316,54 @@ extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pc
     fa.fuse_costas = fused ? 1 : 0;
     fa.costas = ca;
 
-    CU(cudaEventRecord(rx->ev[0], s));
+    if (timed) CU(cudaEventRecord(rx->ev[0], s));
     cudaError_t e;
     const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
     if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, grid, s) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, grid, s);
     else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, grid, s) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, grid, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
-    CU(cudaEventRecord(rx->ev[1], s));
+    if (timed) CU(cudaEventRecord(rx->ev[1], s));
 
     // carry the last 128 PCM samples of every channel (the next call's filter history)
-    save_pcm_tail_kernel<<<(rx->C * 16 + 255) / 256, 256, 0, s>>>(d_pcm, rx->d_pcm_tail, rx->C, (size_t)F * N);
+    const int live = ca.c1 - c0;
+    save_pcm_tail_kernel<<<(live * 16 + 255) / 256, 256, 0, s>>>(d_pcm, rx->d_pcm_tail + (size_t)c0 * QPSK_CHUNK, live, (size_t)F * N);
     CU(cudaGetLastError());
 
-    CU(cudaEventRecord(rx->ev[2], s));
+    if (timed) CU(cudaEventRecord(rx->ev[2], s));
     if (!fused) {
-        costas_kernel<<<(rx->C + 127) / 128, 128, 0, s>>>(ca);
+        costas_kernel<<<(live + 127) / 128, 128, 0, s>>>(ca);
         CU(cudaGetLastError());
         rx->launches += 1;
     }
-    CU(cudaEventRecord(rx->ev[3], s));
+    if (timed) CU(cudaEventRecord(rx->ev[3], s));
     rx->last_fused = fused;
 
     if (rx->d_frames_t) {   // K4: descramble -> de-interleave -> CRC16 per frame
-        int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t, rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters, rx->C, rx->Cpad, F, s);
+        int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t, rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters, c0, ca.c1, rx->Cpad, F, s);
         if (rc) return rc;
         rx->launches += 1;
     }
+    rx->launches += 2;
+    if (timed) rx->timed = true;
+    return 0;
+}
 
-    rx->launches += 3;
-    rx->timed = true;
+static void rx_end_call(qpsk_b200_rx* rx, int F) {
     rx->slot_base = (rx->slot_base + F) % rx->nslots;
     rx->lastF = F;
+}
+
+extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pcm, int nframes, void* cuda_stream) {
+    if (!rx || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nframes < 1 || nframes > rx->maxF) return fail(QPSK_B200_ERR_ARG, "nframes %d outside 1..%d", nframes, rx->maxF);
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 15) != 0) return fail(QPSK_B200_ERR_ARG, "d_pcm must be 16-byte aligned");
+    CU(cudaSetDevice(rx->cfg.device));
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rx->stream;
+    int rc = rx_begin_call(rx, nframes, s);
+    if (rc) return rc;
+    rc = rx_run_slice(rx, d_pcm, 0, rx->C, nframes, s, true);
+    if (rc) return rc;
+    rx_end_call(rx, nframes);
     return QPSK_B200_OK;
 }
 
@@ -474,21 +502,73 @@ extern "C" int qpsk_b200_rx_device_dibits(qpsk_b200_rx* rx, const uint32_t** d_p
     return QPSK_B200_OK;
 }
 
+// Host-buffer entry point.  Large calls are cut into channel slices that flow through three streams
+// (H2D copy, compute, transposed D2H copy of the packed dibits) with double-buffered staging, so the
+// PCIe transfers of one slice overlap the kernels of its neighbours.
 extern "C" int qpsk_b200_rx_process_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, uint8_t* h_dibits) {
     if (!rx || !h_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
     if (nframes < 1 || nframes > rx->maxF) return fail(QPSK_B200_ERR_ARG, "nframes %d outside 1..%d", nframes, rx->maxF);
     CU(cudaSetDevice(rx->cfg.device));
-    const size_t bytes = (size_t)rx->C * nframes * rx->N * sizeof(int16_t);
-    if (!rx->d_pcm_stage) CU(cudaMalloc((void**)&rx->d_pcm_stage, (size_t)rx->C * rx->maxF * rx->N * sizeof(int16_t)));
-    CU(cudaMemcpyAsync(rx->d_pcm_stage, h_pcm, bytes, cudaMemcpyHostToDevice, rx->stream));
-    int rc = qpsk_b200_rx_process_device(rx, rx->d_pcm_stage, nframes, rx->stream);
-    if (rc) return rc;
-    if (h_dibits) {
-        rc = download_transposed<unsigned>(rx, rx->d_dibits_t, nframes * (rx->nsym / 16), h_dibits, rx->stream);
-        if (rc) return rc;
-    } else {
-        CU(cudaStreamSynchronize(rx->stream));
+    const int F = nframes, N = rx->N, C = rx->C;
+    const size_t row_bytes = (size_t)F * N * sizeof(int16_t);
+    const int words = F * (rx->nsym / 16);
+    // slice size: ~256 MiB of PCM, a whole number of 32-channel groups, at least 4 SM-waves of CTAs when possible
+    int slice = (int)((256ull << 20) / row_bytes);
+    slice = slice / QPSK_GROUP * QPSK_GROUP;
+    if (slice < 4 * 148 * QPSK_GROUP) slice = 4 * 148 * QPSK_GROUP;
+    if (slice > C) slice = C;
+    const int nslices = (C + slice - 1) / slice;
+    if (rx->stage_slice_bytes < (size_t)slice * row_bytes) {
+        for (int b = 0; b < 2; b++) {
+            if (rx->d_pcm_stage2[b]) { cudaFree(rx->d_pcm_stage2[b]); rx->d_pcm_stage2[b] = nullptr; }
+            if (rx->d_out_stage2[b]) { cudaFree(rx->d_out_stage2[b]); rx->d_out_stage2[b] = nullptr; }
+        }
+        rx->stage_slice_bytes = 0;
+        for (int b = 0; b < 2; b++) {
+            CU(cudaMalloc((void**)&rx->d_pcm_stage2[b], (size_t)slice * rx->maxF * N * sizeof(int16_t)));
+            CU(cudaMalloc((void**)&rx->d_out_stage2[b], (size_t)slice * rx->maxF * (rx->nsym / 16) * sizeof(unsigned)));
+        }
+        rx->stage_slice_bytes = (size_t)slice * rx->maxF * N * sizeof(int16_t);
     }
+    if (!rx->s_in) {
+        CU(cudaStreamCreateWithFlags(&rx->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&rx->s_out, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CU(cudaEventCreateWithFlags(&rx->ev_in[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&rx->ev_cmp[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&rx->ev_out[b], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t sc = rx->stream;
+    int rc = rx_begin_call(rx, F, sc);
+    if (rc) return rc;
+    for (int i = 0; i < nslices; i++) {
+        const int b = i & 1, c0 = i * slice, nc = (c0 + slice <= C) ? slice : C - c0;
+        // staging buffer b was last read by the kernels of slice i-2
+        if (i >= 2) CU(cudaStreamWaitEvent(rx->s_in, rx->ev_cmp[b], 0));
+        CU(cudaMemcpyAsync(rx->d_pcm_stage2[b], h_pcm + (size_t)c0 * F * N, (size_t)nc * row_bytes, cudaMemcpyHostToDevice, rx->s_in));
+        CU(cudaEventRecord(rx->ev_in[b], rx->s_in));
+        CU(cudaStreamWaitEvent(sc, rx->ev_in[b], 0));
+        rc = rx_run_slice(rx, rx->d_pcm_stage2[b], c0, nc, F, sc, i == 0);
+        if (rc) return rc;
+        if (h_dibits) {
+            // output buffer b was last drained by the D2H copy of slice i-2
+            if (i >= 2) CU(cudaStreamWaitEvent(sc, rx->ev_out[b], 0));
+            dim3 grid((nc + 31) / 32, (words + 31) / 32), block(32, 8);
+            transpose_to_channel_major<unsigned><<<grid, block, 0, sc>>>(rx->d_dibits_t + c0, rx->d_out_stage2[b], words, nc, rx->Cpad);
+            CU(cudaGetLastError());
+            rx->launches += 1;
+        }
+        CU(cudaEventRecord(rx->ev_cmp[b], sc));
+        if (h_dibits) {
+            CU(cudaStreamWaitEvent(rx->s_out, rx->ev_cmp[b], 0));
+            CU(cudaMemcpyAsync(h_dibits + (size_t)c0 * words * 4, rx->d_out_stage2[b], (size_t)nc * words * 4, cudaMemcpyDeviceToHost, rx->s_out));
+            CU(cudaEventRecord(rx->ev_out[b], rx->s_out));
+        }
+    }
+    rx_end_call(rx, F);
+    CU(cudaStreamSynchronize(sc));
+    CU(cudaStreamSynchronize(rx->s_out));
     return QPSK_B200_OK;
 }
 
@@ -927,7 +1007,7 @@ static int frames_codec(const uint8_t* h_in, int nbytes, int nchan, int nframes,
         CU(cudaMalloc(&ok.p, (size_t)nframes * Cpad));
         CU(cudaMalloc(&cnt.p, 2 * sizeof(unsigned long long)));
         CU(cudaMemset(cnt.p, 0, 2 * sizeof(unsigned long long)));
-        rc = launch_frame_decode(nbytes, (const unsigned*)a.p, (unsigned*)b.p, (uint8_t*)ok.p, (unsigned long long*)cnt.p, nchan, Cpad, nframes, 0);
+        rc = launch_frame_decode(nbytes, (const unsigned*)a.p, (unsigned*)b.p, (uint8_t*)ok.p, (unsigned long long*)cnt.p, 0, nchan, Cpad, nframes, 0);
         if (rc) return rc;
     }
     transpose_to_channel_major<unsigned><<<tgrid, tblock>>>((const unsigned*)b.p, (unsigned*)cm.p, rows, nchan, Cpad);

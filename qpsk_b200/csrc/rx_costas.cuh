@@ -17,6 +17,7 @@ struct CostasArgs {
     float2* costas_dbg;      // optional [F][nsym][Cpad] derotated symbols (costas_frame), may be null
     float2* track_t;         // [F][Cpad] (phase, freq) after each frame
     int C, Cpad, F, nsym, sps, N;
+    int c0, c1;              // channels [c0, c1) are processed by the standalone kernel launch
     int slot_base, nslots, ub_mode;
     float alpha, beta, max_freq, min_freq;
     float2 rot45;            // cmplx(ROTATE45) from the host libm, qpsk.c:75
@@ -100,8 +101,8 @@ __device__ __forceinline__ CostasParams costas_params(const CostasArgs& a) {
 }
 
 __global__ void __launch_bounds__(128) costas_kernel(const CostasArgs a) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.C) return;
+    const int c = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.c1) return;
     const CostasParams p = costas_params(a);
     const float2 st = a.loop_state[c];
     float phase = st.x, freq = st.y;

@@ -114,6 +114,7 @@ struct RxFrontArgs {
     int*    index_t;           // [F][Cpad] timing index per frame
     float2* fir_dbg;           // optional [C][F*N] matched-filter output (parity taps), may be null
     int C, Cpad, F, N;
+    int chan_base, chan_count; // this launch covers channels [chan_base, chan_base + chan_count); pcm is indexed from chan_base
     int frames_per_block;      // frames handled by one CTA
     int slot_base, nslots;     // frame f goes to ring slot (slot_base + 1 + f) % nslots
     int ub_mode;
@@ -183,14 +184,15 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
     RxFrontSmem<SPS>& sm = *reinterpret_cast<RxFrontSmem<SPS>*>(smem_raw);
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int ngroups = a.Cpad / QPSK_GROUP;
+    const int ngroups = (a.chan_count + QPSK_GROUP - 1) / QPSK_GROUP;
     const int g = blockIdx.x % ngroups, fb = blockIdx.x / ngroups;
     const int f0 = fb * a.frames_per_block;
     const int f1 = min(a.F, f0 + a.frames_per_block);
     if (f0 >= f1) return;
-    const int ch = g * QPSK_GROUP + lane;
-    const bool live = ch < a.C;
-    const int chl = live ? ch : a.C - 1;            // padded lanes recompute the last channel, stores are masked
+    const int ch = a.chan_base + g * QPSK_GROUP + lane;
+    const int ch_end = min(a.C, a.chan_base + a.chan_count);
+    const bool live = ch < ch_end;
+    const int chl = live ? ch : ch_end - 1;         // padded lanes recompute the last channel, stores are masked
     const int N = a.N;
     constexpr int tiles_per_frame = 512 / QPSK_CHUNK;
     const int nframes = f1 - f0;
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
     if (w < 8) {
         // =================================== FIR warps ===================================
         const size_t row = (size_t)a.F * N;
-        const int16_t* pcm_row = a.pcm + (size_t)chl * row;
+        const int16_t* pcm_row = a.pcm + (size_t)(chl - a.chan_base) * row;
         const int strip = w * R;                     // this thread's 16 samples inside a tile
         u64* xrow = &sm.x[lane][0];
         u64* xcur = xrow + QPSK_CHUNK + strip;
