@@ -21,9 +21,9 @@ struct FftCfg {
     static constexpr int THREADS = (TPF >= 256) ? TPF : 256;
     static constexpr int FPB = THREADS / TPF;                      // transforms per CTA pass
     static constexpr int PTS = FPB * N;
-    static constexpr int SKEW_PTS = PTS + PTS / 8;                 // idx + idx/8: conflict-free scatter of radix-8 outputs
+    static constexpr int SKEW_PTS = PTS + PTS / 16;                // float2 elements, one pad slot per 16: unit-stride and stride-8 accesses are conflict-free
     static constexpr int TW = (N >= 2) ? N / 2 : 1;
-    static constexpr size_t SMEM = sizeof(float) * 2 * SKEW_PTS + sizeof(float2) * TW + sizeof(float) * 64 + sizeof(int) * 64;
+    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + sizeof(float2) * TW + sizeof(float) * 64 + sizeof(int) * 64;
 };
 
 // tolerance-mode arithmetic (1e-5): explicit fused multiply-adds, since the TU is built with -fmad=false
@@ -66,7 +66,7 @@ __device__ __forceinline__ void dft_small<8>(float2 (&v)[8]) {
     v[3] = make_float2(e[3].x + o3.x, e[3].y + o3.y);      v[7] = make_float2(e[3].x - o3.x, e[3].y - o3.y);
 }
 
-__device__ __forceinline__ int fft_skew(int i) { return i + (i >> 3); }
+__device__ __forceinline__ int fft_skew(int i) { return i + (i >> 4); }
 
 struct FftArgs {
     const float2* in;      // [nbursts][N]
@@ -81,7 +81,7 @@ struct FftArgs {
 
 // one Stockham stage for the P points a thread owns: radix R, sub-transform length NS already done
 template <int LOG2N, int R, int NS, bool FIRST, bool LAST>
-__device__ __forceinline__ void fft_stage(float2 (&pts)[FftCfg<LOG2N>::P], float* sre, float* sim, const float2* stw,
+__device__ __forceinline__ void fft_stage(float2 (&pts)[FftCfg<LOG2N>::P], float2* sdat, const float2* stw,
                                           const float2* gin, int j, int base, bool active, float imsgn) {
     using Cfg = FftCfg<LOG2N>;
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R;   // NB butterflies per thread
@@ -93,7 +93,7 @@ __device__ __forceinline__ void fft_stage(float2 (&pts)[FftCfg<LOG2N>::P], float
         for (int r = 0; r < R; r++) {
             const int idx = jj + r * (N / R);
             if (FIRST) { v[r] = active ? gin[idx] : make_float2(0.f, 0.f); v[r].y *= imsgn; }   // inverse = conj(FFT(conj x))
-            else { const int s = fft_skew(base + idx); v[r] = make_float2(sre[s], sim[s]); }
+            else v[r] = sdat[fft_skew(base + idx)];
         }
         if (NS > 1) {
             const int k = jj % NS;
@@ -123,9 +123,7 @@ __device__ __forceinline__ void fft_stage(float2 (&pts)[FftCfg<LOG2N>::P], float
             const int o = (jj / NS) * NS * R + (jj % NS);
 #pragma unroll
             for (int q = 0; q < R; q++) {
-                const int s = fft_skew(base + o + q * NS);
-                sre[s] = pts[t * R + q].x;
-                sim[s] = pts[t * R + q].y;
+                sdat[fft_skew(base + o + q * NS)] = pts[t * R + q];
             }
         }
         __syncthreads();
@@ -133,14 +131,14 @@ __device__ __forceinline__ void fft_stage(float2 (&pts)[FftCfg<LOG2N>::P], float
 }
 
 template <int LOG2N, int NS, bool FIRST>
-__device__ __forceinline__ void fft_stages(float2 (&pts)[FftCfg<LOG2N>::P], float* sre, float* sim, const float2* stw,
+__device__ __forceinline__ void fft_stages(float2 (&pts)[FftCfg<LOG2N>::P], float2* sdat, const float2* stw,
                                            const float2* gin, int j, int base, bool active, float imsgn) {
     constexpr int N = FftCfg<LOG2N>::N;
     constexpr int REM = N / NS;
     constexpr int R = (REM >= 8) ? 8 : REM;
     constexpr bool LAST = (NS * R == N);
-    fft_stage<LOG2N, R, NS, FIRST, LAST>(pts, sre, sim, stw, gin, j, base, active, imsgn);
-    if constexpr (!LAST) fft_stages<LOG2N, NS * R, false>(pts, sre, sim, stw, gin, j, base, active, imsgn);
+    fft_stage<LOG2N, R, NS, FIRST, LAST>(pts, sdat, stw, gin, j, base, active, imsgn);
+    if constexpr (!LAST) fft_stages<LOG2N, NS * R, false>(pts, sdat, stw, gin, j, base, active, imsgn);
 }
 
 // output index of pts[i] after the last stage (radix RLAST, sub-transform length NSL = N / RLAST)
@@ -162,9 +160,8 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
     using Cfg = FftCfg<LOG2N>;
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, FPB = Cfg::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sre = reinterpret_cast<float*>(smem_raw);
-    float* sim = sre + Cfg::SKEW_PTS;
-    float2* stw = reinterpret_cast<float2*>(sim + Cfg::SKEW_PTS);
+    float2* sdat = reinterpret_cast<float2*>(smem_raw);
+    float2* stw = sdat + Cfg::SKEW_PTS;
     float* red_mag = reinterpret_cast<float*>(stw + Cfg::TW);
     int* red_idx = reinterpret_cast<int*>(red_mag + 64);
 
@@ -178,7 +175,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
         const bool active = b < a.nbursts;
         const float2* gin = a.in + (size_t)(active ? b : 0) * N;
         float2 pts[P];
-        fft_stages<LOG2N, 1, true>(pts, sre, sim, stw, gin, j, base, active, a.im_sign);
+        fft_stages<LOG2N, 1, true>(pts, sdat, stw, gin, j, base, active, a.im_sign);
         // ---- epilogue: scale, optional spectrum store, |X|^2 argmax
         float best = -1.0f;
         int besti = 0x7fffffff;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void fir_tap(u64& acc, const u64 xv, const int i) {
 // code at R = 16) stays resident in the instruction cache -- the fully unrolled 70 KB version spent
 // 9 % of its issue slots waiting for instruction fetch (profiles/r01_rx_front_v2).
 template <int NTAPS, int R, int MODE>
-__device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[R]) {
+__device__ __forceinline__ void fir_strip_main(const u64* __restrict__ x, u64 (&acc)[R]) {
     constexpr int STEADY = NTAPS - R + 1;            // d = R-1 .. NTAPS-1
     constexpr int TRIPS = STEADY / R, REM = STEADY % R;
 #pragma unroll
@@ -98,12 +98,22 @@ __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[
 #pragma unroll
         for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, d - r);
     }
+}
+
+template <int NTAPS, int R, int MODE>
+__device__ __forceinline__ void fir_strip_tail(const u64* __restrict__ x, u64 (&acc)[R]) {
 #pragma unroll
     for (int d = NTAPS; d < NTAPS - 1 + R; d++) {    // tail
         const u64 xv = x[d];
 #pragma unroll
         for (int r = d - (NTAPS - 1); r < R; r++) fir_tap<MODE>(acc[r], xv, d - r);
     }
+}
+
+template <int NTAPS, int R, int MODE>
+__device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[R]) {
+    fir_strip_main<NTAPS, R, MODE>(x, acc);
+    fir_strip_tail<NTAPS, R, MODE>(x, acc);
 }
 
 struct RxFrontArgs {
@@ -128,7 +138,7 @@ struct RxFrontSmem {
     static constexpr int OS = 512 + 1;
     u64 x[QPSK_GROUP][XS];        // [0,128) previous tile (halo), [128,256) current tile
     u64 out[QPSK_GROUP][OS];      // matched-filter output of the current frame
-    float2 ph[2][QPSK_CHUNK];     // mixer phasors of the current / next tile
+    float2 ph[3][QPSK_CHUNK];     // mixer phasors of tiles k, k+1, k+2 (ring)
     short pcm[QPSK_GROUP][QPSK_CHUNK + 8];   // cp.async landing zone for the next tile's PCM (row stride 272 B: conflict-free 16 B reads)
     u64 hist[2][QPSK_GROUP];      // 7 x 8-bit amplitude-bin counters for I and for Q
     int index[QPSK_GROUP];
@@ -144,6 +154,18 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// mix 16 PCM samples with their phasors into registers: qpsk.c:117
+__device__ __forceinline__ void mix_regs(u64 (&nx)[16], const uint4& p0, const uint4& p1, const float2* __restrict__ ph) {
+    const unsigned w[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+        const int v = (int)(short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+        const float s = __fmul_rn((float)v, 6.103515625e-05f);   // (float)in / 16384.0f, exact
+        const float2 p = ph[e];
+        nx[e] = pack2(__fmul_rn(p.x, s), __fmul_rn(p.y, s));
+    }
+}
 
 // mix 16 PCM samples with their phasors and store them as the current tile: qpsk.c:117
 __device__ __forceinline__ void mix_store(u64* __restrict__ xrow_cur, const uint4& p0, const uint4& p1,
@@ -219,40 +241,57 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
             for (int e = 0; e < 16; e++) phr[e] = ph[e];
             mix_store(xcur, p0, p1, phr);
         }
-        // PCM and phasors of the next tile travel HBM -> shared memory by cp.async while the filter runs
+        // PCM of the next tile and phasors of the tile after it travel HBM -> shared memory by cp.async while
+        // the filter runs; the next tile is mixed into registers inside the filter's tail (its loads, conversions
+        // and multiplies hide behind the FP pipe), so that only the stores remain between the two barriers
         short* stage = &sm.pcm[lane][strip];
+        const size_t s0 = (size_t)f0 * N;
+        const int ntiles = nframes * tiles_per_frame;
         {
-            const int16_t* src = pcm_row + (size_t)f0 * N + strip;
+            const int16_t* src = pcm_row + s0 + strip;
             cp_async16(stage, src);
             cp_async16(stage + 8, src + 8);
-            if (threadIdx.x < QPSK_CHUNK) cp_async8(&sm.ph[0][threadIdx.x], &a.phasor[QPSK_CHUNK + (size_t)f0 * N + threadIdx.x]);
+            if (threadIdx.x < QPSK_CHUNK) {
+                cp_async8(&sm.ph[0][threadIdx.x], &a.phasor[QPSK_CHUNK + s0 + threadIdx.x]);
+                if (ntiles > 1) cp_async8(&sm.ph[1][threadIdx.x], &a.phasor[QPSK_CHUNK + s0 + QPSK_CHUNK + threadIdx.x]);
+            }
         }
         cp_async_wait_all();
         bar_sync(BAR_FIR_DONE, QPSK_FIR_THREADS);
+        u64 nx[R];                                   // the next tile's mixed samples of this strip
+        {
+            const uint4 n0 = *reinterpret_cast<const uint4*>(stage);
+            const uint4 n1 = *reinterpret_cast<const uint4*>(stage + 8);
+            mix_regs(nx, n0, n1, &sm.ph[0][strip]);
+        }
 
-        const int ntiles = nframes * tiles_per_frame;
         for (int k = 0; k < ntiles; k++) {
-            const size_t tbase = (size_t)f0 * N + (size_t)k * QPSK_CHUNK;   // first sample of this tile in the launch
-            // shift own strip: current -> halo, then mix the staged PCM in as the new current tile
+            const size_t tbase = s0 + (size_t)k * QPSK_CHUNK;   // first sample of this tile in the launch
+            // shift own strip: current -> halo, then the new current tile from registers
 #pragma unroll
             for (int e = 0; e < R; e++) xrow[strip + e] = xcur[e];
-            {
-                const uint4 n0 = *reinterpret_cast<const uint4*>(stage);
-                const uint4 n1 = *reinterpret_cast<const uint4*>(stage + 8);
-                mix_store(xcur, n0, n1, &sm.ph[k & 1][strip]);
-            }
+#pragma unroll
+            for (int e = 0; e < R; e++) xcur[e] = nx[e];
             bar_sync(BAR_ROWS, QPSK_FIR_THREADS);
 
             if (k + 1 < ntiles) {
                 const int16_t* src = pcm_row + tbase + QPSK_CHUNK + strip;
                 cp_async16(stage, src);
                 cp_async16(stage + 8, src + 8);
-                if (threadIdx.x < QPSK_CHUNK) cp_async8(&sm.ph[(k + 1) & 1][threadIdx.x], &a.phasor[QPSK_CHUNK + tbase + QPSK_CHUNK + threadIdx.x]);
+                if (k + 2 < ntiles && threadIdx.x < QPSK_CHUNK)
+                    cp_async8(&sm.ph[(k + 2) % 3][threadIdx.x], &a.phasor[QPSK_CHUNK + tbase + 2 * QPSK_CHUNK + threadIdx.x]);
             }
 
             // matched filter: rrc_fir.c:22-28
             u64 acc[R];
-            fir_strip<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
+            fir_strip_main<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
+            cp_async_wait_all();                       // this thread's PCM of tile k+1 (and its phasor of tile k+2) landed
+            if (k + 1 < ntiles) {
+                const uint4 n0 = *reinterpret_cast<const uint4*>(stage);
+                const uint4 n1 = *reinterpret_cast<const uint4*>(stage + 8);
+                mix_regs(nx, n0, n1, &sm.ph[(k + 1) % 3][strip]);   // phasors of k+1 became visible at the last barrier
+            }
+            fir_strip_tail<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
             const int t = k % tiles_per_frame;
             // sm.out still holds the previous frame until the timing warps have decimated it
             if (t == 0 && k > 0) bar_sync(BAR_FREE, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
@@ -262,7 +301,6 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
 #pragma unroll
             for (int r = 0; r < R; r++) orow[r] = acc[r];
             bar_arrive(BAR_FULL0 + t, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
-            cp_async_wait_all();                       // next tile's PCM and phasors have landed
             bar_sync(BAR_FIR_DONE, QPSK_FIR_THREADS);
         }
     } else if (w < 10) {
