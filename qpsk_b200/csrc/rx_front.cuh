@@ -311,6 +311,9 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
         for (int fr = 0; fr < nframes; fr++) {
             const int f = f0 + fr;
             float av = 0.0f, mx = 0.0f;
+            float th[8];                                       // hv * k for the current maximum (all zero while max == 0)
+#pragma unroll
+            for (int kk = 0; kk < 8; kk++) th[kk] = 0.0f;
             u64 hist = 0ull;
             for (int t = 0; t < tiles_per_frame; t++) {
                 bar_sync(BAR_FULL0 + t, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
@@ -324,11 +327,15 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
                         av = __fadd_rn(av, fabsf(y));
                     }
                     av = __fmul_rn(av, 1.0f / SPS);              // av /= CYCLES, exact for a power of two
-                    if (av > mx) mx = av;
-                    const float hv = __fmul_rn(mx, 0.125f);      // max / 8.0f
+                    if (av > mx) {                                 // the bin edges hv*k only move when the running maximum does
+                        mx = av;
+                        const float hv = __fmul_rn(mx, 0.125f);  // max / 8.0f
+#pragma unroll
+                        for (int kk = 1; kk < 8; kk++) th[kk] = __fmul_rn(hv, (float)kk);
+                    }
                     int bin = 0;                                   // first k in 1..7 with av <= hv*k (hv*k is monotone in k)
 #pragma unroll
-                    for (int kk = 7; kk >= 1; kk--) bin = (av <= __fmul_rn(hv, (float)kk)) ? kk : bin;
+                    for (int kk = 7; kk >= 1; kk--) bin = (av <= th[kk]) ? kk : bin;
                     hist += 1ull << (8 * bin);                     // byte 0 collects "no bin"; counts <= 128 fit a byte
                 }
             }
