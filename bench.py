@@ -49,37 +49,69 @@ FP32_TAPS_PER_CLK_SM = {"exact": 32.0, "fast": 64.0}
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs (NVML every 20 ms; nvidia-smi as a fallback)."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.sm, self.reasons, self.sm_max = [], set(), None
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[gpu_index])
+                except Exception:
+                    idx = gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")]
+        if len(r) >= 6 and r[0].isdigit():
+            self.sm.append(int(r[0]))
+            self.sm_max = int(r[1]) if r[1].isdigit() else self.sm_max
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
+
+    def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.sm.append(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+                    mask = self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                        else self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for name, bit in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02 if self.nvml is not None else 0.1)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["clock sampling unavailable"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def synth_pcm_gpu(torch, qpsk_b200, nchan, nsamp, device, local, seed, rs=2400.0, esn0_db=20.0):
@@ -163,7 +195,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * (time.time() - t0) / (args.warmup + args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "reference rx_frame on host cores, bounded sample of the 65,536-channel 2400-baud config"},
+            "config": {"workload": "configs[2]: 65,536 concurrent 2400-baud channels per GPU x 64 frames x 512 samples (reference arm: the unmodified "
+                                   "reference rx_frame, qpsk.c:88-218, on every host core, each step a bounded ~2 s sample of such channels)",
+                       "channels_per_gpu": NCHAN, "frames_per_step": NFRAMES},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -237,8 +271,10 @@ def main():
     barrier()
     total_ms = ev0.elapsed_time(ev1)
     launches = rx.launch_count() - launches0
-    # per-kernel device time of the dominant kernel (events recorded on the launching stream inside the library)
-    for _ in range(3):
+    # device time of the dominant kernel: CUDA events recorded by the library around the kernel on the launching
+    # stream, read back after each of a second set of identical steps (reading them inside the timed loop would
+    # put a host synchronisation between the steps)
+    for _ in range(max(3, args.steps)):
         rx.process_device(pcm.data_ptr(), NFRAMES, stream)
         torch.cuda.synchronize()
         front_ms.append(rx.kernel_ms())
