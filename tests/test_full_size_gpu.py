@@ -1,0 +1,94 @@
+"""BASELINE.json's full sizes, checked through size-independent properties (the oracle only has to
+run a small base set):
+
+* config 2 size: 65,536 channels.  Every channel is one of 64 base channels; all replicas of a
+  base channel must produce exactly the oracle's decisions for it (channels are independent, so
+  any cross-channel leakage, slicing or padding error shows up as a replica that differs).
+* config 3 size: rrc_fir over 16,384 channels, 256 taps: scaling the input by a power of two
+  scales every output bit-exactly (rounding commutes with exact scaling), and a strided subset
+  equals the oracle.
+* config 4 size: 2^20 bursts of 256 points: a pure tone at a known bin per burst must come back as
+  that bin, for every burst.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_size_replicated_channels(oracle_lib):
+    import torch
+    import qpsk_b200
+    from qpsk_b200 import capi
+    from synth import make_pcm
+    o = oracle_lib.Oracle()
+    F, NB, C = 8, 64, 65536
+    base, _ = make_pcm(NB, F, seed=2024, esn0_db=18.0, oracle=o)
+    want = o.rx_run(base, want=("dibit", "phase", "freq"))
+    rng = np.random.default_rng(1)
+    which = rng.integers(0, NB, C)
+    which[:NB] = np.arange(NB)
+    d_base = torch.from_numpy(base).cuda()
+    d_pcm = d_base[torch.from_numpy(which).cuda()].contiguous()            # [C, F*512] on the device
+    rx = qpsk_b200.Receiver(C, F, decode_frames=True)
+    rx.process_device(d_pcm.data_ptr(), F)
+    rx.sync()
+    got = rx.read(capi.OUT_DIBITS)
+    track = rx.read(capi.OUT_TRACK)
+    packed_want = np.zeros((NB, F * 128 // 4), np.uint8)
+    for k in range(4):
+        packed_want |= (want["dibit"][:, k::4] << (2 * k)).astype(np.uint8)
+    assert np.array_equal(got, packed_want[which])
+    assert np.array_equal(track[..., 0], want["phase"][which]) and np.array_equal(track[..., 1], want["freq"][which])
+    n, _ = rx.crc_counters()
+    assert n == C * F
+    # the host-buffer entry point (sliced, pipelined) gives the same bytes
+    rx.reset()
+    host = rx.rx_frames(d_pcm.cpu().numpy())
+    assert np.array_equal(host, got)
+    rx.close()
+
+
+def test_config3_size_fir_scaling_property(oracle_lib):
+    import torch
+    import qpsk_b200
+    o = oracle_lib.Oracle()
+    C, T, ntaps = 16384, 4096, 256
+    taps = qpsk_b200.rrc_make(ntaps, 9600.0, 1200.0, 0.35)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    x = torch.randn((C, T, 2), generator=g, device="cuda")
+    x2 = (x * 4.0).contiguous()
+    keep = x[::997].cpu().numpy().copy()
+    f = qpsk_b200.Fir(taps, C)
+    f.filter_device(x.data_ptr(), T)
+    f.reset()
+    f.filter_device(x2.data_ptr(), T)
+    torch.cuda.synchronize()
+    assert torch.equal(x2, x * 4.0)                    # power-of-two scaling commutes with every rounding step
+    y = x[::997].cpu().numpy()
+    for i in range(0, keep.shape[0], 3):
+        ref = np.ascontiguousarray(keep[i]).view(np.complex64).reshape(-1).copy()
+        o.fir(taps, np.zeros(ntaps, np.complex64), ref)
+        assert np.array_equal(y[i].view(np.complex64).reshape(-1).view(np.uint32), ref.view(np.uint32))
+    f.close()
+
+
+def test_config4_size_tone_bins():
+    import torch
+    import qpsk_b200
+    n, nb = 256, 1 << 20
+    g = torch.Generator(device="cuda")
+    g.manual_seed(9)
+    bins = torch.randint(0, n, (nb,), generator=g, device="cuda")
+    t = torch.arange(n, device="cuda")
+    ph = (2 * np.pi / n) * (bins[:, None] * t[None, :]).float()
+    x = torch.stack([torch.cos(ph), torch.sin(ph)], dim=-1).contiguous()      # [nb, n, 2]
+    out_bin = torch.empty(nb, dtype=torch.int32, device="cuda")
+    out_mag = torch.empty(nb, dtype=torch.float32, device="cuda")
+    f = qpsk_b200.Fft(n)
+    f.argmax_device(x.data_ptr(), nb, out_bin.data_ptr(), out_mag.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out_bin.long(), bins)
+    assert torch.allclose(out_mag, torch.ones_like(out_mag), atol=1e-4)          # unit tone, forward scaled by 1/n
+    f.close()
