@@ -37,9 +37,14 @@ __device__ __forceinline__ unsigned costas_symbol(const float2 d, float& phase, 
     const float e = __fsub_rn((y.x > 0.0f ? y.y : -y.y), (y.y > 0.0f ? y.x : -y.x));
     freq = __fadd_rn(freq, __fmul_rn(p.beta, e));              // costas_loop.c:57
     phase = __fadd_rn(__fadd_rn(phase, freq), __fmul_rn(p.alpha, e));   // :58
-    // costas_loop.c:61-67: compares and subtracts in double against TAU
-    while ((double)phase > 6.283185307179586) phase = __double2float_rn(__dsub_rn((double)phase, 6.283185307179586));
-    while ((double)phase < -6.283185307179586) phase = __double2float_rn(__dadd_rn((double)phase, 6.283185307179586));
+    // costas_loop.c:61-67 compares and subtracts in double against TAU = 6.283185307179586.  The nearest floats
+    // around TAU are 0x40C90FDA = 6.2831850051879883 (< TAU) and 0x40C90FDB = 6.2831854820251465 (> TAU), so
+    // (double)phase > TAU  <=>  phase > 6.283185f as floats: the common case needs no conversion and no branch
+    // on a double compare; the correction itself (rare, once per ~2*pi/freq symbols) stays in double.
+    if (fabsf(phase) > 6.2831850051879883f) {
+        while ((double)phase > 6.283185307179586) phase = __double2float_rn(__dsub_rn((double)phase, 6.283185307179586));
+        while ((double)phase < -6.283185307179586) phase = __double2float_rn(__dadd_rn((double)phase, 6.283185307179586));
+    }
     if (freq > p.max_freq) freq = p.max_freq;                  // :69-74
     else if (freq < p.min_freq) freq = p.min_freq;
     const float2 r = cmul_exact(y, p.rot45);                   // qpsk.c:74-79

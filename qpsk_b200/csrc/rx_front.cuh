@@ -35,9 +35,11 @@ __global__ void phasor_table_kernel(float2* __restrict__ table, float2* __restri
         float2 ph = *phase_state;
         float2* out = table + QPSK_CHUNK;
         for (int f = 0; f < nframes; f++) {
+            float2* row = out + (size_t)f * frame_size;
+#pragma unroll 16
             for (int i = 0; i < frame_size; i++) {
                 ph = cmul_exact(ph, rect);                       // qpsk.c:115
-                out[(size_t)f * frame_size + i] = ph;
+                row[i] = ph;
             }
             // qpsk.c:120  phase /= cabsf(phase); glibc hypotf == (float)sqrt(re^2 + im^2) in double
             const double dr = (double)ph.x, di = (double)ph.y;
