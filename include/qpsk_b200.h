@@ -205,6 +205,9 @@ int qpsk_b200_tx_end_packet(qpsk_b200_tx *tx);
 /* tx_frame(samples, symbol, length) itself: arbitrary complex symbols, float [C][nsym][2] in host memory */
 int qpsk_b200_tx_symbols_host(qpsk_b200_tx *tx, const float *h_symbols, int nsym, int16_t *h_pcm);
 
+/* test hook: the device NCO (the restated glibc sinf/cosf the Costas kernel uses) evaluated over n host floats */
+int qpsk_b200_debug_nco(const float *h_in, float *h_sin, float *h_cos, int n, int device);
+
 #ifdef __cplusplus
 }
 #endif

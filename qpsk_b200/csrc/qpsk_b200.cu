@@ -1198,3 +1198,31 @@ extern "C" int qpsk_b200_tx_end_packet(qpsk_b200_tx* tx) {
     }
     return QPSK_B200_OK;
 }
+
+// =============================================================================================
+// test hook: the device NCO (sincosf_glibc) over arbitrary arguments
+// =============================================================================================
+__global__ void nco_probe_kernel(const float* __restrict__ in, float* __restrict__ s_out, float* __restrict__ c_out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s, c;
+    sincosf_glibc(in[i], s, c);
+    s_out[i] = s;
+    c_out[i] = c;
+}
+
+extern "C" int qpsk_b200_debug_nco(const float* h_in, float* h_sin, float* h_cos, int n, int device) {
+    if (!h_in || !h_sin || !h_cos || n < 1) return fail(QPSK_B200_ERR_ARG, "bad argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    DevBuf a, b, c;
+    CU(cudaMalloc(&a.p, sizeof(float) * n));
+    CU(cudaMalloc(&b.p, sizeof(float) * n));
+    CU(cudaMalloc(&c.p, sizeof(float) * n));
+    CU(cudaMemcpy(a.p, h_in, sizeof(float) * n, cudaMemcpyHostToDevice));
+    nco_probe_kernel<<<(n + 255) / 256, 256>>>((const float*)a.p, (float*)b.p, (float*)c.p, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(h_sin, b.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_cos, c.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return QPSK_B200_OK;
+}

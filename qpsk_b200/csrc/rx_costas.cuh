@@ -55,7 +55,7 @@ __device__ __forceinline__ unsigned costas_symbol(const float2 d, float& phase, 
 // (slot_base + f), after patching the last symbol of the frame this call produced (slot + 1).
 // CG loads bypass L1
 // for the fused kernel, where other warps of the same CTA have just written the ring.
-template <bool CG>
+template <bool CG, int AHEAD>
 __device__ __forceinline__ void costas_run_frame(const CostasArgs& a, const CostasParams& p, int f, int c, float& phase, float& freq) {
     const size_t slot_elems = (size_t)a.nsym * a.Cpad;
     const float2* cur = a.dec_ring + (size_t)((a.slot_base + f) % a.nslots) * slot_elems + c;
@@ -70,31 +70,40 @@ __device__ __forceinline__ void costas_run_frame(const CostasArgs& a, const Cost
             nxt[(size_t)(a.nsym - 1) * a.Cpad] = ld(cur + (size_t)j * a.Cpad);
         }
     }
-    // symbols are fetched four ahead of the recurrence; the loop stays rolled (four inlined symbol
-    // steps, ~9 KB) so that the Costas warp does not evict the filter loop from the instruction cache
+    // Symbols are fetched AHEAD groups of four ahead of the recurrence.  The fused kernel uses one group (the
+    // loop stays ~9 KB, so the Costas warp does not evict the filter loop from the instruction cache and the
+    // ring is L2-warm); the stand-alone kernel uses four (one output word): with few channels there are few
+    // warps per SM to hide the ~1 us DRAM latency of a cold ring.
     const int groups = a.nsym / 4;
-    float2 d[4], dn[4];
+    float2 d[AHEAD][4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) d[k] = ld(cur + (size_t)k * a.Cpad);
+    for (int q = 0; q < AHEAD; q++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) d[q][k] = ld(cur + (size_t)(q * 4 + k) * a.Cpad);
     unsigned bits = 0u;
 #pragma unroll 1
-    for (int gq = 0; gq < groups; gq++) {
-        if (gq + 1 < groups) {
+    for (int g0 = 0; g0 < groups; g0 += AHEAD) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) dn[k] = ld(cur + (size_t)((gq + 1) * 4 + k) * a.Cpad);
-        }
+        for (int q = 0; q < AHEAD; q++) {
+            const int gq = g0 + q;
+            float2 cur4[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float2 y;
-            bits |= costas_symbol(d[k], phase, freq, p, y) << (2 * ((gq & 3) * 4 + k));
-            if (a.costas_dbg != nullptr) a.costas_dbg[((size_t)f * a.nsym + gq * 4 + k) * a.Cpad + c] = y;
-        }
-        if ((gq & 3) == 3) {                                   // 16 dibits per output word
-            a.dibits_t[((size_t)f * (a.nsym / 16) + (gq >> 2)) * a.Cpad + c] = bits;
-            bits = 0u;
-        }
+            for (int k = 0; k < 4; k++) cur4[k] = d[q][k];
+            if (gq + AHEAD < groups) {                         // refill this slot for AHEAD groups later
 #pragma unroll
-        for (int k = 0; k < 4; k++) d[k] = dn[k];
+                for (int k = 0; k < 4; k++) d[q][k] = ld(cur + (size_t)((gq + AHEAD) * 4 + k) * a.Cpad);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float2 y;
+                bits |= costas_symbol(cur4[k], phase, freq, p, y) << (2 * ((gq & 3) * 4 + k));
+                if (a.costas_dbg != nullptr) a.costas_dbg[((size_t)f * a.nsym + gq * 4 + k) * a.Cpad + c] = y;
+            }
+            if ((gq & 3) == 3) {                               // 16 dibits per output word
+                a.dibits_t[((size_t)f * (a.nsym / 16) + (gq >> 2)) * a.Cpad + c] = bits;
+                bits = 0u;
+            }
+        }
     }
     a.track_t[(size_t)f * a.Cpad + c] = make_float2(phase, freq);
 }
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(128) costas_kernel(const CostasArgs a) {
     const CostasParams p = costas_params(a);
     const float2 st = a.loop_state[c];
     float phase = st.x, freq = st.y;
-    for (int f = 0; f < a.F; f++) costas_run_frame<false>(a, p, f, c, phase, freq);
+    for (int f = 0; f < a.F; f++) costas_run_frame<false, 4>(a, p, f, c, phase, freq);
     a.loop_state[c] = make_float2(phase, freq);
 }
 

@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
             // frame produced by this call, so it must wait until that one has been decimated
             while (sm.frames_decimated < fr + 1) __nanosleep(200);
             __threadfence();
-            costas_run_frame<true>(a.costas, p, f0 + fr, ch, phase, freq);
+            costas_run_frame<true, 1>(a.costas, p, f0 + fr, ch, phase, freq);
         }
         a.costas.loop_state[ch] = make_float2(phase, freq);
     }

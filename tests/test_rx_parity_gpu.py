@@ -198,3 +198,31 @@ def test_multi_slice_host_path(oracle_lib):
     rx2.sync()
     assert np.array_equal(qpsk_b200.unpack_dibits(rx2.read(capi.OUT_DIBITS)), got)
     rx.close(); rx2.close()
+
+
+def test_device_nco_equals_host_libm_on_a_dense_sweep():
+    """sincosf_glibc on the device against the host libm: every float within 2,000 ulps of each quadrant
+    threshold (where the reduction index steps), a dense random sweep of [-7, 7] and the tiny-argument branch."""
+    import ctypes as C
+    from qpsk_b200 import capi
+    L = capi.lib()
+    L.qpsk_b200_debug_nco.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    libm = C.CDLL("libm.so.6")
+    rng = np.random.default_rng(12)
+    parts = [rng.uniform(-7, 7, 2_000_000).astype(np.float32), (rng.uniform(-1, 1, 200_000) * 2.0 ** -11).astype(np.float32),
+             np.array([0.0, -0.0, 6.2831855, -6.2831855, 6.283185, -6.283185], np.float32)]
+    for k in range(1, 9):
+        c = np.float32(k * np.pi / 4).view(np.uint32).astype(np.int64)
+        bits = (c + np.arange(-2000, 2001)).astype(np.uint32)
+        parts += [bits.view(np.float32), -bits.view(np.float32)]
+    x = np.ascontiguousarray(np.concatenate(parts))
+    s, c = np.empty_like(x), np.empty_like(x)
+    capi.check(L.qpsk_b200_debug_nco(x.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), c.ctypes.data_as(C.c_void_p), len(x), 0))
+    # host libm, vectorised through a tiny C loop in the oracle library would be test infrastructure too; ctypes per call is fine for 2.2 M
+    libm.sinf.restype = libm.cosf.restype = C.c_float
+    libm.sinf.argtypes = libm.cosf.argtypes = [C.c_float]
+    idx = np.concatenate([np.arange(0, 2_000_000, 23), np.arange(2_000_000, len(x))])      # every threshold neighbour, a stride of the sweep
+    hs = np.array([libm.sinf(float(v)) for v in x[idx]], np.float32)
+    hc = np.array([libm.cosf(float(v)) for v in x[idx]], np.float32)
+    assert np.array_equal(s[idx].view(np.uint32), hs.view(np.uint32))
+    assert np.array_equal(c[idx].view(np.uint32), hc.view(np.uint32))
