@@ -5,8 +5,8 @@
 // FP32 (north_star tolerance 1e-5), and adds the estimator the reference never wrote: the first
 // strict maximum of |X[k]|^2 (mirroring the argmax idiom of qpsk.c:173-180).
 //
-// Stockham autosort, radix-8 stages (remainder stage radix 4 or 2), 8 points per thread in
-// registers.  Stage 0 reads the burst straight from HBM (coalesced), the last stage leaves its
+// Stockham autosort, radix-16 stages for n >= 256 (radix 8 below; the remainder stage is radix 8, 4 or 2),
+// 16 points per thread in registers: n = 256 crosses shared memory once, 4096 twice.  Stage 0 reads the burst straight from HBM (coalesced), the last stage leaves its
 // outputs in registers for the magnitude/argmax reduction (warp shuffles, then one shared-memory
 // hop across warps), so shared memory is crossed stages-1 times and HBM exactly once.
 #pragma once
@@ -16,9 +16,9 @@
 template <int LOG2N>
 struct FftCfg {
     static constexpr int N = 1 << LOG2N;
-    static constexpr int P = (N >= 8) ? 8 : N;                     // points per thread
+    static constexpr int P = (N >= 256) ? 16 : ((N >= 8) ? 8 : N); // points per thread = largest radix
     static constexpr int TPF = N / P;                              // threads per transform
-    static constexpr int THREADS = (TPF >= 256) ? TPF : 256;
+    static constexpr int THREADS = (TPF >= 128) ? TPF : 128;
     static constexpr int FPB = THREADS / TPF;                      // transforms per CTA pass
     static constexpr int PTS = FPB * N;
     static constexpr int SKEW_PTS = PTS + PTS / 16;                // float2 elements, one pad slot per 16: unit-stride and stride-8 accesses are conflict-free
@@ -66,6 +66,37 @@ __device__ __forceinline__ void dft_small<8>(float2 (&v)[8]) {
     v[3] = make_float2(e[3].x + o3.x, e[3].y + o3.y);      v[7] = make_float2(e[3].x - o3.x, e[3].y - o3.y);
 }
 
+template <>
+__device__ __forceinline__ void dft_small<16>(float2 (&v)[16]) {
+    // 16 = 4 x 4: four radix-4 transforms over stride-4 subsequences, twiddles W16^(q*r), four radix-4 across
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    float2 a[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        float2 t[4] = { v[r], v[r + 4], v[r + 8], v[r + 12] };
+        dft_small<4>(t);
+#pragma unroll
+        for (int q = 0; q < 4; q++) a[r][q] = t[q];
+    }
+    // a[r][q] *= W16^(r*q), W16 = exp(-2 pi i / 16)
+    const float2 w[10] = { {1.f, 0.f}, {c1, -s1}, {h, -h}, {s1, -c1}, {0.f, -1.f}, {-s1, -c1}, {-h, -h}, {-c1, -s1}, {-1.f, 0.f}, {-c1, s1} };
+#pragma unroll
+    for (int r = 1; r < 4; r++)
+#pragma unroll
+        for (int q = 1; q < 4; q++) {
+            const int e = r * q;                      // 1,2,3,2,4,6,3,6,9
+            if (e == 4) a[r][q] = make_float2(a[r][q].y, -a[r][q].x);
+            else a[r][q] = cmulf(a[r][q], w[e]);
+        }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        float2 t[4] = { a[0][q], a[1][q], a[2][q], a[3][q] };
+        dft_small<4>(t);
+#pragma unroll
+        for (int p = 0; p < 4; p++) v[q + 4 * p] = t[p];
+    }
+}
+
 __device__ __forceinline__ int fft_skew(int i) { return i + (i >> 4); }
 
 struct FftArgs {
@@ -104,11 +135,19 @@ __device__ __forceinline__ void fft_stage(float2 (&pts)[FftCfg<LOG2N>::P], float
             } else if (R == 4) {
                 const float2 w2 = stw[2 * ti], w3 = cmulf(w1, w2);
                 v[1] = cmulf(v[1], w1); v[2] = cmulf(v[2], w2); v[3] = cmulf(v[3], w3);
-            } else {
+            } else if (R == 8) {
                 const float2 w2 = stw[2 * ti], w4 = stw[4 * ti];
                 const float2 w3 = cmulf(w1, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
                 v[1] = cmulf(v[1], w1); v[2] = cmulf(v[2], w2); v[3] = cmulf(v[3], w3); v[4] = cmulf(v[4], w4);
                 v[5] = cmulf(v[5], w5); v[6] = cmulf(v[6], w6); v[7] = cmulf(v[7], w7);
+            } else {
+                const float2 w2 = stw[2 * ti], w4 = stw[4 * ti], w8 = stw[8 * ti];
+                const float2 w3 = cmulf(w1, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
+                v[1] = cmulf(v[1], w1); v[2] = cmulf(v[2], w2); v[3] = cmulf(v[3], w3); v[4] = cmulf(v[4], w4);
+                v[5] = cmulf(v[5], w5); v[6] = cmulf(v[6], w6); v[7] = cmulf(v[7], w7); v[8] = cmulf(v[8], w8);
+                v[9] = cmulf(v[9], cmulf(w8, w1)); v[10] = cmulf(v[10], cmulf(w8, w2)); v[11] = cmulf(v[11], cmulf(w8, w3));
+                v[12] = cmulf(v[12], cmulf(w8, w4)); v[13] = cmulf(v[13], cmulf(w8, w5)); v[14] = cmulf(v[14], cmulf(w8, w6));
+                v[15] = cmulf(v[15], cmulf(w8, w7));
             }
         }
         dft_small<R>(v);
@@ -135,7 +174,8 @@ __device__ __forceinline__ void fft_stages(float2 (&pts)[FftCfg<LOG2N>::P], floa
                                            const float2* gin, int j, int base, bool active, float imsgn) {
     constexpr int N = FftCfg<LOG2N>::N;
     constexpr int REM = N / NS;
-    constexpr int R = (REM >= 8) ? 8 : REM;
+    constexpr int RMAX = FftCfg<LOG2N>::P;
+    constexpr int R = (REM >= RMAX) ? RMAX : REM;
     constexpr bool LAST = (NS * R == N);
     fft_stage<LOG2N, R, NS, FIRST, LAST>(pts, sdat, stw, gin, j, base, active, imsgn);
     if constexpr (!LAST) fft_stages<LOG2N, NS * R, false>(pts, sdat, stw, gin, j, base, active, imsgn);
@@ -144,7 +184,7 @@ __device__ __forceinline__ void fft_stages(float2 (&pts)[FftCfg<LOG2N>::P], floa
 // output index of pts[i] after the last stage (radix RLAST, sub-transform length NSL = N / RLAST)
 template <int LOG2N>
 struct FftLast {
-    static constexpr int last_ns() { int ns = 1; while ((1 << LOG2N) / ns > 8) ns *= 8; return ns; }
+    static constexpr int last_ns() { int ns = 1; while ((1 << LOG2N) / ns > FftCfg<LOG2N>::P) ns *= FftCfg<LOG2N>::P; return ns; }
     static constexpr int NSL = last_ns();
     static constexpr int RLAST = (1 << LOG2N) / NSL;
 };
