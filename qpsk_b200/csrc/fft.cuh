@@ -22,75 +22,91 @@ struct FftCfg {
     static constexpr int FPB = THREADS / TPF;                      // transforms per CTA pass
     static constexpr int PTS = FPB * N;
     static constexpr int SKEW_PTS = PTS + PTS / 16;                // float2 elements, one pad slot per 16: unit-stride and stride-8 accesses are conflict-free
-    static constexpr int TW = (N >= 2) ? N / 2 : 1;
+    // per-stage twiddle tables: stage (NS, R) holds exp(-2 pi i m k / (NS R)) for m = 1..R-1, k < NS, laid out [m-1][k]
+    // so that the lanes of a warp (consecutive k) read consecutive words -- no bank conflicts, no products to form
+    static constexpr int tw_count() { int ns = 1, tot = 0; while (ns < N) { int rem = N / ns; int r = rem >= P ? P : rem; if (ns > 1) tot += (r - 1) * ns; ns *= r; } return tot > 0 ? tot : 1; }
+    static constexpr int TW = tw_count();
     static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + sizeof(float2) * TW + sizeof(float) * 64 + sizeof(int) * 64;
 };
 
-// tolerance-mode arithmetic (1e-5): explicit fused multiply-adds, since the TU is built with -fmad=false
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-    return make_float2(__fmaf_rn(a.x, b.x, -(a.y * b.y)), __fmaf_rn(a.x, b.y, a.y * b.x));
+// Tolerance-mode arithmetic (1e-5) on packed FP32 pairs: one complex value per 64-bit register.  FADD2 takes
+// per-operand swizzle/negate modifiers, so a +-i rotation folded into an add costs nothing, and a complex
+// multiply is FMUL2 + FFMA2 (scalar-broadcast and swapped operands are modifiers too) -- half the issue slots
+// of the scalar form, which is what this kernel is short of (profiles/r01_notes.md).
+typedef u64 c64;
+__device__ __forceinline__ c64 cadd(c64 a, c64 b) { return add2(a, b); }
+__device__ __forceinline__ c64 csub(c64 a, c64 b) { c64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// a + (-i) b  and  a - (-i) b = a + i b ;  (-i)(x + iy) = y - ix
+__device__ __forceinline__ c64 cadd_mi(c64 a, c64 b) { float x, y; unpack2(b, x, y); return add2(a, pack2(y, -x)); }
+__device__ __forceinline__ c64 cadd_pi(c64 a, c64 b) { float x, y; unpack2(b, x, y); return add2(a, pack2(-y, x)); }
+__device__ __forceinline__ c64 cmul(c64 a, c64 w) {          // (ax wx - ay wy, ax wy + ay wx)
+    float ax, ay, wx, wy, tx, ty;
+    unpack2(a, ax, ay);
+    unpack2(w, wx, wy);
+    unpack2(mul2(pack2(ay, ay), pack2(wy, wx)), tx, ty);
+    return fma2(pack2(ax, ax), w, pack2(-tx, ty));
 }
+__device__ __forceinline__ c64 cmul_c(c64 a, float wx, float wy) { return cmul(a, pack2(wx, wy)); }
+__device__ __forceinline__ c64 cscale(c64 a, float s) { return mul2(a, pack2(s, s)); }
+__device__ __forceinline__ c64 cconj_if(c64 a, float sgn) { float x, y; unpack2(a, x, y); return pack2(x, y * sgn); }
 
 // forward R-point DFT in registers, natural order in and out
 template <int R>
-__device__ __forceinline__ void dft_small(float2 (&v)[R]);
+__device__ __forceinline__ void dft_small(c64 (&v)[R]);
 
 template <>
-__device__ __forceinline__ void dft_small<2>(float2 (&v)[2]) {
-    const float2 a = v[0], b = v[1];
-    v[0] = make_float2(a.x + b.x, a.y + b.y);
-    v[1] = make_float2(a.x - b.x, a.y - b.y);
+__device__ __forceinline__ void dft_small<2>(c64 (&v)[2]) {
+    const c64 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
 }
 template <>
-__device__ __forceinline__ void dft_small<4>(float2 (&v)[4]) {
-    const float2 s02 = make_float2(v[0].x + v[2].x, v[0].y + v[2].y), d02 = make_float2(v[0].x - v[2].x, v[0].y - v[2].y);
-    const float2 s13 = make_float2(v[1].x + v[3].x, v[1].y + v[3].y), d13 = make_float2(v[1].x - v[3].x, v[1].y - v[3].y);
-    v[0] = make_float2(s02.x + s13.x, s02.y + s13.y);
-    v[2] = make_float2(s02.x - s13.x, s02.y - s13.y);
-    v[1] = make_float2(d02.x + d13.y, d02.y - d13.x);      // d02 + (-i) d13
-    v[3] = make_float2(d02.x - d13.y, d02.y + d13.x);      // d02 + (+i) d13
+__device__ __forceinline__ void dft_small<4>(c64 (&v)[4]) {
+    const c64 s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
+    const c64 s13 = cadd(v[1], v[3]), d13 = csub(v[1], v[3]);
+    v[0] = cadd(s02, s13);
+    v[2] = csub(s02, s13);
+    v[1] = cadd_mi(d02, d13);      // d02 + (-i) d13
+    v[3] = cadd_pi(d02, d13);      // d02 + (+i) d13
 }
 template <>
-__device__ __forceinline__ void dft_small<8>(float2 (&v)[8]) {
+__device__ __forceinline__ void dft_small<8>(c64 (&v)[8]) {
     const float h = 0.70710678118654752f;
-    float2 e[4] = { v[0], v[2], v[4], v[6] }, o[4] = { v[1], v[3], v[5], v[7] };
+    c64 e[4] = { v[0], v[2], v[4], v[6] }, o[4] = { v[1], v[3], v[5], v[7] };
     dft_small<4>(e);
     dft_small<4>(o);
     // o[q] *= exp(-2 pi i q / 8)
-    const float2 o1 = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
-    const float2 o2 = make_float2(o[2].y, -o[2].x);
-    const float2 o3 = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
-    v[0] = make_float2(e[0].x + o[0].x, e[0].y + o[0].y);  v[4] = make_float2(e[0].x - o[0].x, e[0].y - o[0].y);
-    v[1] = make_float2(e[1].x + o1.x, e[1].y + o1.y);      v[5] = make_float2(e[1].x - o1.x, e[1].y - o1.y);
-    v[2] = make_float2(e[2].x + o2.x, e[2].y + o2.y);      v[6] = make_float2(e[2].x - o2.x, e[2].y - o2.y);
-    v[3] = make_float2(e[3].x + o3.x, e[3].y + o3.y);      v[7] = make_float2(e[3].x - o3.x, e[3].y - o3.y);
+    const c64 o1 = cmul_c(o[1], h, -h);
+    const c64 o3 = cmul_c(o[3], -h, -h);
+    v[0] = cadd(e[0], o[0]);     v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);       v[5] = csub(e[1], o1);
+    v[2] = cadd_mi(e[2], o[2]);  v[6] = cadd_pi(e[2], o[2]);
+    v[3] = cadd(e[3], o3);       v[7] = csub(e[3], o3);
 }
-
 template <>
-__device__ __forceinline__ void dft_small<16>(float2 (&v)[16]) {
+__device__ __forceinline__ void dft_small<16>(c64 (&v)[16]) {
     // 16 = 4 x 4: four radix-4 transforms over stride-4 subsequences, twiddles W16^(q*r), four radix-4 across
     const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
-    float2 a[4][4];
+    c64 a[4][4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        float2 t[4] = { v[r], v[r + 4], v[r + 8], v[r + 12] };
+        c64 t[4] = { v[r], v[r + 4], v[r + 8], v[r + 12] };
         dft_small<4>(t);
 #pragma unroll
         for (int q = 0; q < 4; q++) a[r][q] = t[q];
     }
-    // a[r][q] *= W16^(r*q), W16 = exp(-2 pi i / 16)
-    const float2 w[10] = { {1.f, 0.f}, {c1, -s1}, {h, -h}, {s1, -c1}, {0.f, -1.f}, {-s1, -c1}, {-h, -h}, {-c1, -s1}, {-1.f, 0.f}, {-c1, s1} };
-#pragma unroll
-    for (int r = 1; r < 4; r++)
-#pragma unroll
-        for (int q = 1; q < 4; q++) {
-            const int e = r * q;                      // 1,2,3,2,4,6,3,6,9
-            if (e == 4) a[r][q] = make_float2(a[r][q].y, -a[r][q].x);
-            else a[r][q] = cmulf(a[r][q], w[e]);
-        }
+    // a[r][q] *= W16^(r*q), W16 = exp(-2 pi i / 16); the e = 4 case (-i) is folded into the second layer
+    a[1][1] = cmul_c(a[1][1], c1, -s1);  a[1][2] = cmul_c(a[1][2], h, -h);    a[1][3] = cmul_c(a[1][3], s1, -c1);
+    a[2][1] = cmul_c(a[2][1], h, -h);    /* a[2][2] *= -i below */           a[2][3] = cmul_c(a[2][3], -h, -h);
+    a[3][1] = cmul_c(a[3][1], s1, -c1);  a[3][2] = cmul_c(a[3][2], -h, -h);   a[3][3] = cmul_c(a[3][3], -c1, s1);
+    {
+        float x, y;
+        unpack2(a[2][2], x, y);
+        a[2][2] = pack2(y, -x);
+    }
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-        float2 t[4] = { a[0][q], a[1][q], a[2][q], a[3][q] };
+        c64 t[4] = { a[0][q], a[1][q], a[2][q], a[3][q] };
         dft_small<4>(t);
 #pragma unroll
         for (int p = 0; p < 4; p++) v[q + 4 * p] = t[p];
@@ -104,7 +120,7 @@ struct FftArgs {
     float2* spectrum;      // optional [nbursts][N]
     int* bin;              // optional [nbursts] argmax bin
     float* mag2;           // optional [nbursts] |X[bin]|^2 (after scaling)
-    const float2* tw;      // [N/2] exp(-2 pi i t / N), host-computed in double
+    const float2* tw;      // per-stage twiddle tables (FftCfg::TW entries), host-computed in double
     int nbursts;
     float im_sign;         // +1 forward, -1 inverse (inverse = conj(FFT(conj(x))))
     float scale;           // 1/N forward (fft.c:105-107), 1 inverse (fft.c:122-128)
@@ -112,43 +128,24 @@ struct FftArgs {
 
 // one Stockham stage for the P points a thread owns: radix R, sub-transform length NS already done
 template <int LOG2N, int R, int NS, bool FIRST, bool LAST>
-__device__ __forceinline__ void fft_stage(float2 (&pts)[FftCfg<LOG2N>::P], float2* sdat, const float2* stw,
+__device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw,
                                           const float2* gin, int j, int base, bool active, float imsgn) {
     using Cfg = FftCfg<LOG2N>;
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R;   // NB butterflies per thread
 #pragma unroll
     for (int t = 0; t < NB; t++) {
         const int jj = j + t * TPF;                  // butterfly index in [0, N/R)
-        float2 v[R];
+        c64 v[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int idx = jj + r * (N / R);
-            if (FIRST) { v[r] = active ? gin[idx] : make_float2(0.f, 0.f); v[r].y *= imsgn; }   // inverse = conj(FFT(conj x))
+            if (FIRST) v[r] = cconj_if(active ? reinterpret_cast<const c64*>(gin)[idx] : 0ull, imsgn);   // inverse = conj(FFT(conj x))
             else v[r] = sdat[fft_skew(base + idx)];
         }
         if (NS > 1) {
             const int k = jj % NS;
-            const int ti = k * (N / (NS * R));       // w1 = exp(-2 pi i k / (NS*R))
-            const float2 w1 = stw[ti];
-            if (R == 2) {
-                v[1] = cmulf(v[1], w1);
-            } else if (R == 4) {
-                const float2 w2 = stw[2 * ti], w3 = cmulf(w1, w2);
-                v[1] = cmulf(v[1], w1); v[2] = cmulf(v[2], w2); v[3] = cmulf(v[3], w3);
-            } else if (R == 8) {
-                const float2 w2 = stw[2 * ti], w4 = stw[4 * ti];
-                const float2 w3 = cmulf(w1, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
-                v[1] = cmulf(v[1], w1); v[2] = cmulf(v[2], w2); v[3] = cmulf(v[3], w3); v[4] = cmulf(v[4], w4);
-                v[5] = cmulf(v[5], w5); v[6] = cmulf(v[6], w6); v[7] = cmulf(v[7], w7);
-            } else {
-                const float2 w2 = stw[2 * ti], w4 = stw[4 * ti], w8 = stw[8 * ti];
-                const float2 w3 = cmulf(w1, w2), w5 = cmulf(w4, w1), w6 = cmulf(w4, w2), w7 = cmulf(w4, w3);
-                v[1] = cmulf(v[1], w1); v[2] = cmulf(v[2], w2); v[3] = cmulf(v[3], w3); v[4] = cmulf(v[4], w4);
-                v[5] = cmulf(v[5], w5); v[6] = cmulf(v[6], w6); v[7] = cmulf(v[7], w7); v[8] = cmulf(v[8], w8);
-                v[9] = cmulf(v[9], cmulf(w8, w1)); v[10] = cmulf(v[10], cmulf(w8, w2)); v[11] = cmulf(v[11], cmulf(w8, w3));
-                v[12] = cmulf(v[12], cmulf(w8, w4)); v[13] = cmulf(v[13], cmulf(w8, w5)); v[14] = cmulf(v[14], cmulf(w8, w6));
-                v[15] = cmulf(v[15], cmulf(w8, w7));
-            }
+#pragma unroll
+            for (int m = 1; m < R; m++) v[m] = cmul(v[m], stw[(m - 1) * NS + k]);
         }
         dft_small<R>(v);
 #pragma unroll
@@ -170,7 +167,7 @@ __device__ __forceinline__ void fft_stage(float2 (&pts)[FftCfg<LOG2N>::P], float
 }
 
 template <int LOG2N, int NS, bool FIRST>
-__device__ __forceinline__ void fft_stages(float2 (&pts)[FftCfg<LOG2N>::P], float2* sdat, const float2* stw,
+__device__ __forceinline__ void fft_stages(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw,
                                            const float2* gin, int j, int base, bool active, float imsgn) {
     constexpr int N = FftCfg<LOG2N>::N;
     constexpr int REM = N / NS;
@@ -178,7 +175,7 @@ __device__ __forceinline__ void fft_stages(float2 (&pts)[FftCfg<LOG2N>::P], floa
     constexpr int R = (REM >= RMAX) ? RMAX : REM;
     constexpr bool LAST = (NS * R == N);
     fft_stage<LOG2N, R, NS, FIRST, LAST>(pts, sdat, stw, gin, j, base, active, imsgn);
-    if constexpr (!LAST) fft_stages<LOG2N, NS * R, false>(pts, sdat, stw, gin, j, base, active, imsgn);
+    if constexpr (!LAST) fft_stages<LOG2N, NS * R, false>(pts, sdat, stw + (NS > 1 ? (R - 1) * NS : 0), gin, j, base, active, imsgn);
 }
 
 // output index of pts[i] after the last stage (radix RLAST, sub-transform length NSL = N / RLAST)
@@ -200,12 +197,12 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
     using Cfg = FftCfg<LOG2N>;
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, FPB = Cfg::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* sdat = reinterpret_cast<float2*>(smem_raw);
-    float2* stw = sdat + Cfg::SKEW_PTS;
+    c64* sdat = reinterpret_cast<c64*>(smem_raw);
+    c64* stw = sdat + Cfg::SKEW_PTS;
     float* red_mag = reinterpret_cast<float*>(stw + Cfg::TW);
     int* red_idx = reinterpret_cast<int*>(red_mag + 64);
 
-    for (int i = threadIdx.x; i < Cfg::TW; i += blockDim.x) stw[i] = a.tw[i];
+    for (int i = threadIdx.x; i < Cfg::TW; i += blockDim.x) stw[i] = reinterpret_cast<const c64*>(a.tw)[i];
     __syncthreads();
 
     const int fl = threadIdx.x / TPF, j = threadIdx.x % TPF;
@@ -214,7 +211,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
         const int b = b0 + fl;
         const bool active = b < a.nbursts;
         const float2* gin = a.in + (size_t)(active ? b : 0) * N;
-        float2 pts[P];
+        c64 pts[P];
         fft_stages<LOG2N, 1, true>(pts, sdat, stw, gin, j, base, active, a.im_sign);
         // ---- epilogue: scale, optional spectrum store, |X|^2 argmax
         float best = -1.0f;
@@ -222,7 +219,10 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
 #pragma unroll
         for (int i = 0; i < P; i++) {
             const int idx = fft_out_index<LOG2N>(j, i);
-            const float2 x = make_float2(pts[i].x * a.scale, pts[i].y * a.scale * a.im_sign);
+            float2 x;
+            unpack2(pts[i], x.x, x.y);
+            x.x *= a.scale;
+            x.y *= a.scale * a.im_sign;
             if (a.spectrum != nullptr && active) a.spectrum[(size_t)b * N + idx] = x;
             const float m = x.x * x.x + x.y * x.y;
             if (m > best || (m == best && idx < besti)) { best = m; besti = idx; }

@@ -760,12 +760,27 @@ extern "C" int qpsk_b200_fft_create(int n, int device, qpsk_b200_fft** out) {
     memset(f, 0, sizeof *f);
     f->n = n; f->log2n = lg; f->device = device;
     cudaDeviceGetAttribute(&f->nsm, cudaDevAttrMultiProcessorCount, device);
-    // twiddles exp(-2 pi i t / n), t < n/2, evaluated in double on the host (fft.c:55-56) and rounded once
-    const int ntw = n / 2 > 0 ? n / 2 : 1;
+    // per-stage twiddles exp(-2 pi i m k / (ns r)), evaluated in double on the host (fft.c:55-56) and rounded once;
+    // the stage sequence mirrors FftCfg / fft_stages: radix = min(points per thread, remaining length)
+    const int pmax = n >= 256 ? 16 : (n >= 8 ? 8 : n);
+    int ntw = 0;
+    for (int ns = 1; ns < n;) { const int rem = n / ns, r = rem >= pmax ? pmax : rem; if (ns > 1) ntw += (r - 1) * ns; ns *= r; }
+    if (ntw < 1) ntw = 1;
     float2* tw = new float2[ntw];
-    for (int t = 0; t < ntw; t++) {
-        const double ang = kTau * (double)t / (double)n;
-        tw[t] = make_float2((float)cos(ang), (float)(-sin(ang)));
+    tw[0] = make_float2(1.0f, 0.0f);
+    {
+        int pos = 0;
+        for (int ns = 1; ns < n;) {
+            const int rem = n / ns, r = rem >= pmax ? pmax : rem;
+            if (ns > 1) {
+                for (int m = 1; m < r; m++)
+                    for (int k = 0; k < ns; k++) {
+                        const double ang = kTau * (double)m * (double)k / ((double)ns * (double)r);
+                        tw[pos++] = make_float2((float)cos(ang), (float)(-sin(ang)));
+                    }
+            }
+            ns *= r;
+        }
     }
     cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     for (auto& ev : f->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
