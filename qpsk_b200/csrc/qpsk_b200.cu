@@ -81,6 +81,8 @@ struct qpsk_b200_rx {
     size_t stage_slice_bytes;
     cudaStream_t s_in, s_out;
     cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
+    float* d_front_scratch; // front-end per-CTA frame scratch (lazy, grow-only)
+    size_t front_scratch_bytes;
     void* d_scratch;        // transposed download staging (lazy)
     size_t scratch_bytes;
 };
@@ -113,7 +115,7 @@ static int rx_free(qpsk_b200_rx* rx) {
     void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
                      rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters,
-                     rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch };
+                     rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev) if (e) cudaEventDestroy(e);
     for (int b = 0; b < 2; b++) {
@@ -134,6 +136,8 @@ template <int NTAPS, int SPS, int MODE>
 static cudaError_t launch_front(const RxFrontArgs& a, int grid, cudaStream_t s) {
     const size_t smem = sizeof(RxFrontSmem<SPS>);
     cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<NTAPS, SPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rx_front_kernel<NTAPS, SPS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     rx_front_kernel<NTAPS, SPS, MODE><<<grid, QPSK_FRONT_THREADS, smem, s>>>(a);
     return cudaGetLastError();
@@ -302,6 +306,17 @@ static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, 
     fa.frames_per_block = (F + fblocks - 1) / fblocks;
     fblocks = (F + fa.frames_per_block - 1) / fa.frames_per_block;
     const int grid = ngroups * fblocks;
+    // per-CTA frame scratch (512 samples x 2 components x 32 lanes of float); rewritten every frame, so it lives in L2
+    {
+        const size_t need = (size_t)grid * 512 * 2 * QPSK_GROUP * sizeof(float);
+        if (rx->front_scratch_bytes < need) {
+            CU(cudaStreamSynchronize(s));
+            if (rx->d_front_scratch) { cudaFree(rx->d_front_scratch); rx->d_front_scratch = nullptr; rx->front_scratch_bytes = 0; }
+            CU(cudaMalloc((void**)&rx->d_front_scratch, need));
+            rx->front_scratch_bytes = need;
+        }
+        fa.scratch = rx->d_front_scratch;
+    }
 
     // K3 arguments: the Costas loop + slicer, fused into K1 when every CTA owns whole streams
     CostasArgs ca;

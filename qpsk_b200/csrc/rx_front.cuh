@@ -125,6 +125,7 @@ struct RxFrontArgs {
     float2* dec_ring;          // [nslots][nsym][Cpad] decimated symbols, channel-fastest
     int*    index_t;           // [F][Cpad] timing index per frame
     float2* fir_dbg;           // optional [C][F*N] matched-filter output (parity taps), may be null
+    float*  scratch;           // [grid][512][2][32] the current frame's filter output per CTA (L2-resident: rewritten every frame)
     int C, Cpad, F, N;
     int chan_base, chan_count; // this launch covers channels [chan_base, chan_base + chan_count); pcm is indexed from chan_base
     int frames_per_block;      // frames handled by one CTA
@@ -137,15 +138,17 @@ struct RxFrontArgs {
 template <int SPS>
 struct RxFrontSmem {
     static constexpr int XS = 2 * QPSK_CHUNK + 1;   // odd row stride (in float2) => conflict-free 64-bit access
-    static constexpr int OS = 512 + 1;
+    static constexpr int OS = QPSK_CHUNK + 1;
     u64 x[QPSK_GROUP][XS];        // [0,128) previous tile (halo), [128,256) current tile
-    u64 out[QPSK_GROUP][OS];      // matched-filter output of the current frame
-    float2 ph[3][QPSK_CHUNK];     // mixer phasors of tiles k, k+1, k+2 (ring)
+    u64 out[QPSK_GROUP][OS];      // raw matched-filter sums of ONE tile, handed from the filter warps to the timing warps
+    float2 ph[2][QPSK_CHUNK];     // mixer phasors of the current / next tile
     short pcm[QPSK_GROUP][QPSK_CHUNK + 8];   // cp.async landing zone for the next tile's PCM (row stride 272 B: conflict-free 16 B reads)
     u64 hist[2][QPSK_GROUP];      // 7 x 8-bit amplitude-bin counters for I and for Q
     int index[QPSK_GROUP];
     volatile int frames_decimated; // frames whose symbols are in the ring (producer: timing warps, consumer: Costas warp)
 };
+// 110 KB: two CTAs per SM.  While one CTA sits at a barrier or in its fill phase the other one keeps the FP32
+// pipe busy, and two Costas warps per SM run concurrently, so the loop's latency no longer paces the filter.
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -188,9 +191,9 @@ __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile(
 
 enum { BAR_ROWS = 1,      // FIR warps: sample rows of the tile are in shared memory
        BAR_FIR_DONE = 2,  // FIR warps: every strip has finished reading the rows
-       BAR_FULL0 = 3,     // +t: matched-filter outputs of tile t of the frame are in sm.out (FIR arrive, timing sync)
-       BAR_FREE = 7,      // sm.out of the previous frame has been consumed (timing arrive, FIR sync)
-       BAR_AUX = 8 };     // the two timing warps among themselves
+       BAR_FULL = 3,      // the raw sums of a tile are in sm.out (FIR arrive, timing sync)
+       BAR_EMPTY = 4,     // the timing warps have consumed sm.out (timing arrive, FIR sync)
+       BAR_AUX = 5 };     // the two timing warps among themselves
 #define QPSK_FIR_THREADS 256
 #define QPSK_AUX_THREADS 64
 #define QPSK_FRONT_THREADS 352   // 8 FIR warps + 2 timing/decimation warps + 1 Costas warp
@@ -200,7 +203,7 @@ enum { BAR_ROWS = 1,      // FIR warps: sample rows of the tile are in shared me
 // the Costas loop of the previous frame when the CTA owns whole streams.  The auxiliary warps live
 // in the issue slots the packed-FP32 filter leaves free, so the filter never waits for them.
 template <int NTAPS, int SPS, int MODE>
-__global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const RxFrontArgs a) {
+__global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const RxFrontArgs a) {
     static_assert(NTAPS - 1 <= QPSK_CHUNK - 2, "halo must fit in one previous tile");
     constexpr int R = 16;
     constexpr int NSYM = 512 / SPS, TILE_SYMS = QPSK_CHUNK / SPS;
@@ -243,9 +246,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
             for (int e = 0; e < 16; e++) phr[e] = ph[e];
             mix_store(xcur, p0, p1, phr);
         }
-        // PCM of the next tile and phasors of the tile after it travel HBM -> shared memory by cp.async while
-        // the filter runs; the next tile is mixed into registers inside the filter's tail (its loads, conversions
-        // and multiplies hide behind the FP pipe), so that only the stores remain between the two barriers
+        // PCM and phasors of the next tile travel HBM -> shared memory by cp.async while the filter runs
         short* stage = &sm.pcm[lane][strip];
         const size_t s0 = (size_t)f0 * N;
         const int ntiles = nframes * tiles_per_frame;
@@ -253,56 +254,42 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
             const int16_t* src = pcm_row + s0 + strip;
             cp_async16(stage, src);
             cp_async16(stage + 8, src + 8);
-            if (threadIdx.x < QPSK_CHUNK) {
-                cp_async8(&sm.ph[0][threadIdx.x], &a.phasor[QPSK_CHUNK + s0 + threadIdx.x]);
-                if (ntiles > 1) cp_async8(&sm.ph[1][threadIdx.x], &a.phasor[QPSK_CHUNK + s0 + QPSK_CHUNK + threadIdx.x]);
-            }
+            if (threadIdx.x < QPSK_CHUNK) cp_async8(&sm.ph[0][threadIdx.x], &a.phasor[QPSK_CHUNK + s0 + threadIdx.x]);
         }
         cp_async_wait_all();
         bar_sync(BAR_FIR_DONE, QPSK_FIR_THREADS);
-        u64 nx[R];                                   // the next tile's mixed samples of this strip
-        {
-            const uint4 n0 = *reinterpret_cast<const uint4*>(stage);
-            const uint4 n1 = *reinterpret_cast<const uint4*>(stage + 8);
-            mix_regs(nx, n0, n1, &sm.ph[0][strip]);
-        }
 
         for (int k = 0; k < ntiles; k++) {
             const size_t tbase = s0 + (size_t)k * QPSK_CHUNK;   // first sample of this tile in the launch
-            // shift own strip: current -> halo, then the new current tile from registers
+            // shift own strip: current -> halo, then mix the staged PCM in as the new current tile
 #pragma unroll
             for (int e = 0; e < R; e++) xrow[strip + e] = xcur[e];
-#pragma unroll
-            for (int e = 0; e < R; e++) xcur[e] = nx[e];
+            {
+                const uint4 n0 = *reinterpret_cast<const uint4*>(stage);
+                const uint4 n1 = *reinterpret_cast<const uint4*>(stage + 8);
+                mix_store(xcur, n0, n1, &sm.ph[k & 1][strip]);
+            }
             bar_sync(BAR_ROWS, QPSK_FIR_THREADS);
 
             if (k + 1 < ntiles) {
                 const int16_t* src = pcm_row + tbase + QPSK_CHUNK + strip;
                 cp_async16(stage, src);
                 cp_async16(stage + 8, src + 8);
-                if (k + 2 < ntiles && threadIdx.x < QPSK_CHUNK)
-                    cp_async8(&sm.ph[(k + 2) % 3][threadIdx.x], &a.phasor[QPSK_CHUNK + tbase + 2 * QPSK_CHUNK + threadIdx.x]);
+                if (threadIdx.x < QPSK_CHUNK) cp_async8(&sm.ph[(k + 1) & 1][threadIdx.x], &a.phasor[QPSK_CHUNK + tbase + QPSK_CHUNK + threadIdx.x]);
             }
 
             // matched filter: rrc_fir.c:22-28
             u64 acc[R];
-            fir_strip_main<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
-            cp_async_wait_all();                       // this thread's PCM of tile k+1 (and its phasor of tile k+2) landed
-            if (k + 1 < ntiles) {
-                const uint4 n0 = *reinterpret_cast<const uint4*>(stage);
-                const uint4 n1 = *reinterpret_cast<const uint4*>(stage + 8);
-                mix_regs(nx, n0, n1, &sm.ph[(k + 1) % 3][strip]);   // phasors of k+1 became visible at the last barrier
-            }
-            fir_strip_tail<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
-            const int t = k % tiles_per_frame;
-            // sm.out still holds the previous frame until the timing warps have decimated it
-            if (t == 0 && k > 0) bar_sync(BAR_FREE, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+            fir_strip<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
+            // sm.out is a single tile: wait until the timing warps have taken the previous one
+            if (k > 0) bar_sync(BAR_EMPTY, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
             // raw sums go to shared memory; the output gain (a double multiply behind two conversions on the
             // narrow XU pipe) is applied by the timing warps, off the filter's critical path
-            u64* orow = &sm.out[lane][t * QPSK_CHUNK + strip];
+            u64* orow = &sm.out[lane][strip];
 #pragma unroll
             for (int r = 0; r < R; r++) orow[r] = acc[r];
-            bar_arrive(BAR_FULL0 + t, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+            bar_arrive(BAR_FULL, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+            cp_async_wait_all();                       // next tile's PCM and phasors have landed
             bar_sync(BAR_FIR_DONE, QPSK_FIR_THREADS);
         }
     } else if (w < 10) {
@@ -310,6 +297,10 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
         // warp 8 = I, warp 9 = Q, lane = channel: amplitude histograms of qpsk.c:131-167, one tile behind the filter
         const int comp = w - 8;
         const int nsym = N / SPS;
+        // this CTA's frame scratch: [sample][component][lane] floats, 128-byte rows per (sample, component)
+        float* scr = a.scratch + (size_t)blockIdx.x * (512 * 2 * QPSK_GROUP);
+        float* scr_w = scr + comp * QPSK_GROUP + lane;
+        const int ntiles = nframes * tiles_per_frame;
         for (int fr = 0; fr < nframes; fr++) {
             const int f = f0 + fr;
             float av = 0.0f, mx = 0.0f;
@@ -318,14 +309,15 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
             for (int kk = 0; kk < 8; kk++) th[kk] = 0.0f;
             u64 hist = 0ull;
             for (int t = 0; t < tiles_per_frame; t++) {
-                bar_sync(BAR_FULL0 + t, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
-                float* ow = reinterpret_cast<float*>(&sm.out[lane][0]) + comp;
+                bar_sync(BAR_FULL, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+                const float* ow = reinterpret_cast<const float*>(&sm.out[lane][0]) + comp;
 #pragma unroll 2
-                for (int s = t * TILE_SYMS; s < (t + 1) * TILE_SYMS; s++) {
+                for (int s = 0; s < TILE_SYMS; s++) {
 #pragma unroll
                     for (int j = 0; j < SPS; j++) {
-                        const float y = gain_exact(ow[2 * (s * SPS + j)]);      // rrc_fir.c:28, this warp's component
-                        ow[2 * (s * SPS + j)] = y;                                 // the decimation reads it back
+                        const int ti = s * SPS + j;
+                        const float y = gain_exact(ow[2 * ti]);                  // rrc_fir.c:28, this warp's component
+                        scr_w[(size_t)(t * QPSK_CHUNK + ti) * (2 * QPSK_GROUP)] = y;   // kept for the decimation
                         av = __fadd_rn(av, fabsf(y));
                     }
                     av = __fmul_rn(av, 1.0f / SPS);              // av /= CYCLES, exact for a power of two
@@ -340,8 +332,10 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
                     for (int kk = 7; kk >= 1; kk--) bin = (av <= th[kk]) ? kk : bin;
                     hist += 1ull << (8 * bin);                     // byte 0 collects "no bin"; counts <= 128 fit a byte
                 }
+                if (fr * tiles_per_frame + t + 1 < ntiles) bar_arrive(BAR_EMPTY, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
             }
             sm.hist[comp][lane] = hist;
+            __threadfence();                                       // both components of the frame are in the scratch
             bar_sync(BAR_AUX, QPSK_AUX_THREADS);
             int index = 0;
             {                                                      // qpsk.c:173-180 first strict maximum
@@ -354,24 +348,24 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 1) rx_front_kernel(const R
                 }
             }
             if (comp == 0 && live) a.index_t[(size_t)f * a.Cpad + ch] = index;
+            const float* scr_r = scr + lane;
             if (a.fir_dbg != nullptr && live) {                    // parity tap: the whole filtered frame
-                u64* dst = reinterpret_cast<u64*>(a.fir_dbg) + (size_t)ch * ((size_t)a.F * N) + (size_t)f * N;
-                for (int i = comp; i < N; i += 2) dst[i] = sm.out[lane][i];
+                float2* dst = a.fir_dbg + (size_t)ch * ((size_t)a.F * N) + (size_t)f * N;
+                for (int i = comp; i < N; i += 2)
+                    dst[i] = make_float2(__ldcg(scr_r + (size_t)i * (2 * QPSK_GROUP)), __ldcg(scr_r + (size_t)i * (2 * QPSK_GROUP) + QPSK_GROUP));
             }
             // decimate, qpsk.c:186-191: symbol i = sample i*SPS + index, stored channel-fastest
             {
                 const int slot = (a.slot_base + 1 + f) % a.nslots;
-                u64* dst = reinterpret_cast<u64*>(a.dec_ring) + (size_t)slot * nsym * a.Cpad + ch;
+                float2* dst = a.dec_ring + (size_t)slot * nsym * a.Cpad + ch;
                 for (int i = comp; i < NSYM; i += 2) {
-                    const int j = i * SPS + index;
-                    u64 v;
-                    if (j < N) v = sm.out[lane][j];
-                    else if (a.ub_mode == QPSK_UB_CLAMP) v = sm.out[lane][N - 1];
-                    else v = 0ull;   // aliasing read of decimated_frame[j-N]: patched by the Costas stage
+                    int j = i * SPS + index;
+                    float2 v = make_float2(0.0f, 0.0f);            // aliasing read of decimated_frame[j-N]: patched by the Costas stage
+                    if (j >= N && a.ub_mode == QPSK_UB_CLAMP) j = N - 1;
+                    if (j < N) v = make_float2(__ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP)), __ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP) + QPSK_GROUP));
                     if (live) dst[(size_t)i * a.Cpad] = v;
                 }
             }
-            if (fr + 1 < nframes) bar_arrive(BAR_FREE, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
             if (a.fuse_costas) {
                 __threadfence();                                   // ring + index writes before the flag
                 bar_sync(BAR_AUX, QPSK_AUX_THREADS);
