@@ -63,9 +63,12 @@ struct qpsk_b200_rx {
     long long launches;
     // device state
     int16_t* d_pcm_tail;    // [Cpad][128]
-    float2* d_phasor;       // [128 + maxF*N]
-    float2* d_ph_tail;      // [128]
-    float2* d_ph_state;     // [1]
+    float2* d_phasor2[2];   // two tables [128 + maxF*N] (current call / next call, evaluated ahead on s_k0)
+    float2* d_ph_state2;    // [2] mixer phasor after the frames of each table
+    int ph_cur, ph_cur_frames;          // slot and frame count of the table the last call used
+    bool ph_spec_valid; int ph_spec_frames;   // a table for a next call of ph_spec_frames frames is in flight in the other slot
+    cudaStream_t s_k0;
+    cudaEvent_t ev_k0_done, ev_call_start;
     float2* d_dec_ring;     // [nslots][nsym][Cpad]
     int* d_index_t;         // [maxF][Cpad]
     float2* d_loop_state;   // [Cpad]
@@ -112,7 +115,7 @@ __global__ void save_pcm_tail_kernel(const int16_t* __restrict__ pcm, int16_t* _
 static int rx_free(qpsk_b200_rx* rx) {
     if (!rx) return 0;
     cudaSetDevice(rx->cfg.device);
-    void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->d_dec_ring, rx->d_index_t,
+    void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor2[0], rx->d_phasor2[1], rx->d_ph_state2, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
                      rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters,
                      rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch };
@@ -123,6 +126,9 @@ static int rx_free(qpsk_b200_rx* rx) {
         if (rx->ev_cmp[b]) cudaEventDestroy(rx->ev_cmp[b]);
         if (rx->ev_out[b]) cudaEventDestroy(rx->ev_out[b]);
     }
+    if (rx->ev_k0_done) cudaEventDestroy(rx->ev_k0_done);
+    if (rx->ev_call_start) cudaEventDestroy(rx->ev_call_start);
+    if (rx->s_k0) cudaStreamDestroy(rx->s_k0);
     if (rx->s_in) cudaStreamDestroy(rx->s_in);
     if (rx->s_out) cudaStreamDestroy(rx->s_out);
     if (rx->stream) cudaStreamDestroy(rx->stream);
@@ -188,9 +194,12 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (cudaStreamCreateWithFlags(&rx->stream, cudaStreamNonBlocking) != cudaSuccess) e = cudaGetLastError();
     for (auto& ev : rx->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     alloc((void**)&rx->d_pcm_tail, Cp * QPSK_CHUNK * sizeof(int16_t));
-    alloc((void**)&rx->d_phasor, (QPSK_CHUNK + F * N) * sizeof(float2));
-    alloc((void**)&rx->d_ph_tail, QPSK_CHUNK * sizeof(float2));
-    alloc((void**)&rx->d_ph_state, sizeof(float2));
+    alloc((void**)&rx->d_phasor2[0], (QPSK_CHUNK + F * N) * sizeof(float2));
+    alloc((void**)&rx->d_phasor2[1], (QPSK_CHUNK + F * N) * sizeof(float2));
+    alloc((void**)&rx->d_ph_state2, 2 * sizeof(float2));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&rx->s_k0, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_k0_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_call_start, cudaEventDisableTiming);
     alloc((void**)&rx->d_dec_ring, (F + 1) * S * Cp * sizeof(float2));
     alloc((void**)&rx->d_index_t, F * Cp * sizeof(int));
     alloc((void**)&rx->d_loop_state, Cp * sizeof(float2));
@@ -220,14 +229,17 @@ extern "C" int qpsk_b200_rx_reset(qpsk_b200_rx* rx) {
     cudaStream_t s = rx->stream;
     CU(cudaMemsetAsync(rx->d_pcm_tail, 0, Cp * QPSK_CHUNK * sizeof(int16_t), s));
     CU(cudaMemsetAsync(rx->d_dec_ring, 0, (size_t)rx->nslots * S * Cp * sizeof(float2), s));
-    // the carried phasors only ever multiply zero PCM at stream start; keep them finite
+    // slot 0 plays "the table of a previous call with zero frames": its first 128 entries are the phasors of the
+    // samples before the stream start (they only ever multiply zero PCM; keep them finite) and its state is cmplx(0)
+    CU(cudaStreamSynchronize(rx->s_k0));
     float2 ones[QPSK_CHUNK];
     for (auto& v : ones) v = make_float2(1.0f, 0.0f);
-    CU(cudaMemcpyAsync(rx->d_ph_tail, ones, sizeof ones, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(rx->d_phasor2[0], ones, sizeof ones, cudaMemcpyHostToDevice, s));
     float c0[2];
     qpsk_host_cis(0.0, 0, c0);                                                             // qpsk.c:341
     const float2 ph0 = make_float2(c0[0], c0[1]);
-    CU(cudaMemcpyAsync(rx->d_ph_state, &ph0, sizeof ph0, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(rx->d_ph_state2, &ph0, sizeof ph0, cudaMemcpyHostToDevice, s));
+    rx->ph_cur = 0; rx->ph_cur_frames = 0; rx->ph_spec_valid = false;
     // d_phase = d_freq = 0 (costas_loop.c:32-33)
     CU(cudaMemsetAsync(rx->d_loop_state, 0, Cp * sizeof(float2), s));
     if (rx->d_counters) CU(cudaMemsetAsync(rx->d_counters, 0, 2 * sizeof(unsigned long long), s));
@@ -282,9 +294,27 @@ static int rx_begin_call(qpsk_b200_rx* rx, int F, cudaStream_t s) {
         if (rc) return rc;
         g_taps_owner = rx->id;
     }
-    // K0: mixer phasors of this call
-    phasor_table_kernel<<<1, QPSK_CHUNK, 0, s>>>(rx->d_phasor, rx->d_ph_tail, rx->d_ph_state, rx->rect, F, rx->N);
+    // K0: mixer phasors of this call.  If the previous call already evaluated a table for this frame count on the
+    // side stream, just wait for it; otherwise evaluate it now.
+    const int nxt = rx->ph_cur ^ 1;
+    if (rx->ph_spec_valid && rx->ph_spec_frames == F) {
+        CU(cudaStreamWaitEvent(s, rx->ev_k0_done, 0));
+    } else {
+        if (rx->ph_spec_valid) CU(cudaStreamSynchronize(rx->s_k0));       // a table nobody wants is being written into `nxt`
+        phasor_table_kernel<<<1, QPSK_CHUNK, 0, s>>>(rx->d_phasor2[rx->ph_cur], rx->ph_cur_frames, rx->d_ph_state2 + rx->ph_cur,
+                                                     rx->d_phasor2[nxt], rx->d_ph_state2 + nxt, rx->rect, F, rx->N);
+        CU(cudaGetLastError());
+    }
+    rx->ph_cur = nxt; rx->ph_cur_frames = F; rx->ph_spec_valid = false;
+    // the table of a next call with the same frame count, evaluated on the side stream while this call runs; it
+    // overwrites the other slot, which the previous call's kernels (all enqueued before this point on `s`) still read
+    CU(cudaEventRecord(rx->ev_call_start, s));
+    CU(cudaStreamWaitEvent(rx->s_k0, rx->ev_call_start, 0));
+    phasor_table_kernel<<<1, QPSK_CHUNK, 0, rx->s_k0>>>(rx->d_phasor2[rx->ph_cur], F, rx->d_ph_state2 + rx->ph_cur,
+                                                        rx->d_phasor2[rx->ph_cur ^ 1], rx->d_ph_state2 + (rx->ph_cur ^ 1), rx->rect, F, rx->N);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(rx->ev_k0_done, rx->s_k0));
+    rx->ph_spec_valid = true; rx->ph_spec_frames = F;
     rx->launches += 1;
     return 0;
 }
@@ -293,7 +323,7 @@ static int rx_begin_call(qpsk_b200_rx* rx, int F, cudaStream_t s) {
 static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, int F, cudaStream_t s, bool timed) {
     const int N = rx->N;
     RxFrontArgs fa;
-    fa.pcm = d_pcm; fa.pcm_tail = rx->d_pcm_tail; fa.phasor = rx->d_phasor;
+    fa.pcm = d_pcm; fa.pcm_tail = rx->d_pcm_tail; fa.phasor = rx->d_phasor2[rx->ph_cur];
     fa.dec_ring = rx->d_dec_ring; fa.index_t = rx->d_index_t; fa.fir_dbg = rx->d_fir_dbg;
     fa.C = rx->C; fa.Cpad = rx->Cpad; fa.F = F; fa.N = N; fa.chan_base = c0; fa.chan_count = nc;
     fa.slot_base = rx->slot_base; fa.nslots = rx->nslots; fa.ub_mode = rx->cfg.ub_mode;

@@ -24,15 +24,16 @@ __constant__ float2 c_taps2[QPSK_MAX_TAPS];
 // (phase *= rect per sample, renormalised once per frame), identical for every channel of a
 // profile, so one thread evaluates it once per launch and all channels share the table.
 //   table[QPSK_CHUNK + j] = fbb_rx_phase used for sample j of this launch (j = 0 .. F*N-1)
-//   table[0 .. QPSK_CHUNK-1] = the entries of the 128 samples before it (carried in `tail`)
+//   table[0 .. QPSK_CHUNK-1] = the entries of the 128 samples before it (the end of the previous call's table)
+// Two tables alternate, so the table of the next call can be evaluated on a side stream while this call runs.
 // --------------------------------------------------------------------------------------------
-__global__ void phasor_table_kernel(float2* __restrict__ table, float2* __restrict__ tail,
-                                    float2* __restrict__ phase_state, float2 rect, int nframes, int frame_size) {
+__global__ void phasor_table_kernel(const float2* __restrict__ prev_table, int prev_frames, const float2* __restrict__ state_in,
+                                    float2* __restrict__ table, float2* __restrict__ state_out, float2 rect, int nframes, int frame_size) {
     const int t = threadIdx.x;
-    if (t < QPSK_CHUNK) table[t] = tail[t];
-    __syncthreads();
+    // the 128 entries before sample 0 are the last 128 entries of the previous call's table
+    if (t < QPSK_CHUNK) table[t] = prev_table[(size_t)prev_frames * frame_size + t];
     if (t == 0) {
-        float2 ph = *phase_state;
+        float2 ph = *state_in;
         float2* out = table + QPSK_CHUNK;
         for (int f = 0; f < nframes; f++) {
             float2* row = out + (size_t)f * frame_size;
@@ -47,10 +48,8 @@ __global__ void phasor_table_kernel(float2* __restrict__ table, float2* __restri
             ph.x = __fdiv_rn(ph.x, mag);
             ph.y = __fdiv_rn(ph.y, mag);
         }
-        *phase_state = ph;
+        *state_out = ph;
     }
-    __syncthreads();
-    if (t < QPSK_CHUNK) tail[t] = table[(size_t)nframes * frame_size + t];
 }
 
 // --------------------------------------------------------------------------------------------
