@@ -9,4 +9,5 @@ from .receiver import Receiver, unpack_dibits  # noqa: F401
 from .fir import Fir, rrc_make  # noqa: F401
 from .fft import Fft  # noqa: F401
 from . import bits, shard  # noqa: F401
+from .stream import receive_files  # noqa: F401
 from .transmitter import Transmitter, bits_to_symbols  # noqa: F401
