@@ -92,3 +92,26 @@ def test_config4_size_tone_bins():
     assert torch.equal(out_bin.long(), bins)
     assert torch.allclose(out_mag, torch.ones_like(out_mag), atol=1e-4)          # unit tone, forward scaled by 1/n
     f.close()
+
+
+def test_config1_shape_all_channels_bit_exact(oracle_lib):
+    """BASELINE config 1: 1,024 independent 1200-baud channels (10 m profile), AWGN + per-channel carrier offset.
+    No undefined behaviour at 1200 baud, so every channel must agree with the oracle bit for bit (32 frames here;
+    the frame-split grid and the stand-alone Costas kernel are the code path this size takes)."""
+    import qpsk_b200
+    from qpsk_b200 import capi
+    from synth import make_pcm
+    o = oracle_lib.Oracle(rs=1200.0)
+    base, _ = make_pcm(128, 32, rs=1200.0, seed=1200, esn0_db=10.0, oracle=o)
+    rng = np.random.default_rng(3)
+    # 1,024 distinct channels: each base channel with eight different additive noise realisations
+    pcm = np.repeat(base, 8, axis=0).astype(np.int32) + rng.integers(-300, 301, (1024, base.shape[1]))
+    pcm = np.clip(pcm, -32768, 32767).astype(np.int16)
+    want = o.rx_run(pcm, want=("index", "dibit", "phase", "freq"))
+    rx = qpsk_b200.Receiver(1024, 32, rs=1200.0)
+    got = qpsk_b200.unpack_dibits(rx.rx_frames(pcm))
+    assert np.array_equal(got, want["dibit"])
+    assert np.array_equal(rx.read(capi.OUT_INDEX), want["index"])
+    track = rx.read(capi.OUT_TRACK)
+    assert np.array_equal(track[..., 0], want["phase"]) and np.array_equal(track[..., 1], want["freq"])
+    rx.close()
