@@ -2,7 +2,10 @@
  * qpsk_b200.h -- batch C-ABI of the B200-native QPSK receiver (libqpsk_b200.so).
  *
  * Plain C: opaque handles, plain pointers and sizes, int status returns (0 = success, negative
- * = error, text from qpsk_b200_last_error()).  No CPU fallback exists: every entry point that
+ * = error, text from qpsk_b200_last_error()).  A context is not thread-safe and its calls must be
+ * stream-ordered; the filter taps live in one process-wide constant bank, so contexts with
+ * different taps must not run concurrently from different host threads (one process per GPU is
+ * the intended deployment).  No CPU fallback exists: every entry point that
  * computes fails with QPSK_B200_ERR_CUDA when no sm_100 device is usable.
  *
  * The reference (MonsieurETM/QPSK) handles exactly one channel through file-scope singletons;

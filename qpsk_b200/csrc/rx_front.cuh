@@ -4,10 +4,11 @@
 // Replaces, per channel, the first four stages of rx_frame (reference qpsk.c:114-191) and the
 // inner loop of rrc_fir (rrc_fir.c:17-30).  Bit-exact in QPSK_MODE_EXACT.
 //
-// Work decomposition: one CTA = 32 channels (one per lane) x a block of consecutive frames;
-// 8 warps split each 128-sample time tile into 16-sample strips, so a thread owns 16 consecutive
-// outputs of one channel and slides over the 126-sample halo kept in shared memory.  Taps are
-// uniform across the warp and come from the constant bank as (c,c) pairs for FMUL2/FFMA2.
+// Work decomposition: one CTA = 32 channels (one per lane) x a block of consecutive frames, two CTAs
+// per SM.  8 filter warps split each 128-sample time tile into 16-sample strips, so a thread owns 16
+// consecutive outputs of one channel and slides over the 126-sample halo kept in shared memory; two
+// timing warps and one Costas warp follow behind (see rx_front_kernel).  Taps are uniform across the
+// warp and come from the constant bank as (c,c) pairs for FMUL2/FFMA2.
 #pragma once
 
 #include "common.cuh"
@@ -72,7 +73,7 @@ __device__ __forceinline__ void fir_tap(u64& acc, const u64 xv, const int i) {
 // code at R = 16) stays resident in the instruction cache -- the fully unrolled 70 KB version spent
 // 9 % of its issue slots waiting for instruction fetch (profiles/r01_rx_front_v2).
 template <int NTAPS, int R, int MODE>
-__device__ __forceinline__ void fir_strip_main(const u64* __restrict__ x, u64 (&acc)[R]) {
+__device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[R]) {
     constexpr int STEADY = NTAPS - R + 1;            // d = R-1 .. NTAPS-1
     constexpr int TRIPS = STEADY / R, REM = STEADY % R;
 #pragma unroll
@@ -99,22 +100,12 @@ __device__ __forceinline__ void fir_strip_main(const u64* __restrict__ x, u64 (&
 #pragma unroll
         for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, d - r);
     }
-}
-
-template <int NTAPS, int R, int MODE>
-__device__ __forceinline__ void fir_strip_tail(const u64* __restrict__ x, u64 (&acc)[R]) {
 #pragma unroll
     for (int d = NTAPS; d < NTAPS - 1 + R; d++) {    // tail
         const u64 xv = x[d];
 #pragma unroll
         for (int r = d - (NTAPS - 1); r < R; r++) fir_tap<MODE>(acc[r], xv, d - r);
     }
-}
-
-template <int NTAPS, int R, int MODE>
-__device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[R]) {
-    fir_strip_main<NTAPS, R, MODE>(x, acc);
-    fir_strip_tail<NTAPS, R, MODE>(x, acc);
 }
 
 struct RxFrontArgs {
@@ -159,18 +150,6 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// mix 16 PCM samples with their phasors into registers: qpsk.c:117
-__device__ __forceinline__ void mix_regs(u64 (&nx)[16], const uint4& p0, const uint4& p1, const float2* __restrict__ ph) {
-    const unsigned w[8] = { p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w };
-#pragma unroll
-    for (int e = 0; e < 16; e++) {
-        const int v = (int)(short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
-        const float s = __fmul_rn((float)v, 6.103515625e-05f);   // (float)in / 16384.0f, exact
-        const float2 p = ph[e];
-        nx[e] = pack2(__fmul_rn(p.x, s), __fmul_rn(p.y, s));
-    }
-}
-
 // mix 16 PCM samples with their phasors and store them as the current tile: qpsk.c:117
 __device__ __forceinline__ void mix_store(u64* __restrict__ xrow_cur, const uint4& p0, const uint4& p1,
                                           const float2* __restrict__ ph) {
@@ -197,10 +176,12 @@ enum { BAR_ROWS = 1,      // FIR warps: sample rows of the tile are in shared me
 #define QPSK_AUX_THREADS 64
 #define QPSK_FRONT_THREADS 352   // 8 FIR warps + 2 timing/decimation warps + 1 Costas warp
 
-// Warp-specialised front end.  Warps 0-7 mix and filter (the FP32-pipe-bound part); warps 8-9
-// follow one tile behind with the amplitude histograms, the index and the decimation; warp 10 runs
-// the Costas loop of the previous frame when the CTA owns whole streams.  The auxiliary warps live
-// in the issue slots the packed-FP32 filter leaves free, so the filter never waits for them.
+// Warp-specialised front end, two CTAs per SM.  Warps 0-7 mix and filter (the FP32-pipe-bound part) and hand
+// each tile's raw sums to warps 8-9 through a single-tile shared-memory buffer (named barriers BAR_FULL /
+// BAR_EMPTY); warps 8-9 apply the output gain, keep the filtered frame in the CTA's L2-resident scratch, run
+// the amplitude histograms, and at the end of a frame compute the index and decimate; warp 10 runs the Costas
+// loop of the previous frame when the CTA owns whole streams.  The second CTA on the SM fills the pipe slots
+// this one leaves at its barriers and fill phases.
 template <int NTAPS, int SPS, int MODE>
 __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const RxFrontArgs a) {
     static_assert(NTAPS - 1 <= QPSK_CHUNK - 2, "halo must fit in one previous tile");
