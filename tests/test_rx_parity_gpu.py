@@ -226,3 +226,29 @@ def test_device_nco_equals_host_libm_on_a_dense_sweep():
     hc = np.array([libm.cosf(float(v)) for v in x[idx]], np.float32)
     assert np.array_equal(s[idx].view(np.uint32), hs.view(np.uint32))
     assert np.array_equal(c[idx].view(np.uint32), hc.view(np.uint32))
+
+
+def test_long_stream_many_calls_random_frame_counts(oracle_lib):
+    """The reference's own experiment length (2,000 frames) fed in ~90 calls of random size 1..64 frames: ring
+    slot rotation, carried filter history / phasor / loop state and the look-ahead phasor table (which is only
+    reusable when the next call has the same frame count) must never drift from a single pass of the oracle."""
+    import qpsk_b200
+    from qpsk_b200 import capi
+    o = oracle_lib.Oracle()
+    nframes = 2000
+    pcm, _ = make_pcm(6, nframes, seed=2000, esn0_db=14.0, oracle=o)
+    want = o.rx_run(pcm, want=("dibit", "phase", "freq", "index"))
+    rng = np.random.default_rng(8)
+    rx = qpsk_b200.Receiver(6, 64)
+    f, parts, tracks, idxs = 0, [], [], []
+    while f < nframes:
+        nf = int(min(nframes - f, rng.choice([1, 2, 7, 64, 64, 64, 33])))
+        parts.append(qpsk_b200.unpack_dibits(rx.rx_frames(pcm[:, f * 512:(f + nf) * 512])))
+        tracks.append(rx.read(capi.OUT_TRACK))
+        idxs.append(rx.read(capi.OUT_INDEX))
+        f += nf
+    assert np.array_equal(np.concatenate(parts, axis=1), want["dibit"])
+    track = np.concatenate(tracks, axis=1)
+    assert np.array_equal(track[..., 0], want["phase"]) and np.array_equal(track[..., 1], want["freq"])
+    assert np.array_equal(np.concatenate(idxs, axis=1), want["index"])
+    rx.close()
