@@ -208,6 +208,12 @@ int qpsk_b200_tx_end_packet(qpsk_b200_tx *tx);
 /* tx_frame(samples, symbol, length) itself: arbitrary complex symbols, float [C][nsym][2] in host memory */
 int qpsk_b200_tx_symbols_host(qpsk_b200_tx *tx, const float *h_symbols, int nsym, int16_t *h_pcm);
 
+/* Extension, not part of the reference's pipeline (the reference has no frequency estimator): the
+ * carrier offset of every channel from the first 2^log2n decimated symbols of the most recent process call --
+ * 4th power (strips the QPSK modulation), batched FFT, |X|^2 argmax.  Resolution rs / (4 * 2^log2n) Hz, range
+ * +-rs/8.  h_bin (may be NULL) receives the raw argmax bins. */
+int qpsk_b200_rx_estimate_offset(qpsk_b200_rx *rx, int log2n, float *h_offset_hz, int32_t *h_bin);
+
 /* test hook: the device NCO (the restated glibc sinf/cosf the Costas kernel uses) evaluated over n host floats */
 int qpsk_b200_debug_nco(const float *h_in, float *h_sin, float *h_cos, int n, int device);
 

@@ -52,6 +52,7 @@ def lib():
     L.qpsk_b200_rx_launch_count.argtypes = [C.c_void_p]
     L.qpsk_b200_rx_launch_count.restype = C.c_longlong
     L.qpsk_b200_rx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.qpsk_b200_rx_estimate_offset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     _bind_fir(L)
     _bind_fft(L)
     _bind_bits(L)

@@ -43,6 +43,8 @@ extern "C" int qpsk_b200_device_count(void) {
     return n;
 }
 
+struct qpsk_b200_fft;
+
 static const double kTau = 2.0 * 3.14159265358979323846;
 
 // constant-bank taps belong to the context that uploaded them last; ids are never reused
@@ -86,6 +88,7 @@ struct qpsk_b200_rx {
     cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
     float* d_front_scratch; // front-end per-CTA frame scratch (lazy, grow-only)
     size_t front_scratch_bytes;
+    qpsk_b200_fft* est_fft; int est_fft_n;   // estimator extension (lazy)
     void* d_scratch;        // transposed download staging (lazy)
     size_t scratch_bytes;
 };
@@ -112,9 +115,12 @@ __global__ void save_pcm_tail_kernel(const int16_t* __restrict__ pcm, int16_t* _
     reinterpret_cast<uint4*>(tail + (size_t)c * QPSK_CHUNK)[q] = *src;
 }
 
+extern "C" int qpsk_b200_fft_destroy(qpsk_b200_fft* f);
+
 static int rx_free(qpsk_b200_rx* rx) {
     if (!rx) return 0;
     cudaSetDevice(rx->cfg.device);
+    if (rx->est_fft) qpsk_b200_fft_destroy(rx->est_fft);
     void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor2[0], rx->d_phasor2[1], rx->d_ph_state2, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
                      rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters,
@@ -1284,5 +1290,72 @@ extern "C" int qpsk_b200_debug_nco(const float* h_in, float* h_sin, float* h_cos
     CU(cudaGetLastError());
     CU(cudaMemcpy(h_sin, b.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(h_cos, c.p, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return QPSK_B200_OK;
+}
+
+// =============================================================================================
+// Extension (never part of the parity path): carrier-offset estimate of every channel
+// from the 4th power of its decimated symbols, through the batched FFT + argmax kernel.  QPSK on the axes
+// raised to the 4th power is a pure tone at 4 x offset.
+// =============================================================================================
+__global__ void symbol_power4_kernel(const float2* __restrict__ ring, float2* __restrict__ bursts, int C, int Cpad, int nsym,
+                                     int nslots, int first_slot, int n /* burst length */) {
+    // bursts[c][k] = ring[frame k / nsym][k % nsym][c] ^ 4 ; 32 x 32 tile transpose (channel-fastest -> channel-major)
+    __shared__ float2 tile[32][33];
+    const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int k = k0 + j, c = c0 + threadIdx.x;
+        if (k < n && c < C) {
+            const int slot = (first_slot + k / nsym) % nslots;
+            const float2 z = ring[((size_t)slot * nsym + (k % nsym)) * Cpad + c];
+            const float2 z2 = make_float2(z.x * z.x - z.y * z.y, 2.0f * z.x * z.y);
+            tile[j][threadIdx.x] = make_float2(z2.x * z2.x - z2.y * z2.y, 2.0f * z2.x * z2.y);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, k = k0 + threadIdx.x;
+        if (k < n && c < C) bursts[(size_t)c * n + k] = tile[threadIdx.x][j];
+    }
+}
+
+extern "C" int qpsk_b200_rx_estimate_offset(qpsk_b200_rx* rx, int log2n, float* h_offset_hz, int32_t* h_bin) {
+    if (!rx || !h_offset_hz) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (rx->lastF == 0) return fail(QPSK_B200_ERR_STATE, "no process call yet");
+    const int n = 1 << log2n;
+    if (log2n < 5 || log2n > 13 || n > rx->lastF * rx->nsym)
+        return fail(QPSK_B200_ERR_ARG, "burst length 2^%d must be 32..8192 and at most the %d symbols of the last call", log2n, rx->lastF * rx->nsym);
+    CU(cudaSetDevice(rx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    if (!rx->est_fft || rx->est_fft_n != n) {
+        if (rx->est_fft) { qpsk_b200_fft_destroy(rx->est_fft); rx->est_fft = nullptr; }
+        int rc = qpsk_b200_fft_create(n, rx->cfg.device, &rx->est_fft);
+        if (rc) return rc;
+        rx->est_fft_n = n;
+    }
+    DevBuf bursts, bins, mags;
+    CU(cudaMalloc(&bursts.p, (size_t)rx->C * n * sizeof(float2)));
+    CU(cudaMalloc(&bins.p, (size_t)rx->C * sizeof(int)));
+    CU(cudaMalloc(&mags.p, (size_t)rx->C * sizeof(float)));
+    // the frames of the last call sit in ring slots (slot_base_before + 1 + f); use its first n symbols
+    const int base_before = ((rx->slot_base - rx->lastF) % rx->nslots + rx->nslots) % rx->nslots;
+    dim3 grid((rx->C + 31) / 32, (n + 31) / 32), block(32, 8);
+    symbol_power4_kernel<<<grid, block, 0, rx->stream>>>(rx->d_dec_ring, (float2*)bursts.p, rx->C, rx->Cpad, rx->nsym, rx->nslots,
+                                                        (base_before + 1) % rx->nslots, n);
+    CU(cudaGetLastError());
+    int rc = qpsk_b200_fft_argmax_device(rx->est_fft, (const float*)bursts.p, rx->C, (int32_t*)bins.p, (float*)mags.p, rx->stream);
+    if (rc) return rc;
+    int32_t* hb = new (std::nothrow) int32_t[rx->C];
+    if (!hb) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+    cudaError_t e = cudaMemcpyAsync(hb, bins.p, (size_t)rx->C * sizeof(int), cudaMemcpyDeviceToHost, rx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(rx->stream);
+    if (e != cudaSuccess) { delete[] hb; return fail(QPSK_B200_ERR_CUDA, "estimate download failed: %s", cudaGetErrorString(e)); }
+    for (int c = 0; c < rx->C; c++) {
+        const int k = hb[c] < n / 2 ? hb[c] : hb[c] - n;              // signed bin of the 4x tone
+        h_offset_hz[c] = (float)((double)k * (double)rx->cfg.rs / (4.0 * (double)n));
+        if (h_bin) h_bin[c] = hb[c];
+    }
+    delete[] hb;
+    rx->launches += 2;
     return QPSK_B200_OK;
 }

@@ -99,6 +99,14 @@ class Receiver:
         capi.check(self.L.qpsk_b200_rx_crc_counters(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def estimate_offset(self, log2n):
+        """Extension: per-channel carrier offset (Hz) from the 4th-power spectrum of the first 2^log2n decimated
+        symbols of the last call (batched FFT + argmax kernel).  Returns (offset_hz float32 [C], bin int32 [C])."""
+        hz = np.empty(self.nchan, np.float32)
+        bins = np.empty(self.nchan, np.int32)
+        capi.check(self.L.qpsk_b200_rx_estimate_offset(self.h, log2n, hz.ctypes.data_as(C.c_void_p), bins.ctypes.data_as(C.c_void_p)))
+        return hz, bins
+
     def kernel_ms(self):
         a, b = C.c_float(), C.c_float()
         capi.check(self.L.qpsk_b200_rx_last_kernel_ms(self.h, C.byref(a), C.byref(b)))
