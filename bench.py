@@ -234,6 +234,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     W = max(3, args.warmup)
+    # host side of the end-to-end leg: keep this rank's pinned buffers on the GPU's own NUMA node
+    numa_cores = qpsk_b200.shard.bind_host_to_gpu(local) if world > 1 else None
 
     mode = capi.MODE_EXACT if args.mode == "exact" else capi.MODE_FAST
     nsamp = NFRAMES * FRAME
@@ -344,6 +346,8 @@ def main():
                       "note": "random payload: CRC passes are chance (2^-16); counters show K4 ran over every frame"},
         }
         if e2e is not None:
+            if numa_cores is not None:
+                e2e["host_cores_rank0"] = "%d cores local to GPU %d (NVML affinity)" % (len(numa_cores), local)
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (rank 0), per the measurement contract
             try:

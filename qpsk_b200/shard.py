@@ -29,3 +29,25 @@ def max_over_ranks(value, device=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def bind_host_to_gpu(local_index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `local_index` (its NUMA node), so that
+    pinned host buffers allocated afterwards sit behind the same PCIe root as the GPU that reads them.  With
+    one process per GPU and 55 GB/s of host reads per process this decides whether N GPUs share one socket's
+    memory controllers.  Returns the core list, or None when NVML or the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
