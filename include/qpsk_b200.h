@@ -53,8 +53,10 @@ enum {                              /* cfg.flags */
     QPSK_B200_KEEP_FIR = 1,         /* keep the matched-filter output (16 B/sample!) for parity checks */
     QPSK_B200_KEEP_SYMBOLS = 2,     /* keep the derotated symbols (costas_frame) */
     QPSK_B200_DECODE_FRAMES = 4,    /* run descramble -> de-interleave -> CRC16 on every frame's dibits */
-    QPSK_B200_NO_FUSE = 8           /* always run the Costas loop as its own kernel (it is fused into the front end
+    QPSK_B200_NO_FUSE = 8,          /* always run the Costas loop as its own kernel (it is fused into the front end
                                        whenever a CTA owns whole streams, i.e. when channels are plentiful) */
+    QPSK_B200_RESOLVE_ROTATION = 16 /* with DECODE_FRAMES: a frame whose CRC fails is retried with its dibits turned back
+                                       by 90, 180 and 270 degrees (the loop's phase ambiguity); first match wins */
 };
 
 typedef struct {
@@ -83,7 +85,9 @@ enum {
     QPSK_B200_OUT_FIR = 5,      /* float2 [C][F*N]       matched-filter output (needs KEEP_FIR) */
     QPSK_B200_OUT_TAPS = 6,     /* float  [ntaps] */
     QPSK_B200_OUT_FRAMES = 7,   /* uint8  [C][F*nbytes]  de-scrambled, de-interleaved frames: payload | crc16 hi | lo (needs DECODE_FRAMES) */
-    QPSK_B200_OUT_CRC_OK = 8    /* uint8  [C][F]         1 where the frame's CRC16 matched (needs DECODE_FRAMES) */
+    QPSK_B200_OUT_CRC_OK = 8,   /* uint8  [C][F]         1 where the frame's CRC16 matched (needs DECODE_FRAMES) */
+    QPSK_B200_OUT_ROTATION = 9  /* uint8  [C][F]         quarter turns undone before the CRC matched, 0..3; 255 = no match
+                                                          (needs DECODE_FRAMES | RESOLVE_ROTATION) */
 };
 
 const char *qpsk_b200_last_error(void);
@@ -183,6 +187,12 @@ int qpsk_b200_bits_scramble(uint8_t *h_dibits, int ndibits, int nframes, int dev
 int qpsk_b200_frames_encode(const uint8_t *h_payload, int nbytes, int nchan, int nframes, uint8_t *h_dibits, int device);
 /* inverse of the above on host buffers: packed dibits -> frames uint8 [C][F][nbytes] and CRC verdicts uint8 [C][F] */
 int qpsk_b200_frames_decode(const uint8_t *h_dibits, int nbytes, int nchan, int nframes, uint8_t *h_frames, uint8_t *h_crc_ok, int device);
+/* the same with the loop's 90-degree ambiguity resolved on the CRC: constellation index d <-> {1, j, -j, -1}
+ * (qpsk.c:58-63), so a stream received r quarter turns ahead carries rho^r(d), rho = 0->1->3->2->0.  Rotations
+ * 0..3 are tried in order; h_rotation uint8 [C][F] receives the first that matched or 255, in which case the
+ * frame stored is the rotation-0 decode. */
+int qpsk_b200_frames_decode_rotated(const uint8_t *h_dibits, int nbytes, int nchan, int nframes, uint8_t *h_frames,
+                                    uint8_t *h_crc_ok, uint8_t *h_rotation, int device);
 /* counters accumulated by DECODE_FRAMES since create/reset: frames examined and CRC passes */
 int qpsk_b200_rx_crc_counters(qpsk_b200_rx *rx, unsigned long long *frames, unsigned long long *passes);
 

@@ -189,6 +189,21 @@ class Oracle:
         ok = self.L.orc_frame_decode(dibits.ctypes.data_as(C.c_void_p), nbytes, frame.ctypes.data_as(C.c_void_p))
         return frame, bool(ok)
 
+    def frame_decode_rotated(self, dibits, nbytes):
+        """-> (frame, quarter turns undone 0..3 or -1 when no rotation passes the CRC)."""
+        dibits = np.ascontiguousarray(dibits, np.uint8)
+        assert len(dibits) == 4 * nbytes
+        frame = np.zeros(nbytes, np.uint8)
+        self.L.orc_frame_decode_rotated.restype = C.c_int
+        r = self.L.orc_frame_decode_rotated(dibits.ctypes.data_as(C.c_void_p), nbytes, frame.ctypes.data_as(C.c_void_p))
+        return frame, int(r)
+
+    def rotate_dibits(self, dibits, quarter_turns):
+        self.L.orc_rotate_dibit.restype = C.c_uint8
+        self.L.orc_rotate_dibit.argtypes = [C.c_uint8, C.c_int]
+        return np.array([self.L.orc_rotate_dibit(int(d), int(quarter_turns)) for d in np.asarray(dibits).ravel()],
+                        np.uint8).reshape(np.shape(dibits))
+
     def fftn(self, x, inverse=False):
         x = np.ascontiguousarray(x, np.complex128)
         out = np.zeros_like(x)

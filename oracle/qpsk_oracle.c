@@ -541,3 +541,29 @@ int orc_frame_decode(const uint8_t *dibits, int nbytes, uint8_t *frame) {
     const uint16_t crc = orc_crc16(frame, nbytes - 2);
     return frame[nbytes - 2] == (uint8_t)(crc >> 8) && frame[nbytes - 1] == (uint8_t)(crc & 0xff);
 }
+
+/* 90-degree ambiguity (PARITY UNPINNED, this project's composition).  The constellation is
+ * index d -> {1, j, -j, -1} (qpsk.c:58-63) and, at the intended phase, qpsk_demod (qpsk.c:74-79)
+ * returns dibit == index.  Turning the received symbols a quarter turn ahead maps
+ * 1 -> j -> -1 -> -j -> 1, i.e. d -> 1, 3, 0, 2 for d = 0, 1, 2, 3. */
+uint8_t orc_rotate_dibit(uint8_t d, int quarter_turns) {
+    static const uint8_t ahead[4] = { 1, 3, 0, 2 };
+    d &= 3;
+    for (int r = 0; r < (quarter_turns & 3); r++) d = ahead[d];
+    return d;
+}
+
+/* try rotations 0..3 in order: undo r quarter turns on every dibit, decode, accept the first CRC
+ * match.  No match: frame holds the rotation-0 decode and the result is -1. */
+int orc_frame_decode_rotated(const uint8_t *dibits, int nbytes, uint8_t *frame) {
+    uint8_t turned[4 * nbytes], trial[nbytes];
+    for (int r = 0; r < 4; r++) {
+        for (int k = 0; k < 4 * nbytes; k++) turned[k] = orc_rotate_dibit(dibits[k], 4 - r);
+        const int ok = orc_frame_decode(turned, nbytes, r == 0 ? frame : trial);
+        if (ok) {
+            if (r) memcpy(frame, trial, (size_t)nbytes);
+            return r;
+        }
+    }
+    return -1;
+}

@@ -125,6 +125,9 @@ uint16_t orc_crc16(const uint8_t *data, int length);
 /* ---- frame format (parity unpinned composition of the pinned bit stages; see qpsk_oracle.c) */
 void orc_frame_encode(const uint8_t *payload, int nbytes, uint8_t *dibits);
 int  orc_frame_decode(const uint8_t *dibits, int nbytes, uint8_t *frame);
+/* rotation resolved on the CRC: returns the quarter turns undone (0..3) or -1; see the .c file */
+int  orc_frame_decode_rotated(const uint8_t *dibits, int nbytes, uint8_t *frame);
+uint8_t orc_rotate_dibit(uint8_t d, int quarter_turns);
 
 /* ---- glibc 2.39 sinf/cosf (x86-64 FMA ifunc variant), restated: the device NCO follows this */
 float orc_glibc_sinf(float y);

@@ -22,8 +22,8 @@ class RxConfig(C.Structure):
 
 MODE_EXACT, MODE_FAST = 0, 1
 UB_ALIAS, UB_CLAMP = 0, 1
-KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE = 1, 2, 4, 8
-OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK = range(9)
+KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION = 1, 2, 4, 8, 16
+OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK, OUT_ROTATION = range(10)
 
 _lib = None
 
@@ -94,6 +94,7 @@ def _bind_bits(L):
     L.qpsk_b200_bits_scramble.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.qpsk_b200_frames_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     L.qpsk_b200_frames_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.qpsk_b200_frames_decode_rotated.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.qpsk_b200_rx_crc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
 
 

@@ -41,11 +41,16 @@ def frames_encode(payload, device=0):
     return out
 
 
-def frames_decode(packed, nbytes, device=0):
-    """packed dibits uint8 [C, F*nbytes] -> (frames uint8 [C, F, nbytes], crc_ok uint8 [C, F])."""
+def frames_decode(packed, nbytes, device=0, resolve_rotation=False):
+    """packed dibits uint8 [C, F*nbytes] -> (frames uint8 [C, F, nbytes], crc_ok uint8 [C, F]); with
+    resolve_rotation also the quarter turns undone per frame (uint8 [C, F], 255 = no CRC match)."""
     d = np.ascontiguousarray(packed, np.uint8)
     Cn, F = d.shape[0], d.shape[1] // nbytes
     frames = np.zeros((Cn, F, nbytes), np.uint8)
     ok = np.zeros((Cn, F), np.uint8)
+    if resolve_rotation:
+        rot = np.zeros((Cn, F), np.uint8)
+        capi.check(capi.lib().qpsk_b200_frames_decode_rotated(_p(d), nbytes, Cn, F, _p(frames), _p(ok), _p(rot), device))
+        return frames, ok, rot
     capi.check(capi.lib().qpsk_b200_frames_decode(_p(d), nbytes, Cn, F, _p(frames), _p(ok), device))
     return frames, ok

@@ -108,6 +108,7 @@ struct FrameDecodeArgs {
     const unsigned* dibits_t;   // [F][W][Cpad]
     unsigned* frames_t;         // [F][W][Cpad] payload | crc, byte k of the frame at bits 8*(k%4) of word k/4
     uint8_t* crc_ok_t;          // [F][Cpad]
+    uint8_t* rotation_t;        // [F][Cpad] or null: resolve the 90-degree ambiguity of the loop on the CRC (see below)
     unsigned long long* counters;   // [0] frames examined, [1] CRC passes
     int C, Cpad, F;
     int c0;                     // first channel of this launch; C is its end
@@ -127,6 +128,15 @@ __device__ __forceinline__ void permute_frame(const unsigned (&in)[NBYTES / 4], 
     }
 }
 
+// A Costas loop locks on any of four phases 90 degrees apart.  With the reference's mapping (constellation
+// index d <-> {1, j, -j, -1}, qpsk.c:58-63, and the slicer's dibit = b0 | b1 << 1, qpsk.c:74-79) a stream received a
+// quarter turn ahead carries rho(d) = (b0' = !b1, b1' = b0) in place of d: 0 -> 1 -> 3 -> 2 -> 0.  This undoes one
+// quarter turn on 16 packed dibits at once: b0 = b1', b1 = !b0'.
+__device__ __forceinline__ unsigned unrotate_dibits(unsigned w) {
+    const unsigned b0 = w & 0x55555555u, b1 = (w >> 1) & 0x55555555u;
+    return b1 | ((~b0 & 0x55555555u) << 1);
+}
+
 template <int NBYTES>
 __global__ void __launch_bounds__(128) frame_decode_kernel(const FrameDecodeArgs a) {
     constexpr int W = NBYTES / 4;
@@ -134,19 +144,36 @@ __global__ void __launch_bounds__(128) frame_decode_kernel(const FrameDecodeArgs
     const int f = blockIdx.y;
     unsigned ok = 0;
     if (c < a.C) {
-        unsigned in[W], out[W];
+        unsigned raw[W], in[W], out[W], first[W];
 #pragma unroll
-        for (int w = 0; w < W; w++) in[w] = a.dibits_t[((size_t)f * W + w) * a.Cpad + c] ^ c_keystream_words[w];
-        permute_frame<NBYTES, 1>(in, out);
-        uint16_t crc = 0xFFFF;
+        for (int w = 0; w < W; w++) raw[w] = a.dibits_t[((size_t)f * W + w) * a.Cpad + c];
+        // rotation 0 is the plain decode; with rotation_t the other three quarter turns are tried in order and
+        // the first whose CRC matches is kept (no match: the rotation-0 decode is stored, rotation = 255)
+        const int nrot = a.rotation_t ? 4 : 1;
+        int rot = 0;
+#pragma unroll 1
+        for (; rot < nrot; rot++) {
 #pragma unroll
-        for (int k = 0; k < NBYTES - 2; k++) crc = crc16_update(crc, (uint8_t)(out[k >> 2] >> (8 * (k & 3))));
-        const unsigned hi = (out[(NBYTES - 2) >> 2] >> (8 * ((NBYTES - 2) & 3))) & 0xffu;
-        const unsigned lo = (out[(NBYTES - 1) >> 2] >> (8 * ((NBYTES - 1) & 3))) & 0xffu;
-        ok = (hi == (unsigned)(crc >> 8) && lo == (unsigned)(crc & 0xff)) ? 1u : 0u;
+            for (int w = 0; w < W; w++) in[w] = raw[w] ^ c_keystream_words[w];
+            permute_frame<NBYTES, 1>(in, out);
+            uint16_t crc = 0xFFFF;
 #pragma unroll
-        for (int w = 0; w < W; w++) a.frames_t[((size_t)f * W + w) * a.Cpad + c] = out[w];
+            for (int k = 0; k < NBYTES - 2; k++) crc = crc16_update(crc, (uint8_t)(out[k >> 2] >> (8 * (k & 3))));
+            const unsigned hi = (out[(NBYTES - 2) >> 2] >> (8 * ((NBYTES - 2) & 3))) & 0xffu;
+            const unsigned lo = (out[(NBYTES - 1) >> 2] >> (8 * ((NBYTES - 1) & 3))) & 0xffu;
+            ok = (hi == (unsigned)(crc >> 8) && lo == (unsigned)(crc & 0xff)) ? 1u : 0u;
+            if (rot == 0) {
+#pragma unroll
+                for (int w = 0; w < W; w++) first[w] = out[w];
+            }
+            if (ok) break;
+#pragma unroll
+            for (int w = 0; w < W; w++) raw[w] = unrotate_dibits(raw[w]);
+        }
+#pragma unroll
+        for (int w = 0; w < W; w++) a.frames_t[((size_t)f * W + w) * a.Cpad + c] = ok ? out[w] : first[w];
         a.crc_ok_t[(size_t)f * a.Cpad + c] = (uint8_t)ok;
+        if (a.rotation_t) a.rotation_t[(size_t)f * a.Cpad + c] = ok ? (uint8_t)rot : (uint8_t)255;
     }
     // one atomic per warp: ballot the verdicts
     const unsigned live = __ballot_sync(0xffffffffu, c < a.C);

@@ -80,6 +80,7 @@ struct qpsk_b200_rx {
     float2* d_costas_dbg;   // [maxF][nsym][Cpad] or null
     unsigned* d_frames_t;   // [maxF][W][Cpad] decoded frames (DECODE_FRAMES)
     uint8_t* d_crc_ok_t;    // [maxF][Cpad]
+    uint8_t* d_rotation_t;  // [maxF][Cpad] (RESOLVE_ROTATION)
     unsigned long long* d_counters;   // [2]
     int16_t* d_pcm_stage2[2];   // host path: double-buffered PCM slices (lazy)
     unsigned* d_out_stage2[2];  // host path: double-buffered transposed dibit slices
@@ -123,7 +124,7 @@ static int rx_free(qpsk_b200_rx* rx) {
     if (rx->est_fft) qpsk_b200_fft_destroy(rx->est_fft);
     void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor2[0], rx->d_phasor2[1], rx->d_ph_state2, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
-                     rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters,
+                     rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters,
                      rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev) if (e) cudaEventDestroy(e);
@@ -216,6 +217,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (cfg->flags & QPSK_B200_DECODE_FRAMES) {
         alloc((void**)&rx->d_frames_t, F * (S / 16) * Cp * sizeof(unsigned));
         alloc((void**)&rx->d_crc_ok_t, F * Cp);
+        if (cfg->flags & QPSK_B200_RESOLVE_ROTATION) alloc((void**)&rx->d_rotation_t, F * Cp);
         alloc((void**)&rx->d_counters, 2 * sizeof(unsigned long long));
     }
     if (e != cudaSuccess) {
@@ -279,13 +281,13 @@ static int upload_keystream(int nbytes, cudaStream_t s) {
     return 0;
 }
 
-static int launch_frame_decode(int nbytes, const unsigned* dibits_t, unsigned* frames_t, uint8_t* crc_ok_t,
+static int launch_frame_decode(int nbytes, const unsigned* dibits_t, unsigned* frames_t, uint8_t* crc_ok_t, uint8_t* rotation_t,
                                unsigned long long* counters, int c0, int C, int Cpad, int F, cudaStream_t s) {
     if (nbytes != 16 && nbytes != 32) return fail(QPSK_B200_ERR_ARG, "frame decode supports 16- and 32-byte frames, got %d", nbytes);
     int rc = upload_keystream(nbytes, s);
     if (rc) return rc;
     FrameDecodeArgs a;
-    a.dibits_t = dibits_t; a.frames_t = frames_t; a.crc_ok_t = crc_ok_t; a.counters = counters; a.C = C; a.Cpad = Cpad; a.F = F; a.c0 = c0;
+    a.dibits_t = dibits_t; a.frames_t = frames_t; a.crc_ok_t = crc_ok_t; a.rotation_t = rotation_t; a.counters = counters; a.C = C; a.Cpad = Cpad; a.F = F; a.c0 = c0;
     dim3 grid((C - c0 + 127) / 128, F);
     if (nbytes == 32) frame_decode_kernel<32><<<grid, 128, 0, s>>>(a);
     else frame_decode_kernel<16><<<grid, 128, 0, s>>>(a);
@@ -390,7 +392,7 @@ static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, 
     rx->last_fused = fused;
 
     if (rx->d_frames_t) {   // K4: descramble -> de-interleave -> CRC16 per frame
-        int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t, rx->d_frames_t, rx->d_crc_ok_t, rx->d_counters, c0, ca.c1, rx->Cpad, F, s);
+        int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t, rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, c0, ca.c1, rx->Cpad, F, s);
         if (rc) return rc;
         rx->launches += 1;
     }
@@ -470,6 +472,7 @@ extern "C" size_t qpsk_b200_rx_output_bytes(const qpsk_b200_rx* rx, int what) {
         case QPSK_B200_OUT_TAPS: return (size_t)rx->cfg.ntaps * sizeof(float);
         case QPSK_B200_OUT_FRAMES: return C * F * (S / 4);
         case QPSK_B200_OUT_CRC_OK: return C * F;
+        case QPSK_B200_OUT_ROTATION: return C * F;
         default: return 0;
     }
 }
@@ -516,6 +519,9 @@ extern "C" int qpsk_b200_rx_read(qpsk_b200_rx* rx, int what, void* h_dst, size_t
         case QPSK_B200_OUT_CRC_OK:
             if (!rx->d_crc_ok_t) return fail(QPSK_B200_ERR_STATE, "frames were not decoded (QPSK_B200_DECODE_FRAMES)");
             return download_transposed<uint8_t>(rx, rx->d_crc_ok_t, F, h_dst, s);
+        case QPSK_B200_OUT_ROTATION:
+            if (!rx->d_rotation_t) return fail(QPSK_B200_ERR_STATE, "rotations were not resolved (QPSK_B200_DECODE_FRAMES | QPSK_B200_RESOLVE_ROTATION)");
+            return download_transposed<uint8_t>(rx, rx->d_rotation_t, F, h_dst, s);
         case QPSK_B200_OUT_SYMBOLS:
             if (!rx->d_costas_dbg) return fail(QPSK_B200_ERR_STATE, "symbols were not kept (QPSK_B200_KEEP_SYMBOLS)");
             return download_transposed<float2>(rx, rx->d_costas_dbg, F * S, h_dst, s);
@@ -1046,14 +1052,15 @@ __global__ void transpose_from_channel_major(const unsigned* __restrict__ src, u
     }
 }
 
-static int frames_codec(const uint8_t* h_in, int nbytes, int nchan, int nframes, uint8_t* h_out, uint8_t* h_crc_ok, int device, bool encode) {
+static int frames_codec(const uint8_t* h_in, int nbytes, int nchan, int nframes, uint8_t* h_out, uint8_t* h_crc_ok, uint8_t* h_rotation,
+                        int device, bool encode) {
     if (!h_in || !h_out || nchan < 1 || nframes < 1) return fail(QPSK_B200_ERR_ARG, "bad argument");
     if (nbytes != 16 && nbytes != 32) return fail(QPSK_B200_ERR_ARG, "frame codec supports 16- and 32-byte frames, got %d", nbytes);
     int rc = check_device(device);
     if (rc) return rc;
     const int W = nbytes / 4, rows = nframes * W, Cpad = (nchan + 31) / 32 * 32;
     const size_t words = (size_t)rows * Cpad, bytes_cm = (size_t)nchan * rows * 4;
-    DevBuf cm, a, b, ok, cnt, okcm;
+    DevBuf cm, a, b, ok, rot, cnt, okcm;
     CU(cudaMalloc(&cm.p, bytes_cm));
     CU(cudaMalloc(&a.p, words * 4));
     CU(cudaMalloc(&b.p, words * 4));
@@ -1073,7 +1080,9 @@ static int frames_codec(const uint8_t* h_in, int nbytes, int nchan, int nframes,
         CU(cudaMalloc(&ok.p, (size_t)nframes * Cpad));
         CU(cudaMalloc(&cnt.p, 2 * sizeof(unsigned long long)));
         CU(cudaMemset(cnt.p, 0, 2 * sizeof(unsigned long long)));
-        rc = launch_frame_decode(nbytes, (const unsigned*)a.p, (unsigned*)b.p, (uint8_t*)ok.p, (unsigned long long*)cnt.p, 0, nchan, Cpad, nframes, 0);
+        if (h_rotation) CU(cudaMalloc(&rot.p, (size_t)nframes * Cpad));
+        rc = launch_frame_decode(nbytes, (const unsigned*)a.p, (unsigned*)b.p, (uint8_t*)ok.p, (uint8_t*)rot.p, (unsigned long long*)cnt.p, 0, nchan,
+                                 Cpad, nframes, 0);
         if (rc) return rc;
     }
     transpose_to_channel_major<unsigned><<<tgrid, tblock>>>((const unsigned*)b.p, (unsigned*)cm.p, rows, nchan, Cpad);
@@ -1086,15 +1095,28 @@ static int frames_codec(const uint8_t* h_in, int nbytes, int nchan, int nframes,
         CU(cudaGetLastError());
         CU(cudaMemcpy(h_crc_ok, okcm.p, (size_t)nchan * nframes, cudaMemcpyDeviceToHost));
     }
+    if (!encode && h_rotation) {
+        if (!okcm.p) CU(cudaMalloc(&okcm.p, (size_t)nchan * nframes));
+        dim3 g2((nchan + 31) / 32, (nframes + 31) / 32);
+        transpose_to_channel_major<uint8_t><<<g2, tblock>>>((const uint8_t*)rot.p, (uint8_t*)okcm.p, nframes, nchan, Cpad);
+        CU(cudaGetLastError());
+        CU(cudaMemcpy(h_rotation, okcm.p, (size_t)nchan * nframes, cudaMemcpyDeviceToHost));
+    }
     return QPSK_B200_OK;
 }
 
 extern "C" int qpsk_b200_frames_encode(const uint8_t* h_payload, int nbytes, int nchan, int nframes, uint8_t* h_dibits, int device) {
-    return frames_codec(h_payload, nbytes, nchan, nframes, h_dibits, nullptr, device, true);
+    return frames_codec(h_payload, nbytes, nchan, nframes, h_dibits, nullptr, nullptr, device, true);
 }
 
 extern "C" int qpsk_b200_frames_decode(const uint8_t* h_dibits, int nbytes, int nchan, int nframes, uint8_t* h_frames, uint8_t* h_crc_ok, int device) {
-    return frames_codec(h_dibits, nbytes, nchan, nframes, h_frames, h_crc_ok, device, false);
+    return frames_codec(h_dibits, nbytes, nchan, nframes, h_frames, h_crc_ok, nullptr, device, false);
+}
+
+extern "C" int qpsk_b200_frames_decode_rotated(const uint8_t* h_dibits, int nbytes, int nchan, int nframes, uint8_t* h_frames,
+                                               uint8_t* h_crc_ok, uint8_t* h_rotation, int device) {
+    if (!h_rotation) return fail(QPSK_B200_ERR_ARG, "bad argument");
+    return frames_codec(h_dibits, nbytes, nchan, nframes, h_frames, h_crc_ok, h_rotation, device, false);
 }
 
 // =============================================================================================

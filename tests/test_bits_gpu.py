@@ -102,3 +102,60 @@ def test_receiver_decodes_frames_on_device(oracle_lib):
     n, passes = rx.crc_counters()
     assert n == 40 * 6 and passes == int(ok.sum())
     rx.close()
+
+
+@pytest.mark.parametrize("nbytes", [16, 32])
+def test_rotation_resolved_on_the_crc(oracle_lib, nbytes):
+    """RESOLVE_ROTATION: every frame turned by 0..3 quarter turns (the Costas loop's ambiguity) decodes to
+    the same payload and reports the turn; garbage reports 255 and the rotation-0 decode, like the oracle."""
+    import qpsk_b200
+    from qpsk_b200 import bits
+    o = oracle_lib.Oracle()
+    rng = np.random.default_rng(100 + nbytes)
+    C, F = 37, 11
+    payload = rng.integers(0, 256, (C, F, nbytes), dtype=np.uint8)
+    dib = qpsk_b200.unpack_dibits(bits.frames_encode(payload)).reshape(C, F, 4 * nbytes)
+    turns = rng.integers(0, 4, (C, F))
+    ahead = np.array([[0, 1, 2, 3], [1, 3, 0, 2], [3, 2, 1, 0], [2, 0, 3, 1]], np.uint8)   # rho^r(d), qpsk.c:58-63
+    turned = np.stack([[ahead[turns[c, f]][dib[c, f]] for f in range(F)] for c in range(C)]).astype(np.uint8)
+    assert np.array_equal(turned[0, 0], o.rotate_dibits(dib[0, 0], turns[0, 0]))
+    turned[5, 3] = rng.integers(0, 4, 4 * nbytes)                  # one frame of noise
+    flat = turned.reshape(C, F * 4 * nbytes)
+    packed = (flat[:, 0::4] | (flat[:, 1::4] << 2) | (flat[:, 2::4] << 4) | (flat[:, 3::4] << 6)).astype(np.uint8)
+    frames, ok, rot = bits.frames_decode(packed, nbytes, resolve_rotation=True)
+    for c in range(C):
+        for f in range(F):
+            wf, wr = o.frame_decode_rotated(turned[c, f], nbytes)
+            assert int(rot[c, f]) == (wr if wr >= 0 else 255) and bool(ok[c, f]) == (wr >= 0)
+            assert np.array_equal(frames[c, f], wf)
+    good = np.ones((C, F), bool)
+    good[5, 3] = False
+    assert np.array_equal(rot[good], turns[good].astype(np.uint8)) and ok[good].all()
+    assert np.array_equal(frames[good][:, :nbytes - 2], payload[good][:, :nbytes - 2])
+    # without the flag only the unturned frames pass
+    _, ok0 = bits.frames_decode(packed, nbytes)
+    assert np.array_equal(ok0.astype(bool) & good, (turns == 0) & good)
+
+
+def test_receiver_resolves_rotation_on_device(oracle_lib):
+    """DECODE_FRAMES | RESOLVE_ROTATION in the receiver: OUT_ROTATION / OUT_FRAMES / OUT_CRC_OK equal the oracle's
+    rotated decode of the oracle's dibits; a flagless receiver refuses OUT_ROTATION."""
+    import qpsk_b200
+    from qpsk_b200 import capi
+    from synth import make_pcm
+    o = oracle_lib.Oracle()
+    pcm, _ = make_pcm(33, 5, seed=78, esn0_db=20.0, oracle=o)
+    want_dibits = o.rx_run(pcm, want=("dibit",))["dibit"].reshape(33, 5, 128)
+    rx = qpsk_b200.Receiver(33, 5, decode_frames=True, resolve_rotation=True)
+    rx.rx_frames(pcm)
+    frames, ok, rot = rx.read(capi.OUT_FRAMES), rx.read(capi.OUT_CRC_OK), rx.read(capi.OUT_ROTATION)
+    for c in range(33):
+        for f in range(5):
+            wf, wr = o.frame_decode_rotated(want_dibits[c, f], 32)
+            assert np.array_equal(frames[c, f], wf) and int(rot[c, f]) == (wr if wr >= 0 else 255) and bool(ok[c, f]) == (wr >= 0)
+    rx.close()
+    rx = qpsk_b200.Receiver(4, 2, decode_frames=True)
+    rx.rx_frames(pcm[:4, :1024])
+    with pytest.raises(RuntimeError):
+        rx.read(capi.OUT_ROTATION)
+    rx.close()
