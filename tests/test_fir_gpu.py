@@ -30,6 +30,8 @@ def test_fir256_reference_golden(golden):
     (127, 2400.0, 70, (512, 1, 127, 300, 1024)),      # ragged call lengths incl. shorter than the filter
     (256, 1200.0, 33, (700, 5, 256, 129)),            # long-tap profile (config 3), two halo tiles
     (127, 2400.0, 1, (1024,)),                        # the reference's own TX call shape
+    (127, 2400.0, 40, (4099, 2000, 6144)),            # long calls are cut into time blocks (saved halos); odd length = 8-byte path
+    (256, 1200.0, 20, (3001, 4096)),
 ])
 def test_fir_exact_vs_oracle_with_carried_delay_line(oracle_lib, ntaps, rs, nchan, lengths):
     import qpsk_b200
