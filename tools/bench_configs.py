@@ -89,7 +89,7 @@ def main():
     # ---- config 3: 256-tap FIR, 16,384 channels x T samples, in place -------------------------------
     for ntaps, rs in ((256, 1200.0), (127, 2400.0)):
         for mode_name, mode in (("exact", capi.MODE_EXACT), ("fast", capi.MODE_FAST)):
-            Cn, T = 16384, (8192 if args.quick else 32768)
+            Cn, T = 16384, (8192 if args.quick else 65536)      # 8 GiB filtered in place
             taps = qpsk_b200.rrc_make(ntaps, 9600.0, rs, 0.35)
             x = torch.randn((Cn, T, 2), device=dev, dtype=torch.float32)
             f = qpsk_b200.Fir(taps, Cn, mode=mode)
