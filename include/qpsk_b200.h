@@ -47,7 +47,9 @@ enum {
 enum { QPSK_B200_MODE_EXACT = 0,   /* reference arithmetic, bit-exact decisions */
        QPSK_B200_MODE_FAST = 1 };  /* fused multiply-add FIR (<= 1e-5 relative), not bit-exact */
 enum { QPSK_B200_UB_ALIAS = 0,     /* reproduce the Makefile-build out-of-frame read of qpsk.c:190 */
-       QPSK_B200_UB_CLAMP = 1 };   /* fenced: out-of-frame reads return the last sample of the frame */
+       QPSK_B200_UB_CLAMP = 1,     /* fenced: out-of-frame reads return the last sample of the frame */
+       QPSK_B200_UB_PHASE = 2 };   /* extension, not the reference: the timing index only picks the sampling phase
+                                      (sample i*CYCLES + index % CYCLES), so no symbol is ever taken from outside the frame */
 
 enum {                              /* cfg.flags */
     QPSK_B200_KEEP_FIR = 1,         /* keep the matched-filter output (16 B/sample!) for parity checks */
@@ -55,6 +57,9 @@ enum {                              /* cfg.flags */
     QPSK_B200_DECODE_FRAMES = 4,    /* run descramble -> de-interleave -> CRC16 on every frame's dibits */
     QPSK_B200_NO_FUSE = 8,          /* always run the Costas loop as its own kernel (it is fused into the front end
                                        whenever a CTA owns whole streams, i.e. when channels are plentiful) */
+    QPSK_B200_SLICE_DIAGONAL = 32,  /* extension, not the reference: slice the loop output on the diagonals where phase_detector
+                                       locks it, without qpsk_demod's extra 45 degrees (qpsk.c:75) that leaves bits[0] on a
+                                       decision boundary; with UB_PHASE + RESOLVE_ROTATION this makes framed loop-back decodable */
     QPSK_B200_RESOLVE_ROTATION = 16 /* with DECODE_FRAMES: a frame whose CRC fails is retried with its dibits turned back
                                        by 90, 180 and 270 degrees (the loop's phase ambiguity); first match wins */
 };

@@ -87,12 +87,14 @@ class Oracle:
     """One modem profile of the restatement.  Defaults are the reference's (qpsk.h:16-23, rrc_fir.h:13)."""
 
     def __init__(self, fs=9600.0, rs=2400.0, center=1500.0, rrc_alpha=0.35, ntaps=127, frame_size=512,
-                 loop_bw=None, ub_mode=0):
+                 loop_bw=None, ub_mode=0, slice_diagonal=False):
         self.L = lib()
         self.p = _Profile()
         if loop_bw is None:
             loop_bw = np.float32(TAU / 100.0)  # qpsk.c:302
         self.L.orc_profile_init(C.byref(self.p), fs, rs, center, rrc_alpha, ntaps, frame_size, float(loop_bw), ub_mode)
+        if slice_diagonal:
+            self.L.orc_profile_slice_diagonal(C.byref(self.p), 1)
         self.sps, self.frame_size, self.nsym, self.ntaps = self.p.sps, self.p.frame_size, self.p.nsym, self.p.ntaps
         self.fs = fs
 

@@ -164,6 +164,14 @@ void orc_profile_init(orc_profile *p, float fs, float rs, float center, float rr
     orc_loop_create(&p->loop0, loop_bw, -1.0f, 1.0f);            /* qpsk.c:302 */
 }
 
+/* Extension (not the reference): slice the loop output where phase_detector locks it, on the
+ * diagonals, i.e. without qpsk_demod's extra 45 degrees that leaves one bit on a decision boundary
+ * (SURVEY finding 3).  Multiplying by 1+0i keeps orc_qpsk_demod's arithmetic shape. */
+void orc_profile_slice_diagonal(orc_profile *p, int on) {
+    if (on) { p->rot45.re = 1.0f; p->rot45.im = 0.0f; }
+    else p->rot45 = cf_cis((float)(M_PI / 4.0));
+}
+
 void orc_rx_state_init(const orc_profile *p, orc_rx_state *s) {
     memset(s, 0, sizeof *s);
     s->rx_phase = cf_cis(0.0f);                                  /* qpsk.c:341 */
@@ -229,7 +237,8 @@ void orc_rx_frame(const orc_profile *p, orc_rx_state *s, const int16_t *pcm, con
      * decimated_frame[index-4], which this very loop has already refreshed (SURVEY finding 1). */
     for (int i = 0; i < nsym; i++) {
         s->dec[i] = s->dec[nsym + i];
-        const int j = i * sps + index;
+        /* ORC_UB_PHASE (extension, not the reference): the histogram picks a sampling phase only */
+        const int j = i * sps + (p->ub_mode == ORC_UB_PHASE ? index % sps : index);
         if (j < N) s->dec[nsym + i] = frame[j];
         else if (p->ub_mode == ORC_UB_ALIAS) s->dec[nsym + i] = s->dec[j - N];
         else s->dec[nsym + i] = frame[N - 1];

@@ -34,7 +34,8 @@ typedef struct { float re, im; } orc_cf;
 typedef struct { double re, im; } orc_cd;
 
 enum { ORC_UB_ALIAS = 0, /* Makefile (-O0) build: input_frame[512+k] aliases decimated_frame[k] */
-       ORC_UB_CLAMP = 1  /* fenced variant: out-of-frame reads return input_frame[FRAME_SIZE-1] */ };
+       ORC_UB_CLAMP = 1, /* fenced variant: out-of-frame reads return input_frame[FRAME_SIZE-1] */
+       ORC_UB_PHASE = 2  /* extension: sample i*CYCLES + index % CYCLES, never out of frame */ };
 
 /* ---- RRC FIR: rrc_fir.c:17-76 -------------------------------------------------------- */
 void orc_rrc_make(float *taps, int ntaps, float fs, float rs, float alpha);
@@ -97,6 +98,7 @@ void orc_rx_run(const orc_profile *p, orc_rx_state *states, const int16_t *pcm, 
                 float *phase, float *freq);
 
 void orc_qpsk_demod(const orc_profile *p, orc_cf sym, int bits[2]);
+void orc_profile_slice_diagonal(orc_profile *p, int on);
 
 /* ---- transmit: qpsk.c:58-63,225-285 --------------------------------------------------- */
 typedef struct {

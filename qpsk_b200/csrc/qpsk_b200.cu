@@ -165,6 +165,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     const int sps = (int)((double)cfg->fs / (double)cfg->rs);   // CYCLES, qpsk.h:21
     if (sps != 4 && sps != 8) return fail(QPSK_B200_ERR_ARG, "samples/symbol %d unsupported (4 = 2400 baud, 8 = 1200 baud)", sps);
     if (cfg->mode != QPSK_B200_MODE_EXACT && cfg->mode != QPSK_B200_MODE_FAST) return fail(QPSK_B200_ERR_ARG, "bad mode");
+    if (cfg->ub_mode < QPSK_B200_UB_ALIAS || cfg->ub_mode > QPSK_B200_UB_PHASE) return fail(QPSK_B200_ERR_ARG, "bad ub_mode %d", cfg->ub_mode);
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(QPSK_B200_ERR_CUDA, "CUDA device %d not present (%d devices)", cfg->device, ndev);
@@ -193,6 +194,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     rx->rect = make_float2(t2[0], t2[1]);
     qpsk_host_cis(3.14159265358979323846 / 4.0, 0, t2);                                    // qpsk.c:75
     rx->rot45 = make_float2(t2[0], t2[1]);
+    if (cfg->flags & QPSK_B200_SLICE_DIAGONAL) rx->rot45 = make_float2(1.0f, 0.0f);        // extension: qpsk_demod without its 45 degrees
     qpsk_host_loop_create(&rx->loop, cfg->loop_bw, -1.0f, 1.0f);                           // qpsk.c:302
 
     const size_t Cp = rx->Cpad, F = max_frames, N = rx->N, S = rx->nsym;

@@ -15,7 +15,7 @@
 #include "rx_costas.cuh"
 
 enum { QPSK_MODE_EXACT = 0, QPSK_MODE_FAST = 1 };
-enum { QPSK_UB_ALIAS = 0, QPSK_UB_CLAMP = 1 };
+enum { QPSK_UB_ALIAS = 0, QPSK_UB_CLAMP = 1, QPSK_UB_PHASE = 2 };
 
 // taps duplicated into both halves of a 64-bit constant: the packed-FP32 multiplier operand
 __constant__ float2 c_taps2[QPSK_MAX_TAPS];
@@ -338,8 +338,9 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
             {
                 const int slot = (a.slot_base + 1 + f) % a.nslots;
                 float2* dst = a.dec_ring + (size_t)slot * nsym * a.Cpad + ch;
+                const int first = a.ub_mode == QPSK_UB_PHASE ? index % SPS : index;   // extension: a sampling phase, never a slip
                 for (int i = comp; i < NSYM; i += 2) {
-                    int j = i * SPS + index;
+                    int j = i * SPS + first;
                     float2 v = make_float2(0.0f, 0.0f);            // aliasing read of decimated_frame[j-N]: patched by the Costas stage
                     if (j >= N && a.ub_mode == QPSK_UB_CLAMP) j = N - 1;
                     if (j < N) v = make_float2(__ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP)), __ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP) + QPSK_GROUP));
