@@ -341,8 +341,27 @@ static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, 
     // enough CTAs for a few waves over the SMs: split the frames of a channel group when channels are few
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, rx->cfg.device);
+    // How many frame blocks per channel group?  One block (the CTA owns whole streams) lets the Costas loop ride along
+    // in the CTA's spare warp; more blocks fill the machine when channels are few, or when the groups are an awkward
+    // number of waves (16,384 channels = 512 CTAs = 1.73 waves of 2 x nsm), at the price of the loop as its own kernel.
+    // Costs in units of one frame of one resident CTA (~83 us at 2400 baud), from profiles/r01_notes.md: the front end
+    // without the loop runs ~3 % faster, a block start costs about a third of a frame, the stand-alone loop needs
+    // max(latency of one stream at ~520 cycles per symbol, its share of 2.9 ms per 65,536 channels x 64 frames).
     int fblocks = 1;
-    while (ngroups * fblocks < 4 * nsm && fblocks < F) fblocks *= 2;
+    {
+        const int slots = 2 * nsm;
+        const double unit_us = 82.8;
+        const double loop_units = fmax((double)F * rx->nsym * 520.0 / 1965.0 / unit_us,
+                                       2900.0 / unit_us * ((double)nc * F / (65536.0 * 64.0)));
+        double best = rx->no_fuse ? 1e30 : (double)((ngroups + slots - 1) / slots) * F;
+        for (int fb = rx->no_fuse ? 1 : 2; fb <= F; fb++) {              // fb = 1 with the loop fused is `best` already
+            const int fpb = (F + fb - 1) / fb, nb = (F + fpb - 1) / fpb;
+            if (nb != fb) continue;                                     // same split as a smaller fb
+            const double waves = (double)(((long long)ngroups * nb + slots - 1) / slots);
+            const double t = waves * (fpb + 0.3) * 0.97 + loop_units;
+            if (t < best * 0.98) { best = t; fblocks = nb; }            // 2 % hysteresis in favour of fewer blocks
+        }
+    }
     fa.frames_per_block = (F + fblocks - 1) / fblocks;
     fblocks = (F + fa.frames_per_block - 1) / fa.frames_per_block;
     const int grid = ngroups * fblocks;
