@@ -115,3 +115,15 @@ def test_config1_shape_all_channels_bit_exact(oracle_lib):
     track = rx.read(capi.OUT_TRACK)
     assert np.array_equal(track[..., 0], want["phase"]) and np.array_equal(track[..., 1], want["freq"])
     rx.close()
+
+
+def test_config2_every_channel_bit_exact(oracle_lib, monkeypatch, capsys):
+    """SURVEY 8(d) "all channels once": the bench workload itself, 65,536 distinct channels x 64 frames, against the
+    oracle on all host cores (tools/full_parity.py; ~20 s on 16 cores): dibits, timing indices and loop tracks."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import full_parity
+    monkeypatch.setattr(sys, "argv", ["full_parity.py", "65536", "64"])
+    full_parity.main()
+    assert "bit-exact on every channel" in capsys.readouterr().out
