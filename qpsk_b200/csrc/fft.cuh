@@ -13,6 +13,10 @@
 
 #include "common.cuh"
 
+#ifndef QPSK_FFT_PREFETCH_MIN_N
+#define QPSK_FFT_PREFETCH_MIN_N 1024
+#endif
+
 template <int LOG2N>
 struct FftCfg {
     static constexpr int N = 1 << LOG2N;
@@ -26,7 +30,12 @@ struct FftCfg {
     // so that the lanes of a warp (consecutive k) read consecutive words -- no bank conflicts, no products to form
     static constexpr int tw_count() { int ns = 1, tot = 0; while (ns < N) { int rem = N / ns; int r = rem >= P ? P : rem; if (ns > 1) tot += (r - 1) * ns; ns *= r; } return tot > 0 ? tot : 1; }
     static constexpr int TW = tw_count();
-    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + sizeof(float2) * TW + sizeof(float) * 64 + sizeof(int) * 64;
+    // transforms of n >= PREFETCH_MIN_N points are staged: while one pass is being transformed the next pass's input
+    // lands in a second buffer through cp.async, so a CTA that fills its SM (512 threads x 128 registers at n = 8192)
+    // no longer idles through every load
+    static constexpr bool PREFETCH = (N >= QPSK_FFT_PREFETCH_MIN_N);
+    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + sizeof(float2) * TW + sizeof(float) * 64 + sizeof(int) * 64
+                                 + (PREFETCH ? sizeof(float2) * PTS : 0);
 };
 
 // Tolerance-mode arithmetic (1e-5) on packed FP32 pairs: one complex value per 64-bit register.  FADD2 takes
@@ -139,7 +148,8 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int idx = jj + r * (N / R);
-            if (FIRST) v[r] = cconj_if(active ? reinterpret_cast<const c64*>(gin)[idx] : 0ull, imsgn);   // inverse = conj(FFT(conj x))
+            if (FIRST && Cfg::PREFETCH) v[r] = cconj_if(reinterpret_cast<const c64*>(gin)[idx], imsgn);   // gin = this transform in the staging buffer (zero-filled when inactive)
+            else if (FIRST) v[r] = cconj_if(active ? reinterpret_cast<const c64*>(gin)[idx] : 0ull, imsgn);   // inverse = conj(FFT(conj x))
             else v[r] = sdat[fft_skew(base + idx)];
         }
         if (NS > 1) {
@@ -207,12 +217,36 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
 
     const int fl = threadIdx.x / TPF, j = threadIdx.x % TPF;
     const int base = fl * N;
+    c64* stage = reinterpret_cast<c64*>(red_idx + 64);      // [FPB][N], only with Cfg::PREFETCH
+    // one pass = FPB consecutive transforms = PTS contiguous points: P/2 16-byte pieces per thread
+    auto prefetch = [&](int pass_b0) {
+#pragma unroll
+        for (int i = 0; i < P / 2; i++) {
+            const int piece = threadIdx.x + i * Cfg::THREADS;            // 2 points each
+            const int pb = pass_b0 + (2 * piece) / N;
+            const bool in_range = pb < a.nbursts;
+            const float2* src = a.in + (in_range ? (size_t)pass_b0 * N + 2 * (size_t)piece : 0);
+            const unsigned d = (unsigned)__cvta_generic_to_shared(stage + 2 * piece);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(in_range ? 16 : 0) : "memory");
+        }
+    };
+    if (Cfg::PREFETCH && blockIdx.x * FPB < a.nbursts) prefetch(blockIdx.x * FPB);
     for (int b0 = blockIdx.x * FPB; b0 < a.nbursts; b0 += gridDim.x * FPB) {
         const int b = b0 + fl;
         const bool active = b < a.nbursts;
-        const float2* gin = a.in + (size_t)(active ? b : 0) * N;
         c64 pts[P];
-        fft_stages<LOG2N, 1, true>(pts, sdat, stw, gin, j, base, active, a.im_sign);
+        if constexpr (Cfg::PREFETCH) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();                                             // this pass's input has landed for everyone
+            constexpr int R0 = P;                                        // N >= P * P here: the first stage is a full radix-P one
+            fft_stage<LOG2N, R0, 1, true, false>(pts, sdat, stw, reinterpret_cast<const float2*>(stage + base), j, base, active, a.im_sign);
+            // the stage ended with a barrier after everyone's reads of the staging buffer: refill it
+            if (b0 + gridDim.x * FPB < a.nbursts) prefetch(b0 + gridDim.x * FPB);
+            fft_stages<LOG2N, R0, false>(pts, sdat, stw, nullptr, j, base, active, a.im_sign);
+        } else {
+            const float2* gin = a.in + (size_t)(active ? b : 0) * N;
+            fft_stages<LOG2N, 1, true>(pts, sdat, stw, gin, j, base, active, a.im_sign);
+        }
         // ---- epilogue: scale, optional spectrum store, |X|^2 argmax
         float best = -1.0f;
         int besti = 0x7fffffff;
