@@ -16,14 +16,24 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-SHM = "/dev/shm/qpsk_full_parity_pcm.i16"
+def _scratch_path(nbytes):
+    """A file the worker processes can map: /dev/shm when it has room, else the temp directory."""
+    import shutil
+    import tempfile
+    for d in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if os.path.isdir(d) and shutil.disk_usage(d).free > nbytes + (256 << 20):
+                return os.path.join(d, "qpsk_full_parity_%d.i16" % os.getpid())
+        except OSError:
+            pass
+    raise SystemExit("no scratch space for %d bytes of PCM" % nbytes)
 
 
 def _worker(args):
-    c0, c1, nsamp = args
+    path, c0, c1, nsamp = args
     from oracle import Oracle
     o = Oracle()
-    pcm = np.memmap(SHM, dtype=np.int16, mode="r").reshape(-1, nsamp)
+    pcm = np.memmap(path, dtype=np.int16, mode="r").reshape(-1, nsamp)
     out = o.rx_run(np.ascontiguousarray(pcm[c0:c1]), want=("index", "dibit", "phase", "freq"))
     d = out["dibit"]
     packed = (d[:, 0::4] | (d[:, 1::4] << 2) | (d[:, 2::4] << 4) | (d[:, 3::4] << 6)).astype(np.uint8)
@@ -47,24 +57,27 @@ def main():
     idx = rx.read(capi.OUT_INDEX)
     track = rx.read(capi.OUT_TRACK)
     rx.close()
+    SHM = _scratch_path(nchan * nsamp * 2)
     host = np.memmap(SHM, dtype=np.int16, mode="w+", shape=(nchan, nsamp))
     host[:] = pcm.cpu().numpy()
     host.flush()
     del pcm
     cores = os.cpu_count() or 1
     step = max(32, nchan // (cores * 8))
-    jobs = [(c, min(nchan, c + step), nsamp) for c in range(0, nchan, step)]
+    jobs = [(SHM, c, min(nchan, c + step), nsamp) for c in range(0, nchan, step)]
     t0 = time.time()
     bad = {"dibit_bytes": 0, "index": 0, "phase": 0, "freq": 0}
-    with mp.get_context("spawn").Pool(cores) as pool:
-        for c0, packed, windex, wphase, wfreq in pool.imap_unordered(_worker, jobs):
-            c1 = c0 + packed.shape[0]
-            bad["dibit_bytes"] += int((got[c0:c1] != packed).sum())
-            bad["index"] += int((idx[c0:c1] != windex).sum())
-            bad["phase"] += int((track[c0:c1, :, 0].view(np.uint32) != wphase.view(np.uint32)).sum())
-            bad["freq"] += int((track[c0:c1, :, 1].view(np.uint32) != wfreq.view(np.uint32)).sum())
+    try:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            for c0, packed, windex, wphase, wfreq in pool.imap_unordered(_worker, jobs):
+                c1 = c0 + packed.shape[0]
+                bad["dibit_bytes"] += int((got[c0:c1] != packed).sum())
+                bad["index"] += int((idx[c0:c1] != windex).sum())
+                bad["phase"] += int((np.ascontiguousarray(track[c0:c1, :, 0]).view(np.uint32) != wphase.view(np.uint32)).sum())
+                bad["freq"] += int((np.ascontiguousarray(track[c0:c1, :, 1]).view(np.uint32) != wfreq.view(np.uint32)).sum())
+    finally:
+        os.unlink(SHM)
     dt = time.time() - t0
-    os.unlink(SHM)
     print({"channels": nchan, "frames": nframes, "symbols": nchan * nframes * 128, "oracle_cores": cores,
            "oracle_seconds": round(dt, 1), "mismatches": bad})
     if any(bad.values()):
