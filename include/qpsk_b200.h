@@ -60,6 +60,11 @@ enum {                              /* cfg.flags */
     QPSK_B200_SLICE_DIAGONAL = 32,  /* extension, not the reference: slice the loop output on the diagonals where phase_detector
                                        locks it, without qpsk_demod's extra 45 degrees (qpsk.c:75) that leaves bits[0] on a
                                        decision boundary; with UB_PHASE + RESOLVE_ROTATION this makes framed loop-back decodable */
+    QPSK_B200_ESTIMATE_OFFSET = 64, /* run the FFT frequency estimator inside every process call: 4th power of the call's first
+                                       n decimated symbols per channel (n = the largest power of two <= min(1024, symbols of
+                                       the call)) -> batched n-point FFT -> |X|^2 argmax, results in HBM (OUT_OFFSET_BIN/_HZ).
+                                       The reference has fftn() but never calls it: an extension output, the
+                                       receive decisions do not depend on it */
     QPSK_B200_RESOLVE_ROTATION = 16 /* with DECODE_FRAMES: a frame whose CRC fails is retried with its dibits turned back
                                        by 90, 180 and 270 degrees (the loop's phase ambiguity); first match wins */
 };
@@ -91,8 +96,10 @@ enum {
     QPSK_B200_OUT_TAPS = 6,     /* float  [ntaps] */
     QPSK_B200_OUT_FRAMES = 7,   /* uint8  [C][F*nbytes]  de-scrambled, de-interleaved frames: payload | crc16 hi | lo (needs DECODE_FRAMES) */
     QPSK_B200_OUT_CRC_OK = 8,   /* uint8  [C][F]         1 where the frame's CRC16 matched (needs DECODE_FRAMES) */
-    QPSK_B200_OUT_ROTATION = 9  /* uint8  [C][F]         quarter turns undone before the CRC matched, 0..3; 255 = no match
+    QPSK_B200_OUT_ROTATION = 9, /* uint8  [C][F]         quarter turns undone before the CRC matched, 0..3; 255 = no match
                                                           (needs DECODE_FRAMES | RESOLVE_ROTATION) */
+    QPSK_B200_OUT_OFFSET_BIN = 10, /* int32 [C]          argmax bin of the last call's 4th-power spectrum (needs ESTIMATE_OFFSET) */
+    QPSK_B200_OUT_OFFSET_HZ = 11   /* float [C]          the same as a carrier offset: signed bin * rs / (4 n) */
 };
 
 const char *qpsk_b200_last_error(void);

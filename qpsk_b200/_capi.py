@@ -22,8 +22,8 @@ class RxConfig(C.Structure):
 
 MODE_EXACT, MODE_FAST = 0, 1
 UB_ALIAS, UB_CLAMP, UB_PHASE = 0, 1, 2
-KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL = 1, 2, 4, 8, 16, 32
-OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK, OUT_ROTATION = range(10)
+KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL, ESTIMATE_OFFSET = 1, 2, 4, 8, 16, 32, 64
+OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK, OUT_ROTATION, OUT_OFFSET_BIN, OUT_OFFSET_HZ = range(12)
 
 _lib = None
 

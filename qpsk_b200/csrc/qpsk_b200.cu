@@ -81,6 +81,11 @@ struct qpsk_b200_rx {
     unsigned* d_frames_t;   // [maxF][W][Cpad] decoded frames (DECODE_FRAMES)
     uint8_t* d_crc_ok_t;    // [maxF][Cpad]
     uint8_t* d_rotation_t;  // [maxF][Cpad] (RESOLVE_ROTATION)
+    bool est_on;            // ESTIMATE_OFFSET: the estimator runs inside every process call
+    float2* d_est_bursts;   // [C][est_call_n] 4th-power bursts
+    int* d_est_bins;        // [C]
+    float* d_est_mag;       // [C]
+    int est_call_n;         // burst length of the last call
     unsigned long long* d_counters;   // [2]
     int16_t* d_pcm_stage2[2];   // host path: double-buffered PCM slices (lazy)
     unsigned* d_out_stage2[2];  // host path: double-buffered transposed dibit slices
@@ -124,7 +129,7 @@ static int rx_free(qpsk_b200_rx* rx) {
     if (rx->est_fft) qpsk_b200_fft_destroy(rx->est_fft);
     void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor2[0], rx->d_phasor2[1], rx->d_ph_state2, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
-                     rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters,
+                     rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, rx->d_est_bursts, rx->d_est_bins, rx->d_est_mag,
                      rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev) if (e) cudaEventDestroy(e);
@@ -221,6 +226,12 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         alloc((void**)&rx->d_crc_ok_t, F * Cp);
         if (cfg->flags & QPSK_B200_RESOLVE_ROTATION) alloc((void**)&rx->d_rotation_t, F * Cp);
         alloc((void**)&rx->d_counters, 2 * sizeof(unsigned long long));
+    }
+    if (cfg->flags & QPSK_B200_ESTIMATE_OFFSET) {
+        rx->est_on = true;
+        alloc((void**)&rx->d_est_bursts, (size_t)nchan * 1024 * sizeof(float2));
+        alloc((void**)&rx->d_est_bins, (size_t)nchan * sizeof(int));
+        alloc((void**)&rx->d_est_mag, (size_t)nchan * sizeof(float));
     }
     if (e != cudaSuccess) {
         rx_free(rx);
@@ -329,6 +340,18 @@ static int rx_begin_call(qpsk_b200_rx* rx, int F, cudaStream_t s) {
     return 0;
 }
 
+__global__ void symbol_power4_kernel(const float2* __restrict__ ring, float2* __restrict__ bursts, int c_begin, int c_end, int Cpad, int nsym,
+                                     int nslots, int first_slot, int n);
+extern "C" int qpsk_b200_fft_create(int n, int device, qpsk_b200_fft** out);
+extern "C" int qpsk_b200_fft_argmax_device(qpsk_b200_fft* f, const float* d_in, int nbursts, int32_t* d_bin, float* d_mag2, void* cuda_stream);
+
+// burst length of the in-call estimator: the largest power of two <= min(1024, symbols of the call)
+static int est_burst_length(const qpsk_b200_rx* rx, int F) {
+    int n = 32;
+    while (2 * n <= 1024 && 2 * n <= F * rx->nsym) n *= 2;
+    return n;
+}
+
 // channels [c0, c0 + nc) of the call; d_pcm holds exactly those rows.  c0 must be a multiple of 32.
 static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, int F, cudaStream_t s, bool timed) {
     const int N = rx->N;
@@ -417,6 +440,24 @@ static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, 
         if (rc) return rc;
         rx->launches += 1;
     }
+    if (rx->est_on) {       // FFT frequency estimator on this slice's channels: 4th power -> n-point FFT -> argmax
+        const int n = est_burst_length(rx, F);
+        if (!rx->est_fft || rx->est_fft_n != n) {
+            if (rx->est_fft) { CU(cudaStreamSynchronize(s)); qpsk_b200_fft_destroy(rx->est_fft); rx->est_fft = nullptr; }
+            int rc = qpsk_b200_fft_create(n, rx->cfg.device, &rx->est_fft);
+            if (rc) return rc;
+            rx->est_fft_n = n;
+        }
+        rx->est_call_n = n;
+        dim3 grid((ca.c1 - c0 + 31) / 32, (n + 31) / 32), block(32, 8);
+        symbol_power4_kernel<<<grid, block, 0, s>>>(rx->d_dec_ring, rx->d_est_bursts, c0, ca.c1, rx->Cpad, rx->nsym, rx->nslots,
+                                                   (rx->slot_base + 1) % rx->nslots, n);
+        CU(cudaGetLastError());
+        int rc = qpsk_b200_fft_argmax_device(rx->est_fft, reinterpret_cast<const float*>(rx->d_est_bursts + (size_t)c0 * n), ca.c1 - c0,
+                                             rx->d_est_bins + c0, rx->d_est_mag + c0, s);
+        if (rc) return rc;
+        rx->launches += 2;
+    }
     rx->launches += 2;
     if (timed) rx->timed = true;
     return 0;
@@ -494,6 +535,8 @@ extern "C" size_t qpsk_b200_rx_output_bytes(const qpsk_b200_rx* rx, int what) {
         case QPSK_B200_OUT_FRAMES: return C * F * (S / 4);
         case QPSK_B200_OUT_CRC_OK: return C * F;
         case QPSK_B200_OUT_ROTATION: return C * F;
+        case QPSK_B200_OUT_OFFSET_BIN: return C * sizeof(int);
+        case QPSK_B200_OUT_OFFSET_HZ: return C * sizeof(float);
         default: return 0;
     }
 }
@@ -543,6 +586,21 @@ extern "C" int qpsk_b200_rx_read(qpsk_b200_rx* rx, int what, void* h_dst, size_t
         case QPSK_B200_OUT_ROTATION:
             if (!rx->d_rotation_t) return fail(QPSK_B200_ERR_STATE, "rotations were not resolved (QPSK_B200_DECODE_FRAMES | QPSK_B200_RESOLVE_ROTATION)");
             return download_transposed<uint8_t>(rx, rx->d_rotation_t, F, h_dst, s);
+        case QPSK_B200_OUT_OFFSET_BIN:
+        case QPSK_B200_OUT_OFFSET_HZ: {
+            if (!rx->est_on) return fail(QPSK_B200_ERR_STATE, "the estimator did not run (QPSK_B200_ESTIMATE_OFFSET)");
+            CU(cudaMemcpy(h_dst, rx->d_est_bins, (size_t)rx->C * sizeof(int), cudaMemcpyDeviceToHost));
+            if (what == QPSK_B200_OUT_OFFSET_HZ) {
+                const int n = rx->est_call_n;
+                int32_t* b = static_cast<int32_t*>(h_dst);
+                float* hz = static_cast<float*>(h_dst);
+                for (int c = 0; c < rx->C; c++) {
+                    const int k = b[c] < n / 2 ? b[c] : b[c] - n;             // signed bin of the 4x tone
+                    hz[c] = (float)((double)k * (double)rx->cfg.rs / (4.0 * (double)n));
+                }
+            }
+            return 0;
+        }
         case QPSK_B200_OUT_SYMBOLS:
             if (!rx->d_costas_dbg) return fail(QPSK_B200_ERR_STATE, "symbols were not kept (QPSK_B200_KEEP_SYMBOLS)");
             return download_transposed<float2>(rx, rx->d_costas_dbg, F * S, h_dst, s);
@@ -1384,11 +1442,11 @@ extern "C" int qpsk_b200_debug_nco(const float* h_in, float* h_sin, float* h_cos
 // from the 4th power of its decimated symbols, through the batched FFT + argmax kernel.  QPSK on the axes
 // raised to the 4th power is a pure tone at 4 x offset.
 // =============================================================================================
-__global__ void symbol_power4_kernel(const float2* __restrict__ ring, float2* __restrict__ bursts, int C, int Cpad, int nsym,
+__global__ void symbol_power4_kernel(const float2* __restrict__ ring, float2* __restrict__ bursts, int c_begin, int C /* end */, int Cpad, int nsym,
                                      int nslots, int first_slot, int n /* burst length */) {
     // bursts[c][k] = ring[frame k / nsym][k % nsym][c] ^ 4 ; 32 x 32 tile transpose (channel-fastest -> channel-major)
     __shared__ float2 tile[32][33];
-    const int c0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int c0 = c_begin + blockIdx.x * 32, k0 = blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int k = k0 + j, c = c0 + threadIdx.x;
         if (k < n && c < C) {
@@ -1426,7 +1484,7 @@ extern "C" int qpsk_b200_rx_estimate_offset(qpsk_b200_rx* rx, int log2n, float* 
     // the frames of the last call sit in ring slots (slot_base_before + 1 + f); use its first n symbols
     const int base_before = ((rx->slot_base - rx->lastF) % rx->nslots + rx->nslots) % rx->nslots;
     dim3 grid((rx->C + 31) / 32, (n + 31) / 32), block(32, 8);
-    symbol_power4_kernel<<<grid, block, 0, rx->stream>>>(rx->d_dec_ring, (float2*)bursts.p, rx->C, rx->Cpad, rx->nsym, rx->nslots,
+    symbol_power4_kernel<<<grid, block, 0, rx->stream>>>(rx->d_dec_ring, (float2*)bursts.p, 0, rx->C, rx->Cpad, rx->nsym, rx->nslots,
                                                         (base_before + 1) % rx->nslots, n);
     CU(cudaGetLastError());
     int rc = qpsk_b200_fft_argmax_device(rx->est_fft, (const float*)bursts.p, rx->C, (int32_t*)bins.p, (float*)mags.p, rx->stream);

@@ -30,3 +30,32 @@ def test_offset_estimate_matches_numpy_and_truth(oracle_lib):
     with pytest.raises(qpsk_b200.QpskB200Error):
         rx.estimate_offset(13)                             # more symbols than the last call produced
     rx.close()
+
+
+def test_estimator_inside_the_process_call(oracle_lib):
+    """QPSK_B200_ESTIMATE_OFFSET: the same estimator as a stage of every process call (device-resident results,
+    sliced with the channels on the host-buffer path); equals the explicit call at the same burst length and does
+    not disturb the receive decisions."""
+    import qpsk_b200
+    from qpsk_b200 import capi
+    from synth import make_pcm
+    o = oracle_lib.Oracle()
+    C, F = 70, 9                                           # 1,152 symbols per call -> bursts of 1,024
+    pcm, dfs = make_pcm(C, F, seed=45, max_df=70.0, esn0_db=25.0, oracle=o)
+    rx = qpsk_b200.Receiver(C, F, estimate_offset=True)
+    got = rx.rx_frames(pcm)
+    bins, hz = rx.read(capi.OUT_OFFSET_BIN), rx.read(capi.OUT_OFFSET_HZ)
+    hz2, bins2 = rx.estimate_offset(10)
+    assert np.array_equal(bins, bins2) and np.array_equal(hz, hz2)
+    assert np.max(np.abs(hz - dfs)) <= 3 * 2400.0 / 4096 + 0.5
+    want = o.rx_run(pcm, want=("dibit",))["dibit"]
+    assert np.array_equal(qpsk_b200.unpack_dibits(got), want)
+    # a second, shorter call re-plans the burst length (2 frames = 256 symbols)
+    rx.rx_frames(pcm[:, :1024])
+    assert rx.read(capi.OUT_OFFSET_BIN).max() < 256
+    rx.close()
+    plain = qpsk_b200.Receiver(4, 2)
+    plain.rx_frames(pcm[:4, :1024])
+    with pytest.raises(qpsk_b200.QpskB200Error):
+        plain.read(capi.OUT_OFFSET_HZ)
+    plain.close()
