@@ -13,6 +13,17 @@
 
 #include "common.cuh"
 
+// points per thread = largest radix: 32 where it saves a pass through shared memory (512 = 32 x 16, 1024 = 32 x 32 inside
+// one warp, 4096 = 32 x 32 x 4, 8192 = 32 x 32 x 8).  2048 stays 16 x 16 x 8: measured 3.6 % faster than 32 x 8 x 8 and 4 %
+// faster than 32 x 32 x 2 (profiles/r01_notes.md).
+__host__ __device__ constexpr int qpsk_fft_points_per_thread(int n) {
+    return (n >= 512 && n != 2048) ? 32 : ((n >= 256) ? 16 : ((n >= 8) ? 8 : n));
+}
+// radix of the stage that still has `rem` points to combine: the largest one, except that 2 P is split evenly
+// (P/4 x P/4 for P = 32) instead of ending in a radix-2 pass
+__host__ __device__ constexpr int qpsk_fft_radix(int rem, int p) {
+    return (p >= 32 && rem == 2 * p) ? p / 4 : (rem >= p ? p : rem);
+}
 #ifndef QPSK_FFT_PREFETCH_MIN_N
 #define QPSK_FFT_PREFETCH_MIN_N 1024
 #endif
@@ -20,15 +31,16 @@
 template <int LOG2N>
 struct FftCfg {
     static constexpr int N = 1 << LOG2N;
-    static constexpr int P = (N >= 256) ? 16 : ((N >= 8) ? 8 : N); // points per thread = largest radix
+    static constexpr int P = qpsk_fft_points_per_thread(N);
     static constexpr int TPF = N / P;                              // threads per transform
     static constexpr int THREADS = (TPF >= 128) ? TPF : 128;
     static constexpr int FPB = THREADS / TPF;                      // transforms per CTA pass
     static constexpr int PTS = FPB * N;
-    static constexpr int SKEW_PTS = PTS + PTS / 16;                // float2 elements, one pad slot per 16: unit-stride and stride-8 accesses are conflict-free
+    static constexpr int SKEW = (P >= 32) ? 32 : 16;               // one pad slot per SKEW points: unit-stride and stride-P accesses are conflict-free
+    static constexpr int SKEW_PTS = PTS + PTS / SKEW;              // float2 elements
     // per-stage twiddle tables: stage (NS, R) holds exp(-2 pi i m k / (NS R)) for m = 1..R-1, k < NS, laid out [m-1][k]
     // so that the lanes of a warp (consecutive k) read consecutive words -- no bank conflicts, no products to form
-    static constexpr int tw_count() { int ns = 1, tot = 0; while (ns < N) { int rem = N / ns; int r = rem >= P ? P : rem; if (ns > 1) tot += (r - 1) * ns; ns *= r; } return tot > 0 ? tot : 1; }
+    static constexpr int tw_count() { int ns = 1, tot = 0; while (ns < N) { int rem = N / ns; int r = qpsk_fft_radix(rem, P); if (ns > 1) tot += (r - 1) * ns; ns *= r; } return tot > 0 ? tot : 1; }
     static constexpr int TW = tw_count();
     // transforms of n >= PREFETCH_MIN_N points are staged: while one pass is being transformed the next pass's input
     // lands in a second buffer through cp.async, so a CTA that fills its SM (512 threads x 128 registers at n = 8192)
@@ -122,7 +134,29 @@ __device__ __forceinline__ void dft_small<16>(c64 (&v)[16]) {
     }
 }
 
-__device__ __forceinline__ int fft_skew(int i) { return i + (i >> 4); }
+template <>
+__device__ __forceinline__ void dft_small<32>(c64 (&v)[32]) {
+    // 32 = 2 x 16, decimation in time: X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k]
+    const float c1 = 0.98078528040323043f, s1 = 0.19509032201612825f, c2 = 0.92387953251128674f, s2 = 0.38268343236508977f,
+                c3 = 0.83146961230254524f, s3 = 0.55557023301960218f, h = 0.70710678118654752f;
+    c64 e[16], o[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
+    dft_small<16>(e);
+    dft_small<16>(o);
+    o[1] = cmul_c(o[1], c1, -s1);    o[2] = cmul_c(o[2], c2, -s2);    o[3] = cmul_c(o[3], c3, -s3);    o[4] = cmul_c(o[4], h, -h);
+    o[5] = cmul_c(o[5], s3, -c3);    o[6] = cmul_c(o[6], s2, -c2);    o[7] = cmul_c(o[7], s1, -c1);    /* o[8] *= -i below */
+    o[9] = cmul_c(o[9], -s1, -c1);   o[10] = cmul_c(o[10], -s2, -c2); o[11] = cmul_c(o[11], -s3, -c3); o[12] = cmul_c(o[12], -h, -h);
+    o[13] = cmul_c(o[13], -c3, -s3); o[14] = cmul_c(o[14], -c2, -s2); o[15] = cmul_c(o[15], -c1, -s1);
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        if (k == 8) { v[k] = cadd_mi(e[k], o[k]); v[k + 16] = cadd_pi(e[k], o[k]); }
+        else { v[k] = cadd(e[k], o[k]); v[k + 16] = csub(e[k], o[k]); }
+    }
+}
+
+template <int SKEW>
+__device__ __forceinline__ int fft_skew(int i) { return i + i / SKEW; }
 
 struct FftArgs {
     const float2* in;      // [nbursts][N]
@@ -150,7 +184,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
             const int idx = jj + r * (N / R);
             if (FIRST && Cfg::PREFETCH) v[r] = cconj_if(reinterpret_cast<const c64*>(gin)[idx], imsgn);   // gin = this transform in the staging buffer (zero-filled when inactive)
             else if (FIRST) v[r] = cconj_if(active ? reinterpret_cast<const c64*>(gin)[idx] : 0ull, imsgn);   // inverse = conj(FFT(conj x))
-            else v[r] = sdat[fft_skew(base + idx)];
+            else v[r] = sdat[fft_skew<Cfg::SKEW>(base + idx)];
         }
         if (NS > 1) {
             const int k = jj % NS;
@@ -169,7 +203,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
             const int o = (jj / NS) * NS * R + (jj % NS);
 #pragma unroll
             for (int q = 0; q < R; q++) {
-                sdat[fft_skew(base + o + q * NS)] = pts[t * R + q];
+                sdat[fft_skew<Cfg::SKEW>(base + o + q * NS)] = pts[t * R + q];
             }
         }
         __syncthreads();
@@ -182,7 +216,7 @@ __device__ __forceinline__ void fft_stages(c64 (&pts)[FftCfg<LOG2N>::P], c64* sd
     constexpr int N = FftCfg<LOG2N>::N;
     constexpr int REM = N / NS;
     constexpr int RMAX = FftCfg<LOG2N>::P;
-    constexpr int R = (REM >= RMAX) ? RMAX : REM;
+    constexpr int R = qpsk_fft_radix(REM, RMAX);
     constexpr bool LAST = (NS * R == N);
     fft_stage<LOG2N, R, NS, FIRST, LAST>(pts, sdat, stw, gin, j, base, active, imsgn);
     if constexpr (!LAST) fft_stages<LOG2N, NS * R, false>(pts, sdat, stw + (NS > 1 ? (R - 1) * NS : 0), gin, j, base, active, imsgn);
@@ -191,7 +225,10 @@ __device__ __forceinline__ void fft_stages(c64 (&pts)[FftCfg<LOG2N>::P], c64* sd
 // output index of pts[i] after the last stage (radix RLAST, sub-transform length NSL = N / RLAST)
 template <int LOG2N>
 struct FftLast {
-    static constexpr int last_ns() { int ns = 1; while ((1 << LOG2N) / ns > FftCfg<LOG2N>::P) ns *= FftCfg<LOG2N>::P; return ns; }
+    static constexpr int last_ns() {
+        int ns = 1;
+        while (true) { const int rem = (1 << LOG2N) / ns, r = qpsk_fft_radix(rem, FftCfg<LOG2N>::P); if (ns * r == (1 << LOG2N)) return ns; ns *= r; }
+    }
     static constexpr int NSL = last_ns();
     static constexpr int RLAST = (1 << LOG2N) / NSL;
 };

@@ -941,16 +941,16 @@ extern "C" int qpsk_b200_fft_create(int n, int device, qpsk_b200_fft** out) {
     cudaDeviceGetAttribute(&f->nsm, cudaDevAttrMultiProcessorCount, device);
     // per-stage twiddles exp(-2 pi i m k / (ns r)), evaluated in double on the host (fft.c:55-56) and rounded once;
     // the stage sequence mirrors FftCfg / fft_stages: radix = min(points per thread, remaining length)
-    const int pmax = n >= 256 ? 16 : (n >= 8 ? 8 : n);
+    const int pmax = qpsk_fft_points_per_thread(n);
     int ntw = 0;
-    for (int ns = 1; ns < n;) { const int rem = n / ns, r = rem >= pmax ? pmax : rem; if (ns > 1) ntw += (r - 1) * ns; ns *= r; }
+    for (int ns = 1; ns < n;) { const int rem = n / ns, r = qpsk_fft_radix(rem, pmax); if (ns > 1) ntw += (r - 1) * ns; ns *= r; }
     if (ntw < 1) ntw = 1;
     float2* tw = new float2[ntw];
     tw[0] = make_float2(1.0f, 0.0f);
     {
         int pos = 0;
         for (int ns = 1; ns < n;) {
-            const int rem = n / ns, r = rem >= pmax ? pmax : rem;
+            const int rem = n / ns, r = qpsk_fft_radix(rem, pmax);
             if (ns > 1) {
                 for (int m = 1; m < r; m++)
                     for (int k = 0; k < ns; k++) {
