@@ -158,6 +158,14 @@ __device__ __forceinline__ void dft_small<32>(c64 (&v)[32]) {
 template <int SKEW>
 __device__ __forceinline__ int fft_skew(int i) { return i + i / SKEW; }
 
+// the threads of one transform exchange data between passes: a warp-level barrier is enough when a transform lives
+// inside one warp (n / points-per-thread <= 32)
+template <int TPF>
+__device__ __forceinline__ void fft_sync() {
+    if (TPF <= 32) __syncwarp();
+    else __syncthreads();
+}
+
 struct FftArgs {
     const float2* in;      // [nbursts][N]
     float2* spectrum;      // optional [nbursts][N]
@@ -196,7 +204,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
         for (int q = 0; q < R; q++) pts[t * R + q] = v[q];
     }
     if (!LAST) {
-        if (!FIRST) __syncthreads();                 // everyone has read this stage's inputs
+        if (!FIRST) fft_sync<TPF>();                 // everyone has read this stage's inputs
 #pragma unroll
         for (int t = 0; t < NB; t++) {
             const int jj = j + t * TPF;
@@ -206,7 +214,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
                 sdat[fft_skew<Cfg::SKEW>(base + o + q * NS)] = pts[t * R + q];
             }
         }
-        __syncthreads();
+        fft_sync<TPF>();
     }
 }
 
@@ -255,16 +263,17 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
     const int fl = threadIdx.x / TPF, j = threadIdx.x % TPF;
     const int base = fl * N;
     c64* stage = reinterpret_cast<c64*>(red_idx + 64);      // [FPB][N], only with Cfg::PREFETCH
-    // one pass = FPB consecutive transforms = PTS contiguous points: P/2 16-byte pieces per thread
+    // the threads of a transform fetch that transform: N/2 16-byte pieces over TPF threads = P/2 pieces each, so the
+    // staging buffer of a transform is only ever touched by its own threads (a warp-level barrier orders it when TPF <= 32)
     auto prefetch = [&](int pass_b0) {
+        const int pb = pass_b0 + fl;
+        const bool in_range = pb < a.nbursts;
+        const float2* src = a.in + (in_range ? (size_t)pb * N : 0);
 #pragma unroll
         for (int i = 0; i < P / 2; i++) {
-            const int piece = threadIdx.x + i * Cfg::THREADS;            // 2 points each
-            const int pb = pass_b0 + (2 * piece) / N;
-            const bool in_range = pb < a.nbursts;
-            const float2* src = a.in + (in_range ? (size_t)pass_b0 * N + 2 * (size_t)piece : 0);
-            const unsigned d = (unsigned)__cvta_generic_to_shared(stage + 2 * piece);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(in_range ? 16 : 0) : "memory");
+            const int piece = j + i * TPF;                                // 2 points each
+            const unsigned d = (unsigned)__cvta_generic_to_shared(stage + base + 2 * piece);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src + (in_range ? 2 * piece : 0)), "r"(in_range ? 16 : 0) : "memory");
         }
     };
     if (Cfg::PREFETCH && blockIdx.x * FPB < a.nbursts) prefetch(blockIdx.x * FPB);
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
         c64 pts[P];
         if constexpr (Cfg::PREFETCH) {
             asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncthreads();                                             // this pass's input has landed for everyone
+            fft_sync<TPF>();                                             // this transform's input has landed for all its threads
             constexpr int R0 = P;                                        // N >= P * P here: the first stage is a full radix-P one
             fft_stage<LOG2N, R0, 1, true, false>(pts, sdat, stw, reinterpret_cast<const float2*>(stage + base), j, base, active, a.im_sign);
             // the stage ended with a barrier after everyone's reads of the staging buffer: refill it
@@ -330,6 +339,6 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
         // the next pass's stage-0 writes must not race with this pass's last-stage reads: the last
         // stage read shared memory before its registers were final, and every thread passed the
         // barrier inside the previous stage's write phase; one more barrier closes the loop
-        __syncthreads();
+        fft_sync<TPF>();
     }
 }
