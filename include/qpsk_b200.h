@@ -65,6 +65,9 @@ enum {                              /* cfg.flags */
                                        the call)) -> batched n-point FFT -> |X|^2 argmax, results in HBM (OUT_OFFSET_BIN/_HZ).
                                        The reference has fftn() but never calls it: an extension output, the
                                        receive decisions do not depend on it */
+    QPSK_B200_ESTIMATE_TIMING = 128,/* extension, not the reference: per frame the symbol-rate line of the squared matched-filter output,
+                                       S = sum_n y_n^2 e^{-2 pi i n / CYCLES} (Oerder & Meyr), accumulated by the timing warps next to the
+                                       reference's amplitude histogram; OUT_TIMING_SUM / OUT_TIMING_TAU.  The decisions do not use it */
     QPSK_B200_RESOLVE_ROTATION = 16 /* with DECODE_FRAMES: a frame whose CRC fails is retried with its dibits turned back
                                        by 90, 180 and 270 degrees (the loop's phase ambiguity); first match wins */
 };
@@ -99,7 +102,9 @@ enum {
     QPSK_B200_OUT_ROTATION = 9, /* uint8  [C][F]         quarter turns undone before the CRC matched, 0..3; 255 = no match
                                                           (needs DECODE_FRAMES | RESOLVE_ROTATION) */
     QPSK_B200_OUT_OFFSET_BIN = 10, /* int32 [C]          argmax bin of the last call's 4th-power spectrum (needs ESTIMATE_OFFSET) */
-    QPSK_B200_OUT_OFFSET_HZ = 11   /* float [C]          the same as a carrier offset: signed bin * rs / (4 n) */
+    QPSK_B200_OUT_OFFSET_HZ = 11,  /* float [C]          the same as a carrier offset: signed bin * rs / (4 n) */
+    QPSK_B200_OUT_TIMING_SUM = 12, /* float [C][F][2]    (Re S, Im S) per frame (needs ESTIMATE_TIMING) */
+    QPSK_B200_OUT_TIMING_TAU = 13  /* float [C][F]       sampling phase of the eye in samples, -arg(S) CYCLES / (2 pi) in [0, CYCLES) */
 };
 
 const char *qpsk_b200_last_error(void);

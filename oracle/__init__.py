@@ -191,6 +191,16 @@ class Oracle:
         ok = self.L.orc_frame_decode(dibits.ctypes.data_as(C.c_void_p), nbytes, frame.ctypes.data_as(C.c_void_p))
         return frame, bool(ok)
 
+    def timing_sum(self, fir_frames):
+        """fir complex64 [..., frame_size] (rx_run's "fir") -> the extension's timing statistic complex64 [...]."""
+        x = np.ascontiguousarray(fir_frames, np.complex64)
+        flat = x.reshape(-1, x.shape[-1])
+        out = np.zeros(flat.shape[0], np.complex64)
+        for i in range(flat.shape[0]):
+            self.L.orc_timing_sum(flat[i].ctypes.data_as(C.c_void_p), flat.shape[1], self.sps,
+                                  out[i:i + 1].ctypes.data_as(C.c_void_p))
+        return out.reshape(x.shape[:-1])
+
     def frame_decode_rotated(self, dibits, nbytes):
         """-> (frame, quarter turns undone 0..3 or -1 when no rotation passes the CRC)."""
         dibits = np.ascontiguousarray(dibits, np.uint8)

@@ -287,6 +287,43 @@ void orc_rx_run(const orc_profile *p, orc_rx_state *states, const int16_t *pcm, 
     }
 }
 
+/* Extension (PARITY UNPINNED, not in the reference): spectral-line timing statistic of one
+ * filtered frame, S = sum_n y_n^2 e^{-2 pi i n / sps} taken per component and added at the end
+ * (Oerder & Meyr's square-law estimator; tau = -arg(S) sps / (2 pi) samples).  Single rounded
+ * float operations in exactly the order of the CUDA timing warps (rx_front.cuh). */
+static void timing_half(const float *y, int stride, int n, int sps, float *re_out, float *im_out) {
+    float re = 0.0f, im = 0.0f;
+    for (int k = 0; k < n; k++) {
+        const float v = y[(size_t)k * stride];
+        const float p = v * v;
+        const int j = k % sps;
+        if (sps == 4) {
+            if (j == 0) re = re + p; else if (j == 1) im = im - p; else if (j == 2) re = re - p; else im = im + p;
+        } else {
+            const float t = p * 0.70710678118654752f;
+            switch (j) {
+                case 0: re = re + p; break;
+                case 1: re = re + t; im = im - t; break;
+                case 2: im = im - p; break;
+                case 3: re = re - t; im = im - t; break;
+                case 4: re = re - p; break;
+                case 5: re = re - t; im = im + t; break;
+                case 6: im = im + p; break;
+                default: re = re + t; im = im + t; break;
+            }
+        }
+    }
+    *re_out = re; *im_out = im;
+}
+
+void orc_timing_sum(const orc_cf *frame, int n, int sps, orc_cf *out) {
+    float ri, ii, rq, iq;
+    timing_half(&frame[0].re, 2, n, sps, &ri, &ii);
+    timing_half(&frame[0].im, 2, n, sps, &rq, &iq);
+    out->re = ri + rq;
+    out->im = ii + iq;
+}
+
 /* ======================================================================================
  * transmit -- qpsk.c:58-63 (constellation), :225-264 (tx_frame), :269-285
  * ==================================================================================== */

@@ -98,6 +98,8 @@ void orc_rx_run(const orc_profile *p, orc_rx_state *states, const int16_t *pcm, 
                 float *phase, float *freq);
 
 void orc_qpsk_demod(const orc_profile *p, orc_cf sym, int bits[2]);
+/* extension, parity unpinned: square-law timing statistic of one filtered frame (see the .c file) */
+void orc_timing_sum(const orc_cf *frame, int n, int sps, orc_cf *out);
 void orc_profile_slice_diagonal(orc_profile *p, int on);
 
 /* ---- transmit: qpsk.c:58-63,225-285 --------------------------------------------------- */

@@ -81,6 +81,7 @@ struct qpsk_b200_rx {
     unsigned* d_frames_t;   // [maxF][W][Cpad] decoded frames (DECODE_FRAMES)
     uint8_t* d_crc_ok_t;    // [maxF][Cpad]
     uint8_t* d_rotation_t;  // [maxF][Cpad] (RESOLVE_ROTATION)
+    float2* d_timing_t;     // [maxF][Cpad] (ESTIMATE_TIMING)
     bool est_on;            // ESTIMATE_OFFSET: the estimator runs inside every process call
     float2* d_est_bursts;   // [C][est_call_n] 4th-power bursts
     int* d_est_bins;        // [C]
@@ -129,7 +130,7 @@ static int rx_free(qpsk_b200_rx* rx) {
     if (rx->est_fft) qpsk_b200_fft_destroy(rx->est_fft);
     void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor2[0], rx->d_phasor2[1], rx->d_ph_state2, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
-                     rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, rx->d_est_bursts, rx->d_est_bins, rx->d_est_mag,
+                     rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, rx->d_est_bursts, rx->d_est_bins, rx->d_est_mag, rx->d_timing_t,
                      rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev) if (e) cudaEventDestroy(e);
@@ -227,6 +228,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         if (cfg->flags & QPSK_B200_RESOLVE_ROTATION) alloc((void**)&rx->d_rotation_t, F * Cp);
         alloc((void**)&rx->d_counters, 2 * sizeof(unsigned long long));
     }
+    if (cfg->flags & QPSK_B200_ESTIMATE_TIMING) alloc((void**)&rx->d_timing_t, F * Cp * sizeof(float2));
     if (cfg->flags & QPSK_B200_ESTIMATE_OFFSET) {
         rx->est_on = true;
         alloc((void**)&rx->d_est_bursts, (size_t)nchan * 1024 * sizeof(float2));
@@ -357,7 +359,7 @@ static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, 
     const int N = rx->N;
     RxFrontArgs fa;
     fa.pcm = d_pcm; fa.pcm_tail = rx->d_pcm_tail; fa.phasor = rx->d_phasor2[rx->ph_cur];
-    fa.dec_ring = rx->d_dec_ring; fa.index_t = rx->d_index_t; fa.fir_dbg = rx->d_fir_dbg;
+    fa.dec_ring = rx->d_dec_ring; fa.index_t = rx->d_index_t; fa.fir_dbg = rx->d_fir_dbg; fa.timing_t = rx->d_timing_t;
     fa.C = rx->C; fa.Cpad = rx->Cpad; fa.F = F; fa.N = N; fa.chan_base = c0; fa.chan_count = nc;
     fa.slot_base = rx->slot_base; fa.nslots = rx->nslots; fa.ub_mode = rx->cfg.ub_mode;
     const int ngroups = (nc + QPSK_GROUP - 1) / QPSK_GROUP;
@@ -535,6 +537,8 @@ extern "C" size_t qpsk_b200_rx_output_bytes(const qpsk_b200_rx* rx, int what) {
         case QPSK_B200_OUT_FRAMES: return C * F * (S / 4);
         case QPSK_B200_OUT_CRC_OK: return C * F;
         case QPSK_B200_OUT_ROTATION: return C * F;
+        case QPSK_B200_OUT_TIMING_SUM: return C * F * sizeof(float2);
+        case QPSK_B200_OUT_TIMING_TAU: return C * F * sizeof(float);
         case QPSK_B200_OUT_OFFSET_BIN: return C * sizeof(int);
         case QPSK_B200_OUT_OFFSET_HZ: return C * sizeof(float);
         default: return 0;
@@ -586,6 +590,25 @@ extern "C" int qpsk_b200_rx_read(qpsk_b200_rx* rx, int what, void* h_dst, size_t
         case QPSK_B200_OUT_ROTATION:
             if (!rx->d_rotation_t) return fail(QPSK_B200_ERR_STATE, "rotations were not resolved (QPSK_B200_DECODE_FRAMES | QPSK_B200_RESOLVE_ROTATION)");
             return download_transposed<uint8_t>(rx, rx->d_rotation_t, F, h_dst, s);
+        case QPSK_B200_OUT_TIMING_SUM:
+        case QPSK_B200_OUT_TIMING_TAU: {
+            if (!rx->d_timing_t) return fail(QPSK_B200_ERR_STATE, "the timing statistic was not accumulated (QPSK_B200_ESTIMATE_TIMING)");
+            if (what == QPSK_B200_OUT_TIMING_SUM) return download_transposed<float2>(rx, rx->d_timing_t, F, h_dst, s);
+            float2* tmp = new (std::nothrow) float2[(size_t)rx->C * F];
+            if (!tmp) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+            int rc = download_transposed<float2>(rx, rx->d_timing_t, F, tmp, s);
+            if (rc == 0) {
+                float* tau = static_cast<float*>(h_dst);
+                const double sps = (double)rx->sps;
+                for (size_t i = 0; i < (size_t)rx->C * F; i++) {
+                    double t = -atan2((double)tmp[i].y, (double)tmp[i].x) * sps / kTau;      // tau = -arg(S) sps / (2 pi)
+                    if (t < 0.0) t += sps;
+                    tau[i] = (float)t;
+                }
+            }
+            delete[] tmp;
+            return rc;
+        }
         case QPSK_B200_OUT_OFFSET_BIN:
         case QPSK_B200_OUT_OFFSET_HZ: {
             if (!rx->est_on) return fail(QPSK_B200_ERR_STATE, "the estimator did not run (QPSK_B200_ESTIMATE_OFFSET)");

@@ -115,6 +115,7 @@ struct RxFrontArgs {
     float2* dec_ring;          // [nslots][nsym][Cpad] decimated symbols, channel-fastest
     int*    index_t;           // [F][Cpad] timing index per frame
     float2* fir_dbg;           // optional [C][F*N] matched-filter output (parity taps), may be null
+    float2* timing_t;          // optional [F][Cpad] spectral-line timing statistic per frame (extension), may be null
     float*  scratch;           // [grid][512][2][32] the current frame's filter output per CTA (L2-resident: rewritten every frame)
     int C, Cpad, F, N;
     int chan_base, chan_count; // this launch covers channels [chan_base, chan_base + chan_count); pcm is indexed from chan_base
@@ -134,6 +135,7 @@ struct RxFrontSmem {
     float2 ph[2][QPSK_CHUNK];     // mixer phasors of the current / next tile
     short pcm[QPSK_GROUP][QPSK_CHUNK + 8];   // cp.async landing zone for the next tile's PCM (row stride 272 B: conflict-free 16 B reads)
     u64 hist[2][QPSK_GROUP];      // 7 x 8-bit amplitude-bin counters for I and for Q
+    float2 tsum[2][QPSK_GROUP];   // per-component halves of the timing statistic (extension)
     int index[QPSK_GROUP];
     volatile int frames_decimated; // frames whose symbols are in the ring (producer: timing warps, consumer: Costas warp)
 };
@@ -160,6 +162,30 @@ __device__ __forceinline__ void mix_store(u64* __restrict__ xrow_cur, const uint
         const float s = __fmul_rn((float)v, 6.103515625e-05f);   // (float)in / 16384.0f, exact
         const float2 p = ph[e];
         xrow_cur[e] = pack2(__fmul_rn(p.x, s), __fmul_rn(p.y, s));
+    }
+}
+
+// one term of the timing statistic: p = y^2 of sample n (n % SPS == j) times e^{-2 pi i j / SPS}, added to (re, im).
+// Every operation is a single rounded float op in this order (the oracle restates it: orc_timing_sum).
+template <int SPS>
+__device__ __forceinline__ void timing_accumulate(const int j, const float p, float& re, float& im) {
+    if (SPS == 4) {
+        if (j == 0) re = __fadd_rn(re, p);
+        else if (j == 1) im = __fsub_rn(im, p);
+        else if (j == 2) re = __fsub_rn(re, p);
+        else im = __fadd_rn(im, p);
+    } else {
+        const float t = __fmul_rn(p, 0.70710678118654752f);
+        switch (j) {
+            case 0: re = __fadd_rn(re, p); break;
+            case 1: re = __fadd_rn(re, t); im = __fsub_rn(im, t); break;
+            case 2: im = __fsub_rn(im, p); break;
+            case 3: re = __fsub_rn(re, t); im = __fsub_rn(im, t); break;
+            case 4: re = __fsub_rn(re, p); break;
+            case 5: re = __fsub_rn(re, t); im = __fadd_rn(im, t); break;
+            case 6: im = __fadd_rn(im, p); break;
+            default: re = __fadd_rn(re, t); im = __fadd_rn(im, t); break;
+        }
     }
 }
 
@@ -288,6 +314,10 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
 #pragma unroll
             for (int kk = 0; kk < 8; kk++) th[kk] = 0.0f;
             u64 hist = 0ull;
+            // extension (ESTIMATE_TIMING): this component's half of S = sum_n y_n^2 e^{-2 pi i n / SPS}, the symbol-rate line
+            // of the squared matched-filter output (Oerder & Meyr); its argument is the sampling phase of the eye
+            const bool est = a.timing_t != nullptr;
+            float sre = 0.0f, sim = 0.0f;
             for (int t = 0; t < tiles_per_frame; t++) {
                 bar_sync(BAR_FULL, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
                 const float* ow = reinterpret_cast<const float*>(&sm.out[lane][0]) + comp;
@@ -299,6 +329,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
                         const float y = gain_exact(ow[2 * ti]);                  // rrc_fir.c:28, this warp's component
                         scr_w[(size_t)(t * QPSK_CHUNK + ti) * (2 * QPSK_GROUP)] = y;   // kept for the decimation
                         av = __fadd_rn(av, fabsf(y));
+                        if (est) timing_accumulate<SPS>(j, __fmul_rn(y, y), sre, sim);
                     }
                     av = __fmul_rn(av, 1.0f / SPS);              // av /= CYCLES, exact for a power of two
                     if (av > mx) {                                 // the bin edges hv*k only move when the running maximum does
@@ -315,6 +346,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
                 if (fr * tiles_per_frame + t + 1 < ntiles) bar_arrive(BAR_EMPTY, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
             }
             sm.hist[comp][lane] = hist;
+            if (est) sm.tsum[comp][lane] = make_float2(sre, sim);
             __threadfence();                                       // both components of the frame are in the scratch
             bar_sync(BAR_AUX, QPSK_AUX_THREADS);
             int index = 0;
@@ -328,6 +360,10 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
                 }
             }
             if (comp == 0 && live) a.index_t[(size_t)f * a.Cpad + ch] = index;
+            if (est && comp == 0 && live) {
+                const float2 ti = sm.tsum[0][lane], tq = sm.tsum[1][lane];
+                a.timing_t[(size_t)f * a.Cpad + ch] = make_float2(__fadd_rn(ti.x, tq.x), __fadd_rn(ti.y, tq.y));
+            }
             const float* scr_r = scr + lane;
             if (a.fir_dbg != nullptr && live) {                    // parity tap: the whole filtered frame
                 float2* dst = a.fir_dbg + (size_t)ch * ((size_t)a.F * N) + (size_t)f * N;

@@ -13,7 +13,7 @@ from . import _capi as capi
 
 class Receiver:
     def __init__(self, nchan, max_frames, rs=2400.0, mode=capi.MODE_EXACT, ub_mode=capi.UB_ALIAS,
-                 keep_fir=False, keep_symbols=False, decode_frames=False, no_fuse=False, resolve_rotation=False, slice_diagonal=False, estimate_offset=False, device=0, loop_bw=None, center=1500.0):
+                 keep_fir=False, keep_symbols=False, decode_frames=False, no_fuse=False, resolve_rotation=False, slice_diagonal=False, estimate_offset=False, estimate_timing=False, device=0, loop_bw=None, center=1500.0):
         self.L = capi.lib()
         cfg = capi.RxConfig()
         self.L.qpsk_b200_rx_default_config(C.byref(cfg))
@@ -24,7 +24,7 @@ class Receiver:
         cfg.flags = ((capi.KEEP_FIR if keep_fir else 0) | (capi.KEEP_SYMBOLS if keep_symbols else 0)
                      | (capi.DECODE_FRAMES if decode_frames else 0) | (capi.NO_FUSE if no_fuse else 0)
                      | (capi.RESOLVE_ROTATION if resolve_rotation else 0) | (capi.SLICE_DIAGONAL if slice_diagonal else 0)
-                     | (capi.ESTIMATE_OFFSET if estimate_offset else 0))
+                     | (capi.ESTIMATE_OFFSET if estimate_offset else 0) | (capi.ESTIMATE_TIMING if estimate_timing else 0))
         cfg.device = device
         if loop_bw is not None:
             cfg.loop_bw = loop_bw
@@ -88,6 +88,8 @@ class Receiver:
             capi.OUT_ROTATION: ((Cn, F), np.uint8),
             capi.OUT_OFFSET_BIN: ((Cn,), np.int32),
             capi.OUT_OFFSET_HZ: ((Cn,), np.float32),
+            capi.OUT_TIMING_SUM: ((Cn, F), np.complex64),
+            capi.OUT_TIMING_TAU: ((Cn, F), np.float32),
         }
         shape, dt = shapes[what]
         out = np.empty(shape, dt)

@@ -59,3 +59,33 @@ def test_estimator_inside_the_process_call(oracle_lib):
     with pytest.raises(qpsk_b200.QpskB200Error):
         plain.read(capi.OUT_OFFSET_HZ)
     plain.close()
+
+
+@pytest.mark.parametrize("rs", [2400.0, 1200.0])
+def test_square_law_timing_statistic(oracle_lib, rs):
+    """QPSK_B200_ESTIMATE_TIMING (extension): S = sum y^2 e^{-2 pi i n / sps} per frame from the timing warps is
+    bit-identical to the oracle's restatement on the oracle's filter output, its phase sits where the two 127-tap
+    filters put the eye (sample 126 mod sps), and switching it on changes no decision."""
+    import qpsk_b200
+    from qpsk_b200 import capi
+    from synth import make_pcm
+    o = oracle_lib.Oracle(rs=rs)
+    C, F = 40, 7
+    pcm, _ = make_pcm(C, F, rs=rs, seed=46, max_df=60.0, esn0_db=25.0, oracle=o)
+    want = o.rx_run(pcm, want=("fir", "dibit", "index"))
+    rx = qpsk_b200.Receiver(C, F, rs=rs, estimate_timing=True)
+    got = rx.rx_frames(pcm)
+    S, tau = rx.read(capi.OUT_TIMING_SUM), rx.read(capi.OUT_TIMING_TAU)
+    assert np.array_equal(qpsk_b200.unpack_dibits(got), want["dibit"]) and np.array_equal(rx.read(capi.OUT_INDEX), want["index"])
+    rx.close()
+    Sw = o.timing_sum(want["fir"].reshape(C, F, 512))
+    assert np.array_equal(S.view(np.uint32), Sw.view(np.uint32))
+    sps = int(9600.0 / rs)
+    eye = 126 % sps
+    err = (tau[:, 1:] - eye + sps / 2) % sps - sps / 2            # circular error, first frame is the filter filling up
+    assert np.max(np.abs(err)) < 0.35, np.max(np.abs(err))
+    plain = qpsk_b200.Receiver(4, 2, rs=rs)
+    plain.rx_frames(pcm[:4, :1024])
+    with pytest.raises(qpsk_b200.QpskB200Error):
+        plain.read(capi.OUT_TIMING_TAU)
+    plain.close()
