@@ -117,7 +117,7 @@ class ClockSampler(threading.Thread):
 def synth_pcm_gpu(torch, qpsk_b200, nchan, nsamp, device, local, seed, rs=2400.0, esn0_db=20.0):
     """Synthetic QPSK PCM [nchan, nsamp] int16, generated on the GPU: random dibits -> the library's own
     batched transmit path (qpsk_packet_mod/tx_frame semantics, packets of 256 symbols) at a per-channel
-    carrier CENTER + U(-75, 75) Hz -> AWGN at Es/N0 = 20 dB added to the PCM (torch, input plumbing)."""
+    carrier CENTER + U(-75, 75) Hz -> the library's counter-based AWGN at Es/N0 = 20 dB (qpsk_b200_channel_awgn_device)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     sps = int(9600.0 / rs)
@@ -130,13 +130,11 @@ def synth_pcm_gpu(torch, qpsk_b200, nchan, nsamp, device, local, seed, rs=2400.0
     torch.cuda.synchronize()
     tx.close()
     del sym
-    step = 4096
-    power = pcm[:step].float().pow(2).mean()
+    power = pcm[:4096].float().pow(2).mean()
     sigma = float((power * sps / (2.0 * 10.0 ** (esn0_db / 10.0))).sqrt())
-    for c0 in range(0, nchan, step):
-        blk = pcm[c0:c0 + step].float()
-        blk += sigma * torch.randn(blk.shape, generator=g, device=device)
-        pcm[c0:c0 + step] = blk.trunc().clamp_(-32768, 32767).to(torch.int16)
+    # the library's counter-based test noise (Philox-keyed Irwin-Hall, reproducible sample for sample by the oracle)
+    qpsk_b200.awgn_device(pcm.data_ptr(), nchan, nsamp, sigma, seed=seed, device=local)
+    torch.cuda.synchronize()
     return pcm
 
 

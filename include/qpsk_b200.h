@@ -230,6 +230,15 @@ int qpsk_b200_tx_reset(qpsk_b200_tx *tx);
  * pcm: int16 [C][nsym*sps].  nsym must be a multiple of 128/sps.  Device pointers, asynchronous. */
 int qpsk_b200_tx_process_device(qpsk_b200_tx *tx, const uint8_t *d_symbols, int nsym, int16_t *d_pcm, void *cuda_stream);
 int qpsk_b200_tx_process_host(qpsk_b200_tx *tx, const uint8_t *h_symbols, int nsym, int16_t *h_pcm);
+/* new carriers from the next call on: fbb_tx_rect = cmplx(TAU * carrier / FS) again (qpsk.c:320), the up-mix phasor keeps
+ * its phase -- a Doppler ramp is a sequence of calls with stepped carriers */
+int qpsk_b200_tx_set_carrier(qpsk_b200_tx *tx, const float *carrier_hz);
+/* Test-channel noise on int16 PCM in HBM, in place: d_pcm int16 [nchan][nsamples], h_sigma float [nchan] (PCM units).
+ * Counter-based (Philox-4x32-10 keyed by seed, counter = sample pair and first_channel + row) Irwin-Hall(4) noise with
+ * no transcendental functions, so the oracle reproduces every sample (csrc/channel.cuh); first_sample (even) is the
+ * stream position of column 0.  Extension: the reference has no channel model. */
+int qpsk_b200_channel_awgn_device(int16_t *d_pcm, int nchan, long long nsamples, const float *h_sigma, unsigned long long seed,
+                                  long long first_sample, int first_channel, int device, void *cuda_stream);
 /* end the current tx_frame call now: renormalise fbb_tx_phase (qpsk.c:253) and restart the packet position */
 int qpsk_b200_tx_end_packet(qpsk_b200_tx *tx);
 /* tx_frame(samples, symbol, length) itself: arbitrary complex symbols, float [C][nsym][2] in host memory */

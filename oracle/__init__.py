@@ -146,6 +146,11 @@ class Oracle:
         self.L.orc_tx_state_init(C.byref(s), carrier_hz, self.fs)
         return s
 
+    def set_tx_carrier(self, tx, carrier_hz):
+        self.L.orc_tx_set_carrier.argtypes = [C.c_void_p, C.c_float, C.c_float]
+        self.L.orc_tx_set_carrier.restype = None
+        self.L.orc_tx_set_carrier(C.byref(tx), carrier_hz, self.fs)
+
     def packet_mod(self, tx, bits):
         """bits: int32 [2*length] (one bit per int, qpsk.c:273) -> int16 [length*sps]."""
         bits = np.ascontiguousarray(bits, np.int32)
@@ -190,6 +195,16 @@ class Oracle:
         frame = np.zeros(nbytes, np.uint8)
         ok = self.L.orc_frame_decode(dibits.ctypes.data_as(C.c_void_p), nbytes, frame.ctypes.data_as(C.c_void_p))
         return frame, bool(ok)
+
+    def awgn(self, pcm, sigma, seed, first_sample=0, first_channel=0):
+        """pcm int16 [C, T] -> noisy copy; the generator's counter-based noise (extension)."""
+        out = np.ascontiguousarray(pcm, np.int16).copy()
+        sg = np.broadcast_to(np.asarray(sigma, np.float32), (out.shape[0],))
+        self.L.orc_awgn.argtypes = [C.c_void_p, C.c_longlong, C.c_float, C.c_uint64, C.c_longlong, C.c_int]
+        self.L.orc_awgn.restype = None
+        for c in range(out.shape[0]):
+            self.L.orc_awgn(out[c].ctypes.data_as(C.c_void_p), out.shape[1], float(sg[c]), int(seed), int(first_sample), first_channel + c)
+        return out
 
     def timing_sum(self, fir_frames):
         """fir complex64 [..., frame_size] (rx_run's "fir") -> the extension's timing statistic complex64 [...]."""

@@ -287,6 +287,35 @@ void orc_rx_run(const orc_profile *p, orc_rx_state *states, const int16_t *pcm, 
     }
 }
 
+/* Extension (not in the reference): the test channel's noise, restated from qpsk_b200/csrc/channel.cuh.
+ * Philox-4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), counter =
+ * (sample >> 1, channel, sample >> 33, 0), key = seed; four 16-bit halves per sample -> Irwin-Hall(4). */
+static void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void orc_awgn(int16_t *pcm, long long nsamples, float sigma, uint64_t seed, long long first_sample, int channel) {
+    for (long long t = 0; t < nsamples; t++) {
+        const uint64_t n = (uint64_t)(first_sample + t);
+        uint32_t w[4];
+        orc_philox((uint32_t)(n >> 1), (uint32_t)channel, (uint32_t)(n >> 33), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+        const uint32_t w0 = w[2 * (n & 1)], w1 = w[2 * (n & 1) + 1];
+        const int s = (int)(w0 & 0xffffu) + (int)(w0 >> 16) + (int)(w1 & 0xffffu) + (int)(w1 >> 16);
+        const float g = (float)(s - 131070) * (1.0f / 37837.0f);
+        float v = (float)pcm[t] + sigma * g;
+        v = truncf(v);
+        if (v < -32768.0f) v = -32768.0f;
+        if (v > 32767.0f) v = 32767.0f;
+        pcm[t] = (int16_t)(int)v;
+    }
+}
+
 /* Extension (PARITY UNPINNED, not in the reference): spectral-line timing statistic of one
  * filtered frame, S = sum_n y_n^2 e^{-2 pi i n / sps} taken per component and added at the end
  * (Oerder & Meyr's square-law estimator; tau = -arg(S) sps / (2 pi) samples).  Single rounded
@@ -331,6 +360,11 @@ void orc_tx_state_init(orc_tx_state *s, float carrier_hz, float fs) {
     memset(s, 0, sizeof *s);
     s->tx_phase = cf_cis(0.0f);                                              /* qpsk.c:316 */
     s->tx_rect = cf_cis((float)(ORC_TAU * (double)carrier_hz / (double)fs)); /* qpsk.c:320 */
+}
+
+/* a new carrier from the next packet on, phase kept: the assignment of qpsk.c:320 again */
+void orc_tx_set_carrier(orc_tx_state *s, float carrier_hz, float fs) {
+    s->tx_rect = cf_cis((float)(ORC_TAU * (double)carrier_hz / (double)fs));
 }
 
 orc_cf orc_qpsk_mod(const int bits[2]) {

@@ -98,6 +98,8 @@ void orc_rx_run(const orc_profile *p, orc_rx_state *states, const int16_t *pcm, 
                 float *phase, float *freq);
 
 void orc_qpsk_demod(const orc_profile *p, orc_cf sym, int bits[2]);
+/* extension: the generator's counter-based test noise, in place on one channel's PCM (csrc/channel.cuh) */
+void orc_awgn(int16_t *pcm, long long nsamples, float sigma, uint64_t seed, long long first_sample, int channel);
 /* extension, parity unpinned: square-law timing statistic of one filtered frame (see the .c file) */
 void orc_timing_sum(const orc_cf *frame, int n, int sps, orc_cf *out);
 void orc_profile_slice_diagonal(orc_profile *p, int on);
@@ -109,6 +111,7 @@ typedef struct {
     orc_cf fir_mem[ORC_MAX_TAPS];   /* tx_filter[] */
 } orc_tx_state;
 void   orc_tx_state_init(orc_tx_state *s, float carrier_hz, float fs);
+void   orc_tx_set_carrier(orc_tx_state *s, float carrier_hz, float fs);   /* qpsk.c:320 again, phase kept */
 orc_cf orc_qpsk_mod(const int bits[2]);
 int    orc_tx_frame(const orc_profile *p, orc_tx_state *s, int16_t *samples, const orc_cf *symbol, int length);
 int    orc_qpsk_packet_mod(const orc_profile *p, orc_tx_state *s, int16_t *samples, const int *tx_bits, int length);

@@ -10,4 +10,4 @@ from .fir import Fir, rrc_make  # noqa: F401
 from .fft import Fft  # noqa: F401
 from . import bits, shard  # noqa: F401
 from .stream import receive_files  # noqa: F401
-from .transmitter import Transmitter, bits_to_symbols  # noqa: F401
+from .transmitter import Transmitter, awgn_device, bits_to_symbols  # noqa: F401

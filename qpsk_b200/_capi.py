@@ -57,6 +57,7 @@ def lib():
     _bind_fft(L)
     _bind_bits(L)
     _bind_tx(L)
+    _bind_channel(L)
     _lib = L
     return L
 
@@ -96,6 +97,12 @@ def _bind_bits(L):
     L.qpsk_b200_frames_decode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     L.qpsk_b200_frames_decode_rotated.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     L.qpsk_b200_rx_crc_counters.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+
+
+def _bind_channel(L):
+    L.qpsk_b200_tx_set_carrier.argtypes = [C.c_void_p, C.c_void_p]
+    L.qpsk_b200_channel_awgn_device.argtypes = [C.c_void_p, C.c_int, C.c_longlong, C.c_void_p, C.c_ulonglong, C.c_longlong, C.c_int,
+                                                C.c_int, C.c_void_p]
 
 
 def _bind_tx(L):

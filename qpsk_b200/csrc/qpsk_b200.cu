@@ -11,6 +11,7 @@
 #include "../host/host_design.h"
 #include "common.cuh"
 #include "rx_front.cuh"
+#include "channel.cuh"
 #include "rx_costas.cuh"
 #include "fir.cuh"
 #include "fft.cuh"
@@ -1270,6 +1271,7 @@ extern "C" int qpsk_b200_frames_decode_rotated(const uint8_t* h_dibits, int nbyt
 struct qpsk_b200_tx {
     long long id;
     int C, Cpad, sps, ntaps, packet_samples, sample_pos, device;
+    float fs;
     float taps[QPSK_MAX_TAPS];
     float2* d_phase;     // [Cpad]
     float2* d_rect;      // [Cpad]
@@ -1319,6 +1321,7 @@ extern "C" int qpsk_b200_tx_create(float fs, float rs, float rrc_alpha, const fl
     tx->id = g_next_id++;
     tx->C = nchan; tx->Cpad = (nchan + 31) / 32 * 32; tx->sps = sps; tx->ntaps = 127; tx->device = device;
     tx->packet_samples = packet_symbols * sps;
+    tx->fs = fs;
     qpsk_host_rrc_make(tx->taps, tx->ntaps, fs, rs, rrc_alpha);                 // qpsk.c:308
     float2* rect = new float2[tx->Cpad];
     for (int i = 0; i < tx->Cpad; i++) {
@@ -1336,6 +1339,45 @@ extern "C" int qpsk_b200_tx_create(float fs, float rs, float rrc_alpha, const fl
     rc = qpsk_b200_tx_reset(tx);
     if (rc) { qpsk_b200_tx_destroy(tx); return rc; }
     *out = tx;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_tx_set_carrier(qpsk_b200_tx* tx, const float* carrier_hz) {
+    if (!tx || !carrier_hz) return fail(QPSK_B200_ERR_ARG, "null argument");
+    CU(cudaSetDevice(tx->device));
+    float2* rect = new (std::nothrow) float2[tx->Cpad];
+    if (!rect) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+    for (int i = 0; i < tx->Cpad; i++) {
+        float t2[2];
+        qpsk_host_cis(kTau * (double)carrier_hz[i < tx->C ? i : tx->C - 1] / (double)tx->fs, 0, t2);   // qpsk.c:320
+        rect[i] = make_float2(t2[0], t2[1]);
+    }
+    cudaError_t e = cudaDeviceSynchronize();                      // earlier calls still read the old table
+    if (e == cudaSuccess) e = cudaMemcpy(tx->d_rect, rect, sizeof(float2) * tx->Cpad, cudaMemcpyHostToDevice);
+    delete[] rect;
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "carrier upload failed: %s", cudaGetErrorString(e));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_channel_awgn_device(int16_t* d_pcm, int nchan, long long nsamples, const float* h_sigma, unsigned long long seed,
+                                             long long first_sample, int first_channel, int device, void* cuda_stream) {
+    if (!d_pcm || !h_sigma) return fail(QPSK_B200_ERR_ARG, "null argument");
+    if (nchan < 1 || nsamples < 1 || first_sample < 0 || (first_sample & 1)) return fail(QPSK_B200_ERR_ARG, "bad argument");
+    if ((unsigned long long)nchan * (unsigned long long)((nsamples + 511) / 512) > 0x7fffffffull) return fail(QPSK_B200_ERR_ARG, "too many samples for one call");
+    int rc = check_device(device);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    DevBuf sg;
+    CU(cudaMalloc(&sg.p, sizeof(float) * nchan));
+    CU(cudaMemcpyAsync(sg.p, h_sigma, sizeof(float) * nchan, cudaMemcpyHostToDevice, s));
+    AwgnArgs a;
+    a.pcm = d_pcm; a.sigma = (const float*)sg.p; a.C = nchan; a.T = nsamples; a.first_sample = first_sample;
+    a.seed_lo = (unsigned)seed; a.seed_hi = (unsigned)(seed >> 32); a.chan_base = first_channel;
+    const long long pairs = (nsamples + 1) / 2;
+    awgn_kernel<<<(unsigned)((pairs + 255) / 256) * (unsigned)nchan, 256, 0, s>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s));                                 // the sigma table is freed on return
     return QPSK_B200_OK;
 }
 

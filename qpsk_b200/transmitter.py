@@ -48,3 +48,17 @@ class Transmitter:
     def modulate_device(self, d_symbols, nsym, d_pcm, stream=None):
         capi.check(self.L.qpsk_b200_tx_process_device(self.h, C.c_void_p(d_symbols), nsym, C.c_void_p(d_pcm),
                                                       C.c_void_p(stream) if stream else None))
+
+
+    def set_carrier(self, carrier_hz):
+        """New per-channel carriers from the next call on (phase-continuous): steps of a Doppler ramp."""
+        c = np.ascontiguousarray(carrier_hz, np.float32)
+        assert c.shape == (self.nchan,)
+        capi.check(self.L.qpsk_b200_tx_set_carrier(self.h, c.ctypes.data_as(C.c_void_p)))
+
+
+def awgn_device(d_pcm, nchan, nsamples, sigma, seed, first_sample=0, first_channel=0, device=0, stream=None):
+    """Counter-based test-channel noise on int16 PCM in HBM, in place (qpsk_b200_channel_awgn_device)."""
+    sg = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, np.float32), (nchan,)))
+    capi.check(capi.lib().qpsk_b200_channel_awgn_device(C.c_void_p(d_pcm), nchan, nsamples, sg.ctypes.data_as(C.c_void_p), int(seed),
+                                                        int(first_sample), int(first_channel), device, C.c_void_p(stream) if stream else None))

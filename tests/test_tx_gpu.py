@@ -67,3 +67,64 @@ def test_tx_rejects_ragged_symbol_counts():
     pcm = np.zeros((1, 33 * 4), np.int16)
     assert capi.lib().qpsk_b200_tx_process_host(tx.h, s.ctypes.data_as(C.c_void_p), 33, pcm.ctypes.data_as(C.c_void_p)) == -1
     tx.close()
+
+
+@pytest.mark.gpu
+def test_channel_noise_is_reproduced_by_the_oracle(oracle_lib):
+    """Generator extension: counter-based AWGN on PCM in HBM equals the oracle's restatement sample for sample
+    (any split of the stream, any shard of the channel set), and has the requested power."""
+    import torch
+    import qpsk_b200
+    o = oracle_lib.Oracle()
+    rng = np.random.default_rng(3)
+    C, T = 37, 4097                                               # odd length: the last pair is half used
+    pcm = rng.integers(-20000, 20000, (C, T), dtype=np.int16)
+    pcm[0, :50] = 32767                                           # saturation on both sides
+    pcm[1, :50] = -32768
+    sigma = rng.uniform(10.0, 3000.0, C).astype(np.float32)
+    d = torch.from_numpy(pcm).cuda()
+    qpsk_b200.awgn_device(d.data_ptr(), C, T, sigma, seed=0x1234567890ABCDEF)
+    got = d.cpu().numpy()
+    want = o.awgn(pcm, sigma, 0x1234567890ABCDEF)
+    assert np.array_equal(got, want)
+    assert np.abs(got[0, :50]).max() == 32767 and got[1, :50].min() == -32768
+    # the same stream generated in two pieces and as the upper shard of a larger channel set
+    d2 = torch.from_numpy(pcm[5:, 1000:]).contiguous().cuda()
+    qpsk_b200.awgn_device(d2.data_ptr(), C - 5, T - 1000, sigma[5:], seed=0x1234567890ABCDEF, first_sample=1000, first_channel=5)
+    assert np.array_equal(d2.cpu().numpy(), want[5:, 1000:])
+    # unit variance of the underlying noise
+    z = torch.zeros((4, 1 << 20), dtype=torch.int16, device="cuda")
+    qpsk_b200.awgn_device(z.data_ptr(), 4, 1 << 20, 1000.0, seed=7)
+    zz = z.cpu().numpy().astype(np.float64)
+    assert np.all(np.abs(zz.std(axis=1) / 1000.0 - 1.0) < 0.01) and np.all(np.abs(zz.mean(axis=1)) < 5.0)
+    assert np.abs(np.corrcoef(zz[0], zz[1])[0, 1]) < 0.01
+
+
+@pytest.mark.gpu
+def test_carrier_steps_are_phase_continuous_and_match_the_oracle(oracle_lib):
+    """set_carrier between packets (a stepped Doppler ramp) = the reference's fbb_tx_rect assignment (qpsk.c:320)
+    with fbb_tx_phase carried over: bit-exact PCM against the oracle driven the same way."""
+    import qpsk_b200
+    o = oracle_lib.Oracle()
+    rng = np.random.default_rng(4)
+    C, npkt = 5, 4
+    f0 = (1500.0 + rng.uniform(-50, 50, C)).astype(np.float32)
+    sym = rng.integers(0, 4, (C, npkt * 256), dtype=np.uint8)
+    tx = qpsk_b200.Transmitter(f0)
+    got = []
+    for k in range(npkt):
+        tx.set_carrier((f0 + 0.5 * k).astype(np.float32))
+        got.append(tx.modulate(sym[:, k * 256:(k + 1) * 256]))
+    tx.close()
+    got = np.concatenate(got, axis=1)
+    for c in range(C):
+        t = o.new_tx(float(f0[c]))
+        parts = []
+        for k in range(npkt):
+            o.set_tx_carrier(t, float(np.float32(f0[c] + np.float32(0.5 * k))))
+            s = sym[c, k * 256:(k + 1) * 256]
+            bits = np.zeros(512, np.int32)
+            bits[0::2] = s >> 1
+            bits[1::2] = s & 1
+            parts.append(o.packet_mod(t, bits))
+        assert np.array_equal(got[c], np.concatenate(parts)), c
