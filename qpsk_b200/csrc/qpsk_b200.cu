@@ -1386,6 +1386,8 @@ static cudaError_t launch_tx(const TxArgs& a, cudaStream_t s) {
     const size_t smem = sizeof(TxSmem<SPS>);
     cudaError_t e = cudaFuncSetAttribute(tx_kernel<127, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(tx_kernel<127, SPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     tx_kernel<127, SPS><<<a.Cpad / QPSK_GROUP, 256, smem, s>>>(a);
     return cudaGetLastError();
 }

@@ -32,7 +32,7 @@ struct TxSmem {
 };
 
 template <int NTAPS, int SPS>
-__global__ void __launch_bounds__(256, 1) tx_kernel(const TxArgs a) {
+__global__ void __launch_bounds__(256, 3) tx_kernel(const TxArgs a) {
     constexpr int R = 16, TS = QPSK_CHUNK / SPS, SPT = TS / 8;   // SPT symbols loaded per thread per tile
     static_assert(TS % 8 == 0 && (NTAPS - 1) <= QPSK_CHUNK, "tile geometry");
     extern __shared__ __align__(16) unsigned char smem_raw[];
