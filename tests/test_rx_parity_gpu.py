@@ -183,20 +183,24 @@ def test_multi_slice_host_path(oracle_lib):
     pcm = np.empty((C, base.shape[1]), np.int16)
     for c in range(C):                     # distinct rows: a base channel rolled by a per-channel amount
         pcm[c] = np.roll(base[pick[c]], shift[c])
-    rx = qpsk_b200.Receiver(C, 3)
+    rx = qpsk_b200.Receiver(C, 3, estimate_offset=True, estimate_timing=True, decode_frames=True, resolve_rotation=True)
     got = qpsk_b200.unpack_dibits(rx.rx_frames(pcm))
     track = rx.read(capi.OUT_TRACK)
     subset = np.unique(np.concatenate([np.arange(0, C, 331), np.arange(18944 - 40, 18944 + 40), [C - 1]]))
     want = o.rx_run(pcm[subset], want=("dibit", "phase", "freq"))
     assert np.array_equal(got[subset], want["dibit"])
     assert np.array_equal(track[subset, :, 0], want["phase"]) and np.array_equal(track[subset, :, 1], want["freq"])
-    # the device-resident entry point over the same data gives the same answer
+    # the device-resident entry point over the same data gives the same answer, per-slice extension stages included
     import torch
-    rx2 = qpsk_b200.Receiver(C, 3)
+    rx2 = qpsk_b200.Receiver(C, 3, estimate_offset=True, estimate_timing=True, decode_frames=True, resolve_rotation=True)
     d = torch.from_numpy(pcm).cuda()
     rx2.process_device(d.data_ptr(), 3)
     rx2.sync()
     assert np.array_equal(qpsk_b200.unpack_dibits(rx2.read(capi.OUT_DIBITS)), got)
+    for what in (capi.OUT_OFFSET_BIN, capi.OUT_TIMING_SUM, capi.OUT_FRAMES, capi.OUT_CRC_OK, capi.OUT_ROTATION, capi.OUT_INDEX):
+        x, y = rx.read(what), rx2.read(what)
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), what
+    assert rx.crc_counters() == rx2.crc_counters() and rx.crc_counters()[0] == C * 3
     rx.close(); rx2.close()
 
 
