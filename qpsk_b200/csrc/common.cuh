@@ -57,6 +57,17 @@ __device__ __forceinline__ float2 cmul_exact(float2 a, float2 b) {
     return make_float2(__fsub_rn(ac, bd), __fadd_rn(ad, bc));
 }
 
+// the same four rounded products and two rounded sums as two packed multiplies and one packed add (3 FP32-pipe slots
+// instead of 6).  The sign flip between them is an integer XOR, and the product that feeds the add directly carries
+// .ftz, so ptxas cannot contract anything into an FFMA2 (see mul2_exact).
+__device__ __forceinline__ float2 cmul_exact_packed(float2 a, float2 b) {
+    const u64 p1 = mul2_exact(pack2(a.x, a.x), pack2(b.x, b.y));             // (ac, ad)
+    const u64 p2 = mul2(pack2(a.y, a.y), pack2(b.y, b.x)) ^ 0x80000000ull;   // (-bd, bc)
+    float2 r;
+    unpack2(add2(p1, p2), r.x, r.y);
+    return r;
+}
+
 // ---- glibc 2.39 sinf/cosf (x86-64 FMA ifunc variant) restated in FP64: reduce by pi/2, then
 // one sine-type and one cosine-type polynomial with every a+b*c fused (sincosf.h: reduce_fast,
 // sinf_poly).  Valid for |y| < 120.  Bit-identical to the host libm the reference links against

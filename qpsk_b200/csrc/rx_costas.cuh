@@ -32,7 +32,7 @@ struct CostasParams {
 __device__ __forceinline__ unsigned costas_symbol(const float2 d, float& phase, float& freq, const CostasParams& p, float2& y) {
     float s, co;
     sincosf_glibc(phase, s, co);                               // cmplxconj(get_phase()), qpsk.h:36
-    y = cmul_exact(d, make_float2(co, -s));                    // qpsk.c:197
+    y = cmul_exact_packed(d, make_float2(co, -s));             // qpsk.c:197
     // costas_loop.c:44-47: sign(I)*Q - sign(Q)*I with 0 -> -1
     const float e = __fsub_rn((y.x > 0.0f ? y.y : -y.y), (y.y > 0.0f ? y.x : -y.x));
     freq = __fadd_rn(freq, __fmul_rn(p.beta, e));              // costas_loop.c:57
@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned costas_symbol(const float2 d, float& phase, 
     }
     if (freq > p.max_freq) freq = p.max_freq;                  // :69-74
     else if (freq < p.min_freq) freq = p.min_freq;
-    const float2 r = cmul_exact(y, p.rot45);                   // qpsk.c:74-79
+    const float2 r = cmul_exact_packed(y, p.rot45);            // qpsk.c:74-79
     return (r.x < 0.0f ? 1u : 0u) | (r.y < 0.0f ? 2u : 0u);
 }
 
