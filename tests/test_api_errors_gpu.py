@@ -114,3 +114,36 @@ def test_last_error_is_per_call_and_readable():
     assert L.qpsk_b200_fft_create(12, 0, C.byref(h)) == ERR_ARG
     msg = L.qpsk_b200_last_error()
     assert b"12" in msg and b"powers of two" in msg
+
+
+def test_contexts_release_their_device_memory():
+    """create/destroy cycles of every context type leave the device's free memory where it was."""
+    import torch
+    import qpsk_b200
+    taps = qpsk_b200.rrc_make(127, 9600.0, 2400.0, 0.35)
+    pcm = np.zeros((64, 4 * 512), np.int16)
+
+    def cycle():
+        rx = qpsk_b200.Receiver(64, 4, decode_frames=True, resolve_rotation=True, estimate_offset=True, estimate_timing=True,
+                                keep_fir=True, keep_symbols=True)
+        rx.rx_frames(pcm)
+        rx.estimate_offset(8)
+        rx.close()
+        f = qpsk_b200.Fir(taps, 64)
+        f.filter(np.zeros((64, 4096), np.complex64))
+        f.close()
+        t = qpsk_b200.Fft(1024)
+        t.argmax(np.zeros((16, 1024), np.complex64))
+        t.close()
+        tx = qpsk_b200.Transmitter(np.full(64, 1500.0, np.float32))
+        tx.modulate(np.zeros((64, 256), np.uint8))
+        tx.close()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(20):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < (8 << 20), (free0, free1)
