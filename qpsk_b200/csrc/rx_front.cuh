@@ -310,9 +310,6 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
         for (int fr = 0; fr < nframes; fr++) {
             const int f = f0 + fr;
             float av = 0.0f, mx = 0.0f;
-            float th[8];                                       // hv * k for the current maximum (all zero while max == 0)
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++) th[kk] = 0.0f;
             u64 hist = 0ull;
             // extension (ESTIMATE_TIMING): this component's half of S = sum_n y_n^2 e^{-2 pi i n / SPS}, the symbol-rate line
             // of the squared matched-filter output (Oerder & Meyr); its argument is the sampling phase of the eye
@@ -332,15 +329,15 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
                         if (est) timing_accumulate<SPS>(j, __fmul_rn(y, y), sre, sim);
                     }
                     av = __fmul_rn(av, 1.0f / SPS);              // av /= CYCLES, exact for a power of two
-                    if (av > mx) {                                 // the bin edges hv*k only move when the running maximum does
-                        mx = av;
-                        const float hv = __fmul_rn(mx, 0.125f);  // max / 8.0f
-#pragma unroll
-                        for (int kk = 1; kk < 8; kk++) th[kk] = __fmul_rn(hv, (float)kk);
-                    }
-                    int bin = 0;                                   // first k in 1..7 with av <= hv*k (hv*k is monotone in k)
-#pragma unroll
-                    for (int kk = 7; kk >= 1; kk--) bin = (av <= th[kk]) ? kk : bin;
+                    mx = fmaxf(mx, av);                            // qpsk.c:140-146 (strict > or >= give the same maximum)
+                    const float hv = __fmul_rn(mx, 0.125f);      // max / 8.0f
+                    // first k in 1..7 with av <= hv*k, 0 if none (qpsk.c:154-166).  The rounded products hv*k are monotone
+                    // in k (hv >= 0), so three compares of a bisection find it; only the three edges looked at are formed.
+                    const bool p4 = av <= __fmul_rn(hv, 4.0f);
+                    const bool p26 = av <= __fmul_rn(hv, p4 ? 2.0f : 6.0f);
+                    const int lo = p4 ? (p26 ? 1 : 3) : (p26 ? 5 : 7);          // the odd edge that decides between lo and lo + 1
+                    const bool p1 = av <= __fmul_rn(hv, (float)lo);
+                    const int bin = (lo + (p1 ? 0 : 1)) & 7;                    // 7 + 1 -> 0: no edge reached
                     hist += 1ull << (8 * bin);                     // byte 0 collects "no bin"; counts <= 128 fit a byte
                 }
                 if (fr * tiles_per_frame + t + 1 < ntiles) bar_arrive(BAR_EMPTY, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
