@@ -372,12 +372,22 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
                 const int slot = (a.slot_base + 1 + f) % a.nslots;
                 float2* dst = a.dec_ring + (size_t)slot * nsym * a.Cpad + ch;
                 const int first = a.ub_mode == QPSK_UB_PHASE ? index % SPS : index;   // extension: a sampling phase, never a slip
-                for (int i = comp; i < NSYM; i += 2) {
-                    int j = i * SPS + first;
-                    float2 v = make_float2(0.0f, 0.0f);            // aliasing read of decimated_frame[j-N]: patched by the Costas stage
-                    if (j >= N && a.ub_mode == QPSK_UB_CLAMP) j = N - 1;
-                    if (j < N) v = make_float2(__ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP)), __ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP) + QPSK_GROUP));
-                    if (live) dst[(size_t)i * a.Cpad] = v;
+                // The scratch reads come from L2 (~650 cycles each) and the filter warps wait on this warp for their next
+                // hand-off, so they are issued in batches of 16 symbols (32 loads in flight) before anything is stored.
+                constexpr int BATCH = 16;
+                static_assert((NSYM / 2) % BATCH == 0, "decimation batches");
+                for (int i0 = comp; i0 < NSYM; i0 += 2 * BATCH) {
+                    float2 v[BATCH];
+#pragma unroll
+                    for (int b = 0; b < BATCH; b++) {
+                        int j = (i0 + 2 * b) * SPS + first;
+                        v[b] = make_float2(0.0f, 0.0f);            // aliasing read of decimated_frame[j-N]: patched by the Costas stage
+                        if (j >= N && a.ub_mode == QPSK_UB_CLAMP) j = N - 1;
+                        if (j < N) v[b] = make_float2(__ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP)), __ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP) + QPSK_GROUP));
+                    }
+#pragma unroll
+                    for (int b = 0; b < BATCH; b++)
+                        if (live) dst[(size_t)(i0 + 2 * b) * a.Cpad] = v[b];
                 }
             }
             if (a.fuse_costas) {
