@@ -344,8 +344,8 @@ def main():
                        "channels_per_gpu": NCHAN, "frames_per_step": NFRAMES, "l2": "inputs (4 GiB PCM per step) exceed L2; no flush needed",
                        "decoded_mbit_s": value / 2.0, "parallelism": "channels sharded over %d GPU(s), no data-path collective" % world},
             "roofline": {"bound": "hbm", "kernel": "rx_front_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": 11.05e9 * (NCHAN * NFRAMES / (65536.0 * 64.0)), "peak_kind": peak_kind, "kernel_ms": k_front,
-                         "note": "kernel is FP32-issue-bound, not HBM-bound (508 flop per 2.06 B): see fp32; traffic = dram read+write of one launch from profiles/r01_rx_front_v5.summary.csv (PCM 4.3 GB in, symbol ring 4.3 GB out, frame scratch spill ~2.4 GB)",
+                         "frac": achieved / hbm_peak, "traffic": 10.86e9 * (NCHAN * NFRAMES / (65536.0 * 64.0)), "peak_kind": peak_kind, "kernel_ms": k_front,
+                         "note": "kernel is FP32-issue-bound, not HBM-bound (508 flop per 2.06 B): see fp32; traffic = dram read+write of one launch from profiles/r01_rx_front_v6.summary.csv (PCM 4.3 GB in, symbol ring 4.3 GB out, frame scratch spill ~2.4 GB)",
                          "fp32": {"achieved_tap_updates_per_s": fp_ach, "peak_tap_updates_per_s": fp_peak, "frac": fp_ach / fp_peak,
                                   "peak_kind": "2 packed FP32 instr per tap at 64 lanes/clk/SM x 148 SM x sampled SM clock"}},
             "kernels_ms": {"rx_front": k_front, "costas": k_costas},
