@@ -303,9 +303,12 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
         // warp 8 = I, warp 9 = Q, lane = channel: amplitude histograms of qpsk.c:131-167, one tile behind the filter
         const int comp = w - 8;
         const int nsym = N / SPS;
-        // this CTA's frame scratch: [sample][component][lane] floats, 128-byte rows per (sample, component)
+        // this CTA's frame scratch: [symbol][component][lane][SPS] floats, so that a symbol's SPS samples of one lane are one
+        // (or two) 128-bit stores and a warp writes whole 512-byte runs
         float* scr = a.scratch + (size_t)blockIdx.x * (512 * 2 * QPSK_GROUP);
-        float* scr_w = scr + comp * QPSK_GROUP + lane;
+        auto scr_at = [&](int n, int c) -> const float* {         // sample n of the frame, component c, this lane
+            return scr + ((size_t)((n / SPS) * 2 + c) * QPSK_GROUP + lane) * SPS + (n % SPS);
+        };
         const int ntiles = nframes * tiles_per_frame;
         for (int fr = 0; fr < nframes; fr++) {
             const int f = f0 + fr;
@@ -320,13 +323,19 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
                 const float* ow = reinterpret_cast<const float*>(&sm.out[lane][0]) + comp;
 #pragma unroll 2
                 for (int s = 0; s < TILE_SYMS; s++) {
+                    float ys[SPS];
 #pragma unroll
                     for (int j = 0; j < SPS; j++) {
                         const int ti = s * SPS + j;
                         const float y = gain_exact(ow[2 * ti]);                  // rrc_fir.c:28, this warp's component
-                        scr_w[(size_t)(t * QPSK_CHUNK + ti) * (2 * QPSK_GROUP)] = y;   // kept for the decimation
+                        ys[j] = y;
                         av = __fadd_rn(av, fabsf(y));
                         if (est) timing_accumulate<SPS>(j, __fmul_rn(y, y), sre, sim);
+                    }
+                    {                                                          // kept for the decimation
+                        float4* dst = reinterpret_cast<float4*>(scr + ((size_t)((t * TILE_SYMS + s) * 2 + comp) * QPSK_GROUP + lane) * SPS);
+#pragma unroll
+                        for (int q = 0; q < SPS / 4; q++) dst[q] = make_float4(ys[4 * q], ys[4 * q + 1], ys[4 * q + 2], ys[4 * q + 3]);
                     }
                     av = __fmul_rn(av, 1.0f / SPS);              // av /= CYCLES, exact for a power of two
                     mx = fmaxf(mx, av);                            // qpsk.c:140-146 (strict > or >= give the same maximum)
@@ -361,11 +370,9 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
                 const float2 ti = sm.tsum[0][lane], tq = sm.tsum[1][lane];
                 a.timing_t[(size_t)f * a.Cpad + ch] = make_float2(__fadd_rn(ti.x, tq.x), __fadd_rn(ti.y, tq.y));
             }
-            const float* scr_r = scr + lane;
             if (a.fir_dbg != nullptr && live) {                    // parity tap: the whole filtered frame
                 float2* dst = a.fir_dbg + (size_t)ch * ((size_t)a.F * N) + (size_t)f * N;
-                for (int i = comp; i < N; i += 2)
-                    dst[i] = make_float2(__ldcg(scr_r + (size_t)i * (2 * QPSK_GROUP)), __ldcg(scr_r + (size_t)i * (2 * QPSK_GROUP) + QPSK_GROUP));
+                for (int i = comp; i < N; i += 2) dst[i] = make_float2(__ldcg(scr_at(i, 0)), __ldcg(scr_at(i, 1)));
             }
             // decimate, qpsk.c:186-191: symbol i = sample i*SPS + index, stored channel-fastest
             {
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
                         int j = (i0 + 2 * b) * SPS + first;
                         v[b] = make_float2(0.0f, 0.0f);            // aliasing read of decimated_frame[j-N]: patched by the Costas stage
                         if (j >= N && a.ub_mode == QPSK_UB_CLAMP) j = N - 1;
-                        if (j < N) v[b] = make_float2(__ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP)), __ldcg(scr_r + (size_t)j * (2 * QPSK_GROUP) + QPSK_GROUP));
+                        if (j < N) v[b] = make_float2(__ldcg(scr_at(j, 0)), __ldcg(scr_at(j, 1)));
                     }
 #pragma unroll
                     for (int b = 0; b < BATCH; b++)
