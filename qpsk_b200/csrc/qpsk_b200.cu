@@ -742,6 +742,10 @@ struct qpsk_b200_fir {
     float2* d_state;      // [C][ntaps]
     float2* d_stage;      // host-path staging (lazy)
     size_t stage_elems;
+    float2* d_stage2[2];  // sliced host path: two slices in flight (lazy)
+    size_t stage2_elems;
+    cudaStream_t s_in, s_out;
+    cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
     float2* d_halo;       // inputs in front of time blocks 1.. (lazy), see fir_save_halo_kernel
     size_t halo_elems;
     int sm_count;
@@ -761,6 +765,14 @@ extern "C" int qpsk_b200_fir_destroy(qpsk_b200_fir* f) {
     cudaSetDevice(f->device);
     if (f->d_state) cudaFree(f->d_state);
     if (f->d_stage) cudaFree(f->d_stage);
+    for (auto& p : f->d_stage2) if (p) cudaFree(p);
+    if (f->s_in) cudaStreamDestroy(f->s_in);
+    if (f->s_out) cudaStreamDestroy(f->s_out);
+    for (int b = 0; b < 2; b++) {
+        if (f->ev_in[b]) cudaEventDestroy(f->ev_in[b]);
+        if (f->ev_k[b]) cudaEventDestroy(f->ev_k[b]);
+        if (f->ev_out[b]) cudaEventDestroy(f->ev_out[b]);
+    }
     if (f->d_halo) cudaFree(f->d_halo);
     for (auto& e : f->ev) if (e) cudaEventDestroy(e);
     if (f->stream) cudaStreamDestroy(f->stream);
@@ -858,11 +870,17 @@ static cudaError_t launch_fir(qpsk_b200_fir* f, FirArgs a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// channels [c0, c0 + nc) of the filter bank over d_samples (exactly those rows), on stream s
+static int fir_run(qpsk_b200_fir* f, float* d_samples, int c0, int nc, int nsamples, cudaStream_t s, bool timed);
+
 extern "C" int qpsk_b200_fir_process_device(qpsk_b200_fir* f, float* d_samples, int nsamples, void* cuda_stream) {
     if (!f || !d_samples) return fail(QPSK_B200_ERR_ARG, "null argument");
     if (nsamples < 1) return fail(QPSK_B200_ERR_ARG, "nsamples must be positive");
     CU(cudaSetDevice(f->device));
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : f->stream;
+    return fir_run(f, d_samples, 0, f->C, nsamples, cuda_stream ? (cudaStream_t)cuda_stream : f->stream, true);
+}
+
+static int fir_run(qpsk_b200_fir* f, float* d_samples, int c0, int nc, int nsamples, cudaStream_t s, bool timed) {
     if (g_taps_owner != f->id) {
         float2 t2[QPSK_MAX_TAPS];
         for (int i = 0; i < f->ntaps; i++) t2[i] = make_float2(f->taps[i], f->taps[i]);
@@ -871,15 +889,14 @@ extern "C" int qpsk_b200_fir_process_device(qpsk_b200_fir* f, float* d_samples, 
         g_taps_owner = f->id;
     }
     FirArgs a;
-    a.data = reinterpret_cast<float2*>(d_samples); a.state = f->d_state; a.C = f->C; a.T = nsamples;
-    CU(cudaEventRecord(f->ev[0], s));
+    a.data = reinterpret_cast<float2*>(d_samples); a.state = f->d_state + (size_t)c0 * f->ntaps; a.C = nc; a.T = nsamples;
+    if (timed) CU(cudaEventRecord(f->ev[0], s));
     cudaError_t e;
     const bool fast = f->mode == QPSK_B200_MODE_FAST;
     if (f->ntaps == 127) e = fast ? launch_fir<127, QPSK_MODE_FAST>(f, a, s) : launch_fir<127, QPSK_MODE_EXACT>(f, a, s);
     else                 e = fast ? launch_fir<256, QPSK_MODE_FAST>(f, a, s) : launch_fir<256, QPSK_MODE_EXACT>(f, a, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "FIR kernel launch failed: %s", cudaGetErrorString(e));
-    CU(cudaEventRecord(f->ev[1], s));
-    f->timed = true;
+    if (timed) { CU(cudaEventRecord(f->ev[1], s)); f->timed = true; }
     return QPSK_B200_OK;
 }
 
@@ -887,6 +904,48 @@ extern "C" int qpsk_b200_fir_process_host(qpsk_b200_fir* f, float* h_samples, in
     if (!f || !h_samples) return fail(QPSK_B200_ERR_ARG, "null argument");
     if (nsamples < 1) return fail(QPSK_B200_ERR_ARG, "nsamples must be positive");
     CU(cudaSetDevice(f->device));
+    // Large banks go through in channel slices over three streams (copy in / filter / copy out, two slices in flight), like
+    // the receiver's host path: with page-locked buffers the two PCIe directions and the kernel overlap.
+    const size_t slice_target = (size_t)32 << 20;                       // complex samples per slice (256 MiB)
+    if ((size_t)f->C * nsamples > 2 * slice_target && f->C >= 64) {
+        int nc_slice = (int)(slice_target / (size_t)nsamples) / 32 * 32;
+        if (nc_slice < 32) nc_slice = 32;
+        const size_t se = (size_t)nc_slice * nsamples;
+        if (!f->s_in) {
+            CU(cudaStreamCreateWithFlags(&f->s_in, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; b++) {
+                CU(cudaEventCreateWithFlags(&f->ev_in[b], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&f->ev_k[b], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&f->ev_out[b], cudaEventDisableTiming));
+            }
+        }
+        if (f->stage2_elems < se) {
+            for (auto& p : f->d_stage2) if (p) { cudaFree(p); p = nullptr; }
+            f->stage2_elems = 0;
+            for (auto& p : f->d_stage2) CU(cudaMalloc((void**)&p, se * sizeof(float2)));
+            f->stage2_elems = se;
+        }
+        float2* h = reinterpret_cast<float2*>(h_samples);
+        int i = 0;
+        for (int c0 = 0; c0 < f->C; c0 += nc_slice, i++) {
+            const int b = i & 1, nc = (f->C - c0 < nc_slice) ? f->C - c0 : nc_slice;
+            const size_t bytes = (size_t)nc * nsamples * sizeof(float2);
+            if (i >= 2) CU(cudaStreamWaitEvent(f->s_in, f->ev_out[b], 0));          // buffer b has been copied out
+            CU(cudaMemcpyAsync(f->d_stage2[b], h + (size_t)c0 * nsamples, bytes, cudaMemcpyHostToDevice, f->s_in));
+            CU(cudaEventRecord(f->ev_in[b], f->s_in));
+            CU(cudaStreamWaitEvent(f->stream, f->ev_in[b], 0));
+            int rc = fir_run(f, reinterpret_cast<float*>(f->d_stage2[b]), c0, nc, nsamples, f->stream, false);
+            if (rc) return rc;
+            CU(cudaEventRecord(f->ev_k[b], f->stream));
+            CU(cudaStreamWaitEvent(f->s_out, f->ev_k[b], 0));
+            CU(cudaMemcpyAsync(h + (size_t)c0 * nsamples, f->d_stage2[b], bytes, cudaMemcpyDeviceToHost, f->s_out));
+            CU(cudaEventRecord(f->ev_out[b], f->s_out));
+        }
+        CU(cudaStreamSynchronize(f->s_out));
+        CU(cudaStreamSynchronize(f->stream));
+        return QPSK_B200_OK;
+    }
     const size_t elems = (size_t)f->C * nsamples;
     if (f->stage_elems < elems) {
         if (f->d_stage) { cudaFree(f->d_stage); f->d_stage = nullptr; f->stage_elems = 0; }

@@ -88,3 +88,37 @@ def test_fir_fast_mode_tolerance(oracle_lib):
     err = np.max(np.abs(got - want), axis=1) / np.max(np.abs(want), axis=1)
     assert err.max() <= 1e-5
     f.close()
+
+
+@pytest.mark.gpu
+def test_large_host_call_is_sliced_and_equals_the_device_path(oracle_lib):
+    """A bank above 2 x 32 M complex samples goes through the host entry point in channel slices over three streams;
+    the bytes must equal the unsliced device path, a strided subset the oracle, and the delay lines must carry on."""
+    import torch
+    import qpsk_b200
+    o = oracle_lib.Oracle()
+    taps = qpsk_b200.rrc_make(127, 9600.0, 2400.0, 0.35)
+    C, T = 2100, 32768                                           # 68.8 M samples: three slices of 1,024 / 1,024 / 52 channels
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal((C, T), dtype=np.float32) + 1j * rng.standard_normal((C, T), dtype=np.float32)).astype(np.complex64)
+    f = qpsk_b200.Fir(taps, C)
+    got = f.filter(x.copy())
+    mem = f.memory
+    g = qpsk_b200.Fir(taps, C)
+    d = torch.from_numpy(x.view(np.float32).reshape(C, T, 2)).cuda()
+    g.filter_device(d.data_ptr(), T)
+    torch.cuda.synchronize()
+    want = d.cpu().numpy().reshape(C, T * 2).view(np.complex64)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(mem.view(np.uint32), g.memory.view(np.uint32))
+    for c in (0, 1023, 1024, 2047, 2048, 2099):
+        ref = x[c].copy()
+        o.fir(taps, np.zeros(127, np.complex64), ref)
+        assert np.array_equal(got[c].view(np.uint32), ref.view(np.uint32)), c
+    # a second (short, unsliced) call continues from the carried delay lines
+    y = x[:, :300].copy()
+    got2 = f.filter(y.copy())
+    ref = np.concatenate([x[7], y[7]])
+    o.fir(taps, np.zeros(127, np.complex64), ref)
+    assert np.array_equal(got2[7].view(np.uint32), ref[T:].view(np.uint32))
+    f.close(); g.close()
