@@ -102,7 +102,12 @@ __global__ void scramble_rows_kernel(uint8_t* __restrict__ dibits, const uint8_t
 // 16 dibits per word, LSB first) -> de-scrambled, de-interleaved frame words [F][W][Cpad],
 // CRC verdict [F][Cpad] and pass/fail counters.
 // ---------------------------------------------------------------------------------------------
-__constant__ unsigned c_keystream_words[16];    // scrambler keystream of one frame, packed like the dibits
+// The scrambler keystream of one frame (packed like the dibits) travels in the kernel arguments: it is data
+// independent, 64 bytes at most, and per launch -- nothing process-wide to upload per device or to order
+// against kernels in flight.
+struct Keystream {
+    unsigned w[8];
+};
 
 struct FrameDecodeArgs {
     const unsigned* dibits_t;   // [F][W][Cpad]
@@ -112,6 +117,7 @@ struct FrameDecodeArgs {
     unsigned long long* counters;   // [0] frames examined, [1] CRC passes
     int C, Cpad, F;
     int c0;                     // first channel of this launch; C is its end
+    Keystream ks;
 };
 
 template <int NBYTES, int DIR>
@@ -154,7 +160,7 @@ __global__ void __launch_bounds__(128) frame_decode_kernel(const FrameDecodeArgs
 #pragma unroll 1
         for (; rot < nrot; rot++) {
 #pragma unroll
-            for (int w = 0; w < W; w++) in[w] = raw[w] ^ c_keystream_words[w];
+            for (int w = 0; w < W; w++) in[w] = raw[w] ^ a.ks.w[w];
             permute_frame<NBYTES, 1>(in, out);
             uint16_t crc = 0xFFFF;
 #pragma unroll
@@ -190,6 +196,7 @@ struct FrameEncodeArgs {
     const unsigned* payload_t;
     unsigned* dibits_t;
     int C, Cpad, F;
+    Keystream ks;
 };
 
 template <int NBYTES>
@@ -208,5 +215,5 @@ __global__ void __launch_bounds__(128) frame_encode_kernel(const FrameEncodeArgs
     in[W - 1] = (in[W - 1] & 0x0000ffffu) | ((unsigned)(crc >> 8) << 16) | ((unsigned)(crc & 0xff) << 24);
     permute_frame<NBYTES, 0>(in, out);
 #pragma unroll
-    for (int w = 0; w < W; w++) a.dibits_t[((size_t)f * W + w) * a.Cpad + c] = out[w] ^ c_keystream_words[w];
+    for (int w = 0; w < W; w++) a.dibits_t[((size_t)f * W + w) * a.Cpad + c] = out[w] ^ a.ks.w[w];
 }

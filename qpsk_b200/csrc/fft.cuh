@@ -5,17 +5,28 @@
 // FP32 (north_star tolerance 1e-5), and adds the estimator the reference never wrote: the first
 // strict maximum of |X[k]|^2 (mirroring the argmax idiom of qpsk.c:173-180).
 //
-// Stockham autosort, radix-16 stages for n >= 256 (radix 8 below; the remainder stage is radix 8, 4 or 2),
-// 16 points per thread in registers: n = 256 crosses shared memory once, 4096 twice.  Stage 0 reads the burst straight from HBM (coalesced), the last stage leaves its
-// outputs in registers for the magnitude/argmax reduction (warp shuffles, then one shared-memory
-// hop across warps), so shared memory is crossed stages-1 times and HBM exactly once.
+// Stockham autosort, 16 or 32 points per thread in registers (radix-16 / radix-32 stages, the
+// remainder stage is radix 16, 8, 4 or 2): n = 256 crosses shared memory once, 4096 and 8192 twice.
+// Stage 0 reads the burst straight from HBM (coalesced), the last stage leaves its outputs in
+// registers for the magnitude/argmax reduction (warp shuffles, then one shared-memory hop across
+// warps), so HBM is crossed exactly once.
+//
+// The kernel is issue-bound (profiles/r01_notes.md: ~68 instructions per point in round 1, of which
+// 19 are the packed butterflies), so round 2 is about the other 49:
+//   * every shared-memory access is `per-thread base + compile-time offset`: the skew (one pad slot per
+//     SKEW points) is linear in the unrolled indices, see fft_off();
+//   * the estimator entry point (forward, argmax only) is its own instantiation: no conjugation, no
+//     scaling, no spectrum store, |X|^2 as one FMUL2 + one FADD per point, the maximum as an FMNMX tree
+//     and the bin recovered only by the thread(s) that hold the maximum;
+//   * the twiddles of a remainder stage are factored, w^(m (j + t TPF)) = w^(m j) W_P^(m t) with the second
+//     factor a compile-time constant, which shrinks the largest table from ~n to ~n/P entries: 8192 points
+//     fit two CTAs per SM and 4096 four, without the staging buffer of round 1.
 #pragma once
 
 #include "common.cuh"
 
 // points per thread = largest radix: 32 where it saves a pass through shared memory (512 = 32 x 16, 1024 = 32 x 32 inside
-// one warp, 4096 = 32 x 32 x 4, 8192 = 32 x 32 x 8).  2048 stays 16 x 16 x 8: measured 3.6 % faster than 32 x 8 x 8 and 4 %
-// faster than 32 x 32 x 2 (profiles/r01_notes.md).
+// one warp, 4096 = 32 x 32 x 4, 8192 = 32 x 32 x 8).  2048 stays 16 x 16 x 8 (fewer registers, more resident warps).
 __host__ __device__ constexpr int qpsk_fft_points_per_thread(int n) {
     return (n >= 512 && n != 2048) ? 32 : ((n >= 256) ? 16 : ((n >= 8) ? 8 : n));
 }
@@ -24,9 +35,52 @@ __host__ __device__ constexpr int qpsk_fft_points_per_thread(int n) {
 __host__ __device__ constexpr int qpsk_fft_radix(int rem, int p) {
     return (p >= 32 && rem == 2 * p) ? p / 4 : (rem >= p ? p : rem);
 }
-#ifndef QPSK_FFT_PREFETCH_MIN_N
-#define QPSK_FFT_PREFETCH_MIN_N 1024
+// entries per twiddle index m of the stage (ns, r) of an n-point transform with tpf threads: a remainder stage whose
+// sub-transform length exceeds the thread count keeps only the first tpf columns (the rest are constant multiples)
+__host__ __device__ constexpr int qpsk_fft_tw_cols(int ns, int tpf) { return ns < tpf ? ns : tpf; }
+__host__ __device__ constexpr int qpsk_fft_tw_count(int n) {
+    const int p = qpsk_fft_points_per_thread(n), tpf = n / p;
+    int ns = 1, tot = 0;
+    while (ns < n) {
+        const int r = qpsk_fft_radix(n / ns, p);
+        if (ns > 1) tot += (r - 1) * qpsk_fft_tw_cols(ns, tpf);
+        ns *= r;
+    }
+    return tot > 0 ? tot : 1;
+}
+
+// Per-stage twiddles exp(-2 pi i m k / (ns r)), m = 1..r-1, k < qpsk_fft_tw_cols(ns, tpf), laid out [m-1][k] so that
+// the lanes of a warp (consecutive k) read consecutive words; evaluated in double on the host (fft.c:55-56) and
+// rounded once.  `tw` holds qpsk_fft_tw_count(n) entries.
+inline void qpsk_fft_make_twiddles(int n, float2* tw) {
+    const int p = qpsk_fft_points_per_thread(n), tpf = n / p;
+    tw[0] = make_float2(1.0f, 0.0f);
+    int pos = 0;
+    for (int ns = 1; ns < n;) {
+        const int r = qpsk_fft_radix(n / ns, p);
+        if (ns > 1) {
+            const int cols = qpsk_fft_tw_cols(ns, tpf);
+            for (int m = 1; m < r; m++)
+                for (int k = 0; k < cols; k++) {
+                    const double ang = 2.0 * 3.14159265358979323846 * (double)m * (double)k / ((double)ns * (double)r);
+                    tw[pos++] = make_float2((float)cos(ang), (float)(-sin(ang)));
+                }
+        }
+        ns *= r;
+    }
+}
+
+// resident CTAs per SM the register allocation of each kernel family is capped for (tools/fft_bench.cu sweeps them)
+#ifndef QPSK_FFT_MINB_8192
+#define QPSK_FFT_MINB_8192 2
 #endif
+#ifndef QPSK_FFT_MINB_P32
+#define QPSK_FFT_MINB_P32 4
+#endif
+#ifndef QPSK_FFT_MINB_P16
+#define QPSK_FFT_MINB_P16 6
+#endif
+#define QPSK_FFT_MINB(n, p) ((n) >= 8192 ? QPSK_FFT_MINB_8192 : ((p) >= 32 ? QPSK_FFT_MINB_P32 : ((n) >= 256 ? QPSK_FFT_MINB_P16 : 4)))
 
 template <int LOG2N>
 struct FftCfg {
@@ -38,22 +92,16 @@ struct FftCfg {
     static constexpr int PTS = FPB * N;
     static constexpr int SKEW = (P >= 32) ? 32 : 16;               // one pad slot per SKEW points: unit-stride and stride-P accesses are conflict-free
     static constexpr int SKEW_PTS = PTS + PTS / SKEW;              // float2 elements
-    // per-stage twiddle tables: stage (NS, R) holds exp(-2 pi i m k / (NS R)) for m = 1..R-1, k < NS, laid out [m-1][k]
-    // so that the lanes of a warp (consecutive k) read consecutive words -- no bank conflicts, no products to form
-    static constexpr int tw_count() { int ns = 1, tot = 0; while (ns < N) { int rem = N / ns; int r = qpsk_fft_radix(rem, P); if (ns > 1) tot += (r - 1) * ns; ns *= r; } return tot > 0 ? tot : 1; }
-    static constexpr int TW = tw_count();
-    // transforms of n >= PREFETCH_MIN_N points are staged: while one pass is being transformed the next pass's input
-    // lands in a second buffer through cp.async, so a CTA that fills its SM (512 threads x 128 registers at n = 8192)
-    // no longer idles through every load
-    static constexpr bool PREFETCH = (N >= QPSK_FFT_PREFETCH_MIN_N);
-    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + sizeof(float2) * TW + sizeof(float) * 64 + sizeof(int) * 64
-                                 + (PREFETCH ? sizeof(float2) * PTS : 0);
+    static constexpr int TW = qpsk_fft_tw_count(N);
+    static constexpr bool LIN = (N >= 256);                        // linear skew offsets (static_asserted per stage)
+    // resident CTAs per SM the register allocation is capped for
+    static constexpr int MINB = QPSK_FFT_MINB(N, P);
+    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + sizeof(float2) * TW + sizeof(float) * 64 + sizeof(int) * 64;
 };
 
-// Tolerance-mode arithmetic (1e-5) on packed FP32 pairs: one complex value per 64-bit register.  FADD2 takes
-// per-operand swizzle/negate modifiers, so a +-i rotation folded into an add costs nothing, and a complex
-// multiply is FMUL2 + FFMA2 (scalar-broadcast and swapped operands are modifiers too) -- half the issue slots
-// of the scalar form, which is what this kernel is short of (profiles/r01_notes.md).
+// Tolerance-mode arithmetic (1e-5) on packed FP32 pairs: one complex value per 64-bit register.  FADD2/FMUL2/FFMA2 take
+// per-operand swap / negate / scalar-broadcast modifiers, so a +-i rotation folded into an add costs nothing and a
+// complex multiply is exactly FMUL2 + FFMA2 (checked in SASS: no MOVs).
 typedef u64 c64;
 __device__ __forceinline__ c64 cadd(c64 a, c64 b) { return add2(a, b); }
 __device__ __forceinline__ c64 csub(c64 a, c64 b) { c64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -68,21 +116,82 @@ __device__ __forceinline__ c64 cmul(c64 a, c64 w) {          // (ax wx - ay wy, 
     return fma2(pack2(ax, ax), w, pack2(-tx, ty));
 }
 __device__ __forceinline__ c64 cmul_c(c64 a, float wx, float wy) { return cmul(a, pack2(wx, wy)); }
-__device__ __forceinline__ c64 cscale(c64 a, float s) { return mul2(a, pack2(s, s)); }
 __device__ __forceinline__ c64 cconj_if(c64 a, float sgn) { float x, y; unpack2(a, x, y); return pack2(x, y * sgn); }
+
+// cos / sin of 2 pi k / 32 as compile-time constants
+__host__ __device__ constexpr float qpsk_cos32(int k) {
+    constexpr float C[9] = { 1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+                             0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f };
+    k &= 31;
+    if (k > 16) k = 32 - k;
+    return k <= 8 ? C[k] : -C[16 - k];
+}
+__host__ __device__ constexpr float qpsk_sin32(int k) { return qpsk_cos32(k - 8); }
+// Every constant twiddle of the small DFTs is a power of W32 = exp(-2 pi i / 32), and every such power is +-1 times an
+// optionally swapped copy of (c, s) or (c, -s), (c, s) = (cos, sin)(2 pi r / 32), r = 1..4.  Those eight pairs live in
+// registers for the whole kernel (FftConsts); swap and a common sign fold into the operand modifiers of FMUL2 / FFMA2
+// (a sign on ONE half of a broadcast operand does not, hence both (c, s) and (c, -s)), so a constant complex multiply is
+// two instructions.  As immediates every use cost two extra MOVs to assemble the 64-bit operand (checked in SASS).
+struct FftConsts {
+    c64 bp[4];     // (c, s)
+    c64 bm[4];     // (c, -s)
+};
+// the host fills FftArgs::kbase with (c, s) x 4 then (c, -s) x 4; arriving as kernel arguments the pairs are whole
+// 64-bit uniform-register operands, opaque to the optimiser (which would otherwise fold them back into immediates)
+inline void fft_consts_host(float2 (&kb)[8]) {
+    for (int r = 1; r <= 4; r++) {
+        kb[r - 1] = make_float2(qpsk_cos32(r), qpsk_sin32(r));
+        kb[4 + r - 1] = make_float2(qpsk_cos32(r), -qpsk_sin32(r));
+    }
+}
+// a * W, W = SGN * (SW ? swap(base) : base)
+template <int SW, int SGN>
+__device__ __forceinline__ c64 cmul_base(c64 a, c64 base) {
+    float ax, ay, bx, by, tx, ty;
+    unpack2(a, ax, ay);
+    unpack2(base, bx, by);
+    const float u = SW ? by : bx, v = SW ? bx : by;              // W = SGN (u, v)
+    unpack2(mul2(pack2(ay, ay), pack2(v, u)), tx, ty);           // (ay v, ay u)
+    return fma2(pack2(SGN > 0 ? ax : -ax, SGN > 0 ? ax : -ax), pack2(u, v), pack2(SGN > 0 ? -tx : tx, SGN > 0 ? ty : -ty));
+}
+// v * W32^K, K a compile-time constant
+template <int K>
+__device__ __forceinline__ c64 cmul_w32(c64 v, const FftConsts& kc) {
+    constexpr int k = K & 31, q = k / 8, r = k % 8;
+    if constexpr (r == 0) {
+        float x, y;
+        unpack2(v, x, y);
+        if constexpr (q == 0) return v;
+        else if constexpr (q == 1) return pack2(y, -x);
+        else if constexpr (q == 2) return pack2(-x, -y);
+        else return pack2(-y, x);
+    } else if constexpr (r <= 4) {                    // W32^r = (c, -s); times (-i)^q
+        constexpr int i = r - 1;
+        if constexpr (q == 0) return cmul_base<0, 1>(v, kc.bm[i]);         // ( c, -s)
+        else if constexpr (q == 1) return cmul_base<1, -1>(v, kc.bp[i]);   // (-s, -c)
+        else if constexpr (q == 2) return cmul_base<0, -1>(v, kc.bm[i]);   // (-c,  s)
+        else return cmul_base<1, 1>(v, kc.bp[i]);                          // ( s,  c)
+    } else {                                          // W32^r = (s', -c') with (c', s') the pair of 8 - r
+        constexpr int i = 8 - r - 1;
+        if constexpr (q == 0) return cmul_base<1, -1>(v, kc.bm[i]);        // ( s, -c)
+        else if constexpr (q == 1) return cmul_base<0, -1>(v, kc.bp[i]);   // (-c, -s)
+        else if constexpr (q == 2) return cmul_base<1, 1>(v, kc.bm[i]);    // (-s,  c)
+        else return cmul_base<0, 1>(v, kc.bp[i]);                          // ( c,  s)
+    }
+}
 
 // forward R-point DFT in registers, natural order in and out
 template <int R>
-__device__ __forceinline__ void dft_small(c64 (&v)[R]);
+__device__ __forceinline__ void dft_small(c64 (&v)[R], const FftConsts& kc);
 
 template <>
-__device__ __forceinline__ void dft_small<2>(c64 (&v)[2]) {
+__device__ __forceinline__ void dft_small<2>(c64 (&v)[2], const FftConsts&) {
     const c64 a = v[0], b = v[1];
     v[0] = cadd(a, b);
     v[1] = csub(a, b);
 }
 template <>
-__device__ __forceinline__ void dft_small<4>(c64 (&v)[4]) {
+__device__ __forceinline__ void dft_small<4>(c64 (&v)[4], const FftConsts&) {
     const c64 s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
     const c64 s13 = cadd(v[1], v[3]), d13 = csub(v[1], v[3]);
     v[0] = cadd(s02, s13);
@@ -91,63 +200,54 @@ __device__ __forceinline__ void dft_small<4>(c64 (&v)[4]) {
     v[3] = cadd_pi(d02, d13);      // d02 + (+i) d13
 }
 template <>
-__device__ __forceinline__ void dft_small<8>(c64 (&v)[8]) {
-    const float h = 0.70710678118654752f;
+__device__ __forceinline__ void dft_small<8>(c64 (&v)[8], const FftConsts& kc) {
     c64 e[4] = { v[0], v[2], v[4], v[6] }, o[4] = { v[1], v[3], v[5], v[7] };
-    dft_small<4>(e);
-    dft_small<4>(o);
+    dft_small<4>(e, kc);
+    dft_small<4>(o, kc);
     // o[q] *= exp(-2 pi i q / 8)
-    const c64 o1 = cmul_c(o[1], h, -h);
-    const c64 o3 = cmul_c(o[3], -h, -h);
+    const c64 o1 = cmul_w32<4>(o[1], kc);
+    const c64 o3 = cmul_w32<12>(o[3], kc);
     v[0] = cadd(e[0], o[0]);     v[4] = csub(e[0], o[0]);
     v[1] = cadd(e[1], o1);       v[5] = csub(e[1], o1);
     v[2] = cadd_mi(e[2], o[2]);  v[6] = cadd_pi(e[2], o[2]);
     v[3] = cadd(e[3], o3);       v[7] = csub(e[3], o3);
 }
 template <>
-__device__ __forceinline__ void dft_small<16>(c64 (&v)[16]) {
+__device__ __forceinline__ void dft_small<16>(c64 (&v)[16], const FftConsts& kc) {
     // 16 = 4 x 4: four radix-4 transforms over stride-4 subsequences, twiddles W16^(q*r), four radix-4 across
-    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
     c64 a[4][4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         c64 t[4] = { v[r], v[r + 4], v[r + 8], v[r + 12] };
-        dft_small<4>(t);
+        dft_small<4>(t, kc);
 #pragma unroll
         for (int q = 0; q < 4; q++) a[r][q] = t[q];
     }
     // a[r][q] *= W16^(r*q), W16 = exp(-2 pi i / 16); the e = 4 case (-i) is folded into the second layer
-    a[1][1] = cmul_c(a[1][1], c1, -s1);  a[1][2] = cmul_c(a[1][2], h, -h);    a[1][3] = cmul_c(a[1][3], s1, -c1);
-    a[2][1] = cmul_c(a[2][1], h, -h);    /* a[2][2] *= -i below */           a[2][3] = cmul_c(a[2][3], -h, -h);
-    a[3][1] = cmul_c(a[3][1], s1, -c1);  a[3][2] = cmul_c(a[3][2], -h, -h);   a[3][3] = cmul_c(a[3][3], -c1, s1);
-    {
-        float x, y;
-        unpack2(a[2][2], x, y);
-        a[2][2] = pack2(y, -x);
-    }
+    a[1][1] = cmul_w32<2>(a[1][1], kc);  a[1][2] = cmul_w32<4>(a[1][2], kc);   a[1][3] = cmul_w32<6>(a[1][3], kc);
+    a[2][1] = cmul_w32<4>(a[2][1], kc);  a[2][2] = cmul_w32<8>(a[2][2], kc);   a[2][3] = cmul_w32<12>(a[2][3], kc);
+    a[3][1] = cmul_w32<6>(a[3][1], kc);  a[3][2] = cmul_w32<12>(a[3][2], kc);  a[3][3] = cmul_w32<18>(a[3][3], kc);
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         c64 t[4] = { a[0][q], a[1][q], a[2][q], a[3][q] };
-        dft_small<4>(t);
+        dft_small<4>(t, kc);
 #pragma unroll
         for (int p = 0; p < 4; p++) v[q + 4 * p] = t[p];
     }
 }
 
 template <>
-__device__ __forceinline__ void dft_small<32>(c64 (&v)[32]) {
+__device__ __forceinline__ void dft_small<32>(c64 (&v)[32], const FftConsts& kc) {
     // 32 = 2 x 16, decimation in time: X[k] = E[k] + W32^k O[k], X[k+16] = E[k] - W32^k O[k]
-    const float c1 = 0.98078528040323043f, s1 = 0.19509032201612825f, c2 = 0.92387953251128674f, s2 = 0.38268343236508977f,
-                c3 = 0.83146961230254524f, s3 = 0.55557023301960218f, h = 0.70710678118654752f;
     c64 e[16], o[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) { e[k] = v[2 * k]; o[k] = v[2 * k + 1]; }
-    dft_small<16>(e);
-    dft_small<16>(o);
-    o[1] = cmul_c(o[1], c1, -s1);    o[2] = cmul_c(o[2], c2, -s2);    o[3] = cmul_c(o[3], c3, -s3);    o[4] = cmul_c(o[4], h, -h);
-    o[5] = cmul_c(o[5], s3, -c3);    o[6] = cmul_c(o[6], s2, -c2);    o[7] = cmul_c(o[7], s1, -c1);    /* o[8] *= -i below */
-    o[9] = cmul_c(o[9], -s1, -c1);   o[10] = cmul_c(o[10], -s2, -c2); o[11] = cmul_c(o[11], -s3, -c3); o[12] = cmul_c(o[12], -h, -h);
-    o[13] = cmul_c(o[13], -c3, -s3); o[14] = cmul_c(o[14], -c2, -s2); o[15] = cmul_c(o[15], -c1, -s1);
+    dft_small<16>(e, kc);
+    dft_small<16>(o, kc);
+    o[1] = cmul_w32<1>(o[1], kc);    o[2] = cmul_w32<2>(o[2], kc);    o[3] = cmul_w32<3>(o[3], kc);    o[4] = cmul_w32<4>(o[4], kc);
+    o[5] = cmul_w32<5>(o[5], kc);    o[6] = cmul_w32<6>(o[6], kc);    o[7] = cmul_w32<7>(o[7], kc);    /* o[8] *= -i below */
+    o[9] = cmul_w32<9>(o[9], kc);    o[10] = cmul_w32<10>(o[10], kc); o[11] = cmul_w32<11>(o[11], kc); o[12] = cmul_w32<12>(o[12], kc);
+    o[13] = cmul_w32<13>(o[13], kc); o[14] = cmul_w32<14>(o[14], kc); o[15] = cmul_w32<15>(o[15], kc);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
         if (k == 8) { v[k] = cadd_mi(e[k], o[k]); v[k + 16] = cadd_pi(e[k], o[k]); }
@@ -156,7 +256,13 @@ __device__ __forceinline__ void dft_small<32>(c64 (&v)[32]) {
 }
 
 template <int SKEW>
-__device__ __forceinline__ int fft_skew(int i) { return i + i / SKEW; }
+__host__ __device__ constexpr int fft_skew(int i) { return i + i / SKEW; }
+
+// Offset of a compile-time displacement c from a per-thread base whose skewed address is already known:
+// skew(base + c) = skew(base) + fft_off(c), provided the low parts never carry into another pad slot
+// (proved per stage at compile time by fft_stage_linear_ok).
+template <int SKEW>
+__host__ __device__ constexpr int fft_off(int c) { return c + c / SKEW; }
 
 // the threads of one transform exchange data between passes: a warp-level barrier is enough when a transform lives
 // inside one warp (n / points-per-thread <= 32)
@@ -175,59 +281,125 @@ struct FftArgs {
     int nbursts;
     float im_sign;         // +1 forward, -1 inverse (inverse = conj(FFT(conj(x))))
     float scale;           // 1/N forward (fft.c:105-107), 1 inverse (fft.c:122-128)
+    float2 kbase[8];       // (cos, sin) and (cos, -sin) of 2 pi r / 32, r = 1..4, see FftConsts
 };
 
-// one Stockham stage for the P points a thread owns: radix R, sub-transform length NS already done
-template <int LOG2N, int R, int NS, bool FIRST, bool LAST>
-__device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw,
-                                          const float2* gin, int j, int base, bool active, float imsgn) {
+// One Stockham stage for the P points a thread owns: radix R, sub-transform length NS already done.
+// GEN: the general entry points (inverse through conjugation); the estimator instantiation loads plain.
+template <int LOG2N, int R, int NS, bool FIRST, bool LAST, bool GEN>
+__device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw, const c64* gin, int j, int base, float imsgn,
+                                          const FftConsts& kc) {
     using Cfg = FftCfg<LOG2N>;
-    constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R;   // NB butterflies per thread
+    constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R, S = Cfg::SKEW;   // NB butterflies per thread
+    constexpr int STRIDE = N / R;
+    constexpr int KT = qpsk_fft_tw_cols(NS, TPF);        // twiddle columns of this stage
+    constexpr bool FACT = LAST && NS > TPF;              // w^(m k), k = j + t TPF  =  table[m][j] * W_P^(m t)
+    static_assert(LAST || NS <= TPF, "only a remainder stage may have more sub-transform columns than threads");
+    static_assert(!FACT || (N / TPF == P && 32 % P == 0), "factored twiddles assume n / tpf == P, a divisor of 32");
+
+    const c64* rd = sdat + fft_skew<S>(base + j);
+    c64 tw[(NS > 1) ? R - 1 : 1];
+    if (NS > 1) {
+        const int k = j % KT;
+#pragma unroll
+        for (int m = 1; m < R; m++) tw[m - 1] = stw[(m - 1) * KT + k];
+    }
 #pragma unroll
     for (int t = 0; t < NB; t++) {
-        const int jj = j + t * TPF;                  // butterfly index in [0, N/R)
         c64 v[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const int idx = jj + r * (N / R);
-            if (FIRST && Cfg::PREFETCH) v[r] = cconj_if(reinterpret_cast<const c64*>(gin)[idx], imsgn);   // gin = this transform in the staging buffer (zero-filled when inactive)
-            else if (FIRST) v[r] = cconj_if(active ? reinterpret_cast<const c64*>(gin)[idx] : 0ull, imsgn);   // inverse = conj(FFT(conj x))
-            else v[r] = sdat[fft_skew<Cfg::SKEW>(base + idx)];
+            const int c = t * TPF + r * STRIDE;          // butterfly j + t TPF, input r
+            if (FIRST) {
+                v[r] = gin[j + c];
+                if (GEN) v[r] = cconj_if(v[r], imsgn);    // inverse = conj(FFT(conj x))
+            } else if (Cfg::LIN) {
+                v[r] = rd[fft_off<S>(c)];
+            } else {
+                v[r] = sdat[fft_skew<S>(base + j + c)];
+            }
         }
         if (NS > 1) {
-            const int k = jj % NS;
 #pragma unroll
-            for (int m = 1; m < R; m++) v[m] = cmul(v[m], stw[(m - 1) * NS + k]);
+            for (int m = 1; m < R; m++) {
+                v[m] = cmul(v[m], tw[m - 1]);
+                if (FACT && t > 0) {
+                    // W_P^(m t) as a power of W32
+                    switch ((m * t * (32 / P)) & 31) {
+#define QPSK_W32_CASE(K) case K: v[m] = cmul_w32<K>(v[m], kc); break;
+                        QPSK_W32_CASE(1) QPSK_W32_CASE(2) QPSK_W32_CASE(3) QPSK_W32_CASE(4) QPSK_W32_CASE(5) QPSK_W32_CASE(6) QPSK_W32_CASE(7)
+                        QPSK_W32_CASE(8) QPSK_W32_CASE(9) QPSK_W32_CASE(10) QPSK_W32_CASE(11) QPSK_W32_CASE(12) QPSK_W32_CASE(13) QPSK_W32_CASE(14)
+                        QPSK_W32_CASE(15) QPSK_W32_CASE(16) QPSK_W32_CASE(17) QPSK_W32_CASE(18) QPSK_W32_CASE(19) QPSK_W32_CASE(20) QPSK_W32_CASE(21)
+                        QPSK_W32_CASE(22) QPSK_W32_CASE(23) QPSK_W32_CASE(24) QPSK_W32_CASE(25) QPSK_W32_CASE(26) QPSK_W32_CASE(27) QPSK_W32_CASE(28)
+                        QPSK_W32_CASE(29) QPSK_W32_CASE(30) QPSK_W32_CASE(31)
+#undef QPSK_W32_CASE
+                        default: break;
+                    }
+                }
+            }
         }
-        dft_small<R>(v);
+        dft_small<R>(v, kc);
 #pragma unroll
         for (int q = 0; q < R; q++) pts[t * R + q] = v[q];
     }
     if (!LAST) {
         if (!FIRST) fft_sync<TPF>();                 // everyone has read this stage's inputs
+        // butterfly jj = j + t TPF writes o + q NS, o = (jj / NS) NS R + jj % NS
+        const int dyn = (NS == 1) ? j * R : (j / NS) * NS * R + (j % NS);
+        c64* wr = sdat + fft_skew<S>(base + dyn);
 #pragma unroll
         for (int t = 0; t < NB; t++) {
-            const int jj = j + t * TPF;
-            const int o = (jj / NS) * NS * R + (jj % NS);
 #pragma unroll
             for (int q = 0; q < R; q++) {
-                sdat[fft_skew<Cfg::SKEW>(base + o + q * NS)] = pts[t * R + q];
+                const int c = t * TPF * R + q * NS;
+                if (Cfg::LIN) wr[fft_off<S>(c)] = pts[t * R + q];
+                else sdat[fft_skew<S>(base + dyn + c)] = pts[t * R + q];
             }
         }
         fft_sync<TPF>();
     }
 }
 
-template <int LOG2N, int NS, bool FIRST>
-__device__ __forceinline__ void fft_stages(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw,
-                                           const float2* gin, int j, int base, bool active, float imsgn) {
+// compile-time proof of the linear-offset claims for one stage (evaluated by static_assert in fft_stages)
+template <int LOG2N, int R, int NS, bool FIRST, bool LAST>
+__host__ __device__ constexpr bool fft_stage_linear_ok() {
+    using Cfg = FftCfg<LOG2N>;
+    constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R, S = Cfg::SKEW;
+    if (!Cfg::LIN) return true;
+    if ((Cfg::N % S) != 0) return false;                               // transform bases are multiples of S
+    if (!FIRST) {                                                      // reads: base + j + c
+        for (int t = 0; t < NB; t++)
+            for (int r = 0; r < R; r++) {
+                const int c = t * TPF + r * (N / R);
+                if (TPF >= S) { if (c % S != 0) return false; }        // j spans whole pad periods: c must not disturb them
+                else if ((c % S) + TPF > S) return false;              // j < TPF < S: no carry into the next pad slot
+            }
+    }
+    if (!LAST) {                                                       // writes: base + dyn + c
+        if (NS == 1) { if (R != S) return false; }                     // dyn = j R is a multiple of S, c = t TPF R + q, q < S
+        else if (NS % S != 0 || TPF % NS != 0) return false;           // dyn = (j/NS) NS R + j % NS, c a multiple of S
+        for (int t = 0; t < NB; t++)
+            for (int q = 0; q < R; q++) {
+                const int c = t * TPF * R + q * NS;
+                if (NS == 1) { if ((c - q) % S != 0 || q >= S) return false; }
+                else if (c % S != 0) return false;
+            }
+    }
+    return true;
+}
+
+template <int LOG2N, int NS, bool FIRST, bool GEN>
+__device__ __forceinline__ void fft_stages(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw, const c64* gin, int j, int base, float imsgn,
+                                           const FftConsts& kc) {
     constexpr int N = FftCfg<LOG2N>::N;
     constexpr int REM = N / NS;
     constexpr int RMAX = FftCfg<LOG2N>::P;
     constexpr int R = qpsk_fft_radix(REM, RMAX);
     constexpr bool LAST = (NS * R == N);
-    fft_stage<LOG2N, R, NS, FIRST, LAST>(pts, sdat, stw, gin, j, base, active, imsgn);
-    if constexpr (!LAST) fft_stages<LOG2N, NS * R, false>(pts, sdat, stw + (NS > 1 ? (R - 1) * NS : 0), gin, j, base, active, imsgn);
+    static_assert(fft_stage_linear_ok<LOG2N, R, NS, FIRST, LAST>(), "skewed shared-memory offsets of this stage are not linear");
+    fft_stage<LOG2N, R, NS, FIRST, LAST, GEN>(pts, sdat, stw, gin, j, base, imsgn, kc);
+    if constexpr (!LAST)
+        fft_stages<LOG2N, NS * R, false, GEN>(pts, sdat, stw + (NS > 1 ? (R - 1) * qpsk_fft_tw_cols(NS, FftCfg<LOG2N>::TPF) : 0), gin, j, base, imsgn, kc);
 }
 
 // output index of pts[i] after the last stage (radix RLAST, sub-transform length NSL = N / RLAST)
@@ -247,8 +419,10 @@ __device__ __forceinline__ int fft_out_index(int j, int i) {
     return (j + t * FftCfg<LOG2N>::TPF) + q * NSL;
 }
 
-template <int LOG2N>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftArgs a) {
+// GEN = false: forward transform, argmax only (a.bin required; a.spectrum, a.im_sign ignored) -- the estimator hot path.
+// GEN = true : forward or inverse, optional spectrum store, optional argmax.
+template <int LOG2N, bool GEN>
+__global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) fft_kernel(const FftArgs a) {
     using Cfg = FftCfg<LOG2N>;
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, FPB = Cfg::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -258,82 +432,118 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS) fft_kernel(const FftAr
     int* red_idx = reinterpret_cast<int*>(red_mag + 64);
 
     for (int i = threadIdx.x; i < Cfg::TW; i += blockDim.x) stw[i] = reinterpret_cast<const c64*>(a.tw)[i];
+    if (threadIdx.x < 64) red_idx[threadIdx.x] = 0x7fffffff;
     __syncthreads();
 
     const int fl = threadIdx.x / TPF, j = threadIdx.x % TPF;
     const int base = fl * N;
-    c64* stage = reinterpret_cast<c64*>(red_idx + 64);      // [FPB][N], only with Cfg::PREFETCH
-    // the threads of a transform fetch that transform: N/2 16-byte pieces over TPF threads = P/2 pieces each, so the
-    // staging buffer of a transform is only ever touched by its own threads (a warp-level barrier orders it when TPF <= 32)
-    auto prefetch = [&](int pass_b0) {
-        const int pb = pass_b0 + fl;
-        const bool in_range = pb < a.nbursts;
-        const float2* src = a.in + (in_range ? (size_t)pb * N : 0);
+    const float scale2 = a.scale * a.scale;
+    FftConsts kc;
 #pragma unroll
-        for (int i = 0; i < P / 2; i++) {
-            const int piece = j + i * TPF;                                // 2 points each
-            const unsigned d = (unsigned)__cvta_generic_to_shared(stage + base + 2 * piece);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src + (in_range ? 2 * piece : 0)), "r"(in_range ? 16 : 0) : "memory");
-        }
-    };
-    if (Cfg::PREFETCH && blockIdx.x * FPB < a.nbursts) prefetch(blockIdx.x * FPB);
+    for (int r = 0; r < 4; r++) {
+        kc.bp[r] = *reinterpret_cast<const c64*>(&a.kbase[r]);
+        kc.bm[r] = *reinterpret_cast<const c64*>(&a.kbase[4 + r]);
+    }
     for (int b0 = blockIdx.x * FPB; b0 < a.nbursts; b0 += gridDim.x * FPB) {
         const int b = b0 + fl;
         const bool active = b < a.nbursts;
+        // an inactive slot of the last pass recomputes the last burst; only its stores are masked
+        const c64* gin = reinterpret_cast<const c64*>(a.in) + (size_t)(active ? b : a.nbursts - 1) * N;
         c64 pts[P];
-        if constexpr (Cfg::PREFETCH) {
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            fft_sync<TPF>();                                             // this transform's input has landed for all its threads
-            constexpr int R0 = P;                                        // N >= P * P here: the first stage is a full radix-P one
-            fft_stage<LOG2N, R0, 1, true, false>(pts, sdat, stw, reinterpret_cast<const float2*>(stage + base), j, base, active, a.im_sign);
-            // the stage ended with a barrier after everyone's reads of the staging buffer: refill it
-            if (b0 + gridDim.x * FPB < a.nbursts) prefetch(b0 + gridDim.x * FPB);
-            fft_stages<LOG2N, R0, false>(pts, sdat, stw, nullptr, j, base, active, a.im_sign);
+        fft_stages<LOG2N, 1, true, GEN>(pts, sdat, stw, gin, j, base, a.im_sign, kc);
+
+        if constexpr (GEN) {
+            // ---- general epilogue: scale, optional spectrum store, |X|^2 argmax
+            float best = -1.0f;
+            int besti = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < P; i++) {
+                const int idx = fft_out_index<LOG2N>(j, i);
+                float2 x;
+                unpack2(pts[i], x.x, x.y);
+                x.x *= a.scale;
+                x.y *= a.scale * a.im_sign;
+                if (a.spectrum != nullptr && active) a.spectrum[(size_t)b * N + idx] = x;
+                const float m = x.x * x.x + x.y * x.y;
+                if (m > best || (m == best && idx < besti)) { best = m; besti = idx; }
+            }
+            if (a.bin != nullptr) {
+                // reduce over the TPF threads of this transform: first strict maximum = largest value, lowest index on ties
+                constexpr int W = (TPF < 32) ? TPF : 32;
+#pragma unroll
+                for (int off = W / 2; off > 0; off >>= 1) {
+                    const float om = __shfl_down_sync(0xffffffffu, best, off, W);
+                    const int oi = __shfl_down_sync(0xffffffffu, besti, off, W);
+                    if (om > best || (om == best && oi < besti)) { best = om; besti = oi; }
+                }
+                if (TPF <= 32) {
+                    if (j == 0 && active) { a.bin[b] = besti; if (a.mag2) a.mag2[b] = best; }
+                } else {
+                    constexpr int WPF = TPF / 32;            // warps per transform (FPB == 1 whenever TPF > 32)
+                    const int wib = threadIdx.x >> 5;
+                    if ((threadIdx.x & 31) == 0) { red_mag[wib] = best; red_idx[32 + wib] = besti; }
+                    __syncthreads();
+                    if (j == 0 && active) {
+                        const int w0 = fl * WPF;
+                        for (int w = 1; w < WPF; w++) {
+                            const float om = red_mag[w0 + w];
+                            const int oi = red_idx[32 + w0 + w];
+                            if (om > best || (om == best && oi < besti)) { best = om; besti = oi; }
+                        }
+                        a.bin[b] = besti;
+                        if (a.mag2) a.mag2[b] = best;
+                    }
+                    __syncthreads();
+                }
+            }
         } else {
-            const float2* gin = a.in + (size_t)(active ? b : 0) * N;
-            fft_stages<LOG2N, 1, true>(pts, sdat, stw, gin, j, base, active, a.im_sign);
-        }
-        // ---- epilogue: scale, optional spectrum store, |X|^2 argmax
-        float best = -1.0f;
-        int besti = 0x7fffffff;
+            // ---- estimator epilogue: |X|^2 of the unscaled outputs (the 1/n is a power of two: it commutes with every
+            // rounding and is applied once to the winner), maximum first, bin second
+            float mg[P];
 #pragma unroll
-        for (int i = 0; i < P; i++) {
-            const int idx = fft_out_index<LOG2N>(j, i);
-            float2 x;
-            unpack2(pts[i], x.x, x.y);
-            x.x *= a.scale;
-            x.y *= a.scale * a.im_sign;
-            if (a.spectrum != nullptr && active) a.spectrum[(size_t)b * N + idx] = x;
-            const float m = x.x * x.x + x.y * x.y;
-            if (m > best || (m == best && idx < besti)) { best = m; besti = idx; }
-        }
-        if (a.bin != nullptr) {
-            // reduce over the TPF threads of this transform: first strict maximum = largest value, lowest index on ties
+            for (int i = 0; i < P; i++) {
+                float x, y;
+                unpack2(mul2(pts[i], pts[i]), x, y);
+                mg[i] = __fadd_rn(x, y);
+            }
+            float red[P];
+#pragma unroll
+            for (int i = 0; i < P; i++) red[i] = mg[i];
+#pragma unroll
+            for (int w = P / 2; w > 0; w >>= 1)
+#pragma unroll
+                for (int i = 0; i < w; i++) red[i] = fmaxf(red[i], red[i + w]);
+            const float lmax = red[0];
             constexpr int W = (TPF < 32) ? TPF : 32;
+            float g = lmax;
 #pragma unroll
-            for (int off = W / 2; off > 0; off >>= 1) {
-                const float om = __shfl_down_sync(0xffffffffu, best, off, W);
-                const int oi = __shfl_down_sync(0xffffffffu, besti, off, W);
-                if (om > best || (om == best && oi < besti)) { best = om; besti = oi; }
+            for (int off = W / 2; off > 0; off >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, off, W));
+            if (TPF > 32) {
+                const int wib = threadIdx.x >> 5;
+                if ((threadIdx.x & 31) == 0) red_mag[wib] = g;
+                __syncthreads();
+                constexpr int WPF = (TPF > 32) ? TPF / 32 : 1;
+#pragma unroll
+                for (int w = 0; w < WPF; w++) g = fmaxf(g, red_mag[fl * WPF + w]);
+            }
+            // first strict maximum: the lowest bin among the points equal to the maximum
+            int cand = 0x7fffffff;
+            if (lmax == g) {
+#pragma unroll
+                for (int i = 0; i < P; i++)
+                    if (mg[i] == g) cand = min(cand, fft_out_index<LOG2N>(j, i));
             }
             if (TPF <= 32) {
-                if (j == 0 && active) { a.bin[b] = besti; if (a.mag2) a.mag2[b] = best; }
+#pragma unroll
+                for (int off = W / 2; off > 0; off >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, off, W));
+                if (j == 0 && active) { a.bin[b] = cand; if (a.mag2) a.mag2[b] = g * scale2; }
             } else {
-                constexpr int WPF = TPF / 32;            // warps per transform (FPB == 1 whenever TPF > 256; else FPB*WPF == 8)
-                const int wib = threadIdx.x >> 5;
-                if ((threadIdx.x & 31) == 0) { red_mag[wib] = best; red_idx[wib] = besti; }
+                if (cand != 0x7fffffff) atomicMin(&red_idx[fl], cand);
                 __syncthreads();
-                if (j == 0 && active) {
-                    const int w0 = fl * WPF;
-                    for (int w = 1; w < WPF; w++) {
-                        const float om = red_mag[w0 + w];
-                        const int oi = red_idx[w0 + w];
-                        if (om > best || (om == best && oi < besti)) { best = om; besti = oi; }
-                    }
-                    a.bin[b] = besti;
-                    if (a.mag2) a.mag2[b] = best;
+                if (j == 0) {
+                    if (active) { a.bin[b] = red_idx[fl]; if (a.mag2) a.mag2[b] = g * scale2; }
+                    red_idx[fl] = 0x7fffffff;          // the next pass's atomics come after at least one more barrier
                 }
-                __syncthreads();
             }
         }
         // the next pass's stage-0 writes must not race with this pass's last-stage reads: the last

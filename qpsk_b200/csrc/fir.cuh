@@ -10,23 +10,24 @@
 #pragma once
 
 #include "common.cuh"
-#include "rx_front.cuh"   // c_taps2, fir_strip
+#include "rx_front.cuh"   // TapBank, fir_strip
 
 struct FirArgs {
     float2* data;     // [C][T] complex samples, filtered in place
     float2* state;    // [C][NTAPS] delay line: the last NTAPS inputs, oldest first (rrc_fir's `memory`)
-    const float2* halo;  // [C][nblocks-1][NTAPS-1] inputs preceding time blocks 1.., saved by fir_save_halo_kernel
+    const float2* halo;  // [C][nblocks][NTAPS-1] inputs preceding every time block, saved by fir_save_halo_kernel (nblocks > 1)
     int C, T;
     int nblocks, tiles_per_block;   // blockIdx.y = time block: the call is cut so the grid fills whole waves of CTAs
 };
 
-// The filter works in place, so the NTAPS-1 inputs in front of every time block but the first are copied aside
-// before the main kernel overwrites them.
-__global__ void __launch_bounds__(128) fir_save_halo_kernel(const float2* __restrict__ data, float2* __restrict__ halo, int T,
-                                                            int halo_len, int nblocks, int block_len) {
-    const int ch = blockIdx.x, b = blockIdx.y + 1;
-    const float2* src = data + (size_t)ch * T + (size_t)b * block_len - halo_len;
-    float2* dst = halo + ((size_t)ch * (nblocks - 1) + (b - 1)) * halo_len;
+// The filter works in place, so the NTAPS-1 inputs in front of every time block are copied aside before the main
+// kernel overwrites them; for block 0 they are memory[1 .. NTAPS-1] of the delay line, which the CTA of the last
+// time block rewrites (no CTA of the main kernel reads `state` when the call is cut into blocks).
+__global__ void __launch_bounds__(128) fir_save_halo_kernel(const float2* __restrict__ data, const float2* __restrict__ state,
+                                                            float2* __restrict__ halo, int T, int halo_len, int nblocks, int block_len) {
+    const int ch = blockIdx.x, b = blockIdx.y;
+    const float2* src = b == 0 ? state + (size_t)ch * (halo_len + 1) + 1 : data + (size_t)ch * T + (size_t)b * block_len - halo_len;
+    float2* dst = halo + ((size_t)ch * nblocks + b) * halo_len;
     for (int i = threadIdx.x; i < halo_len; i += blockDim.x) dst[i] = src[i];
 }
 
@@ -111,7 +112,7 @@ __device__ __forceinline__ void fir_store_tile(FirSmem<NTAPS, NW>& sm, const Fir
 }
 
 template <int NTAPS, int MODE, int NW>
-__global__ void __launch_bounds__(32 * NW, (sizeof(FirSmem<NTAPS, NW>) <= 112 * 1024) ? 2 : 1) fir_kernel(const FirArgs a) {
+__global__ void __launch_bounds__(32 * NW, (sizeof(FirSmem<NTAPS, NW>) <= 112 * 1024) ? 2 : 1) fir_kernel(const __grid_constant__ FirArgs a, const __grid_constant__ TapBank<NTAPS> tb) {
     constexpr int R = 16, TILE = 16 * NW;
     constexpr int HT = FirSmem<NTAPS, NW>::HT;
     constexpr int CUR = HT * TILE;                   // first slot of the current tile
@@ -133,8 +134,8 @@ __global__ void __launch_bounds__(32 * NW, (sizeof(FirSmem<NTAPS, NW>) <= 112 * 
     // first tile on its way; halo <- memory[1 .. NTAPS-1] (memory[0] is never read again by rrc_fir) or, for a
     // later time block, the inputs saved by the pre-pass
     fir_load_tile<NTAPS, NW>(sm, a, k0, w, lane, vec16);
-    const u64* before = blockIdx.y == 0 ? state + 1
-        : reinterpret_cast<const u64*>(a.halo) + ((size_t)chl * (a.nblocks - 1) + (blockIdx.y - 1)) * (NTAPS - 1);
+    const u64* before = a.nblocks == 1 ? state + 1
+        : reinterpret_cast<const u64*>(a.halo) + ((size_t)chl * a.nblocks + blockIdx.y) * (NTAPS - 1);
     for (int i = w; i < NTAPS - 1; i += NW) xrow[CUR - (NTAPS - 1) + i] = before[i];
     cp_async_wait_all();
     __syncthreads();
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(32 * NW, (sizeof(FirSmem<NTAPS, NW>) <= 112 * 
         __syncwarp();
         if (!last) fir_load_tile<NTAPS, NW>(sm, a, k + 1, w, lane, vec16);
         u64 acc[R];
-        fir_strip<NTAPS, R, MODE>(xrow + CUR + strip - (NTAPS - 1), acc);
+        fir_strip<NTAPS, R, MODE>(xrow + CUR + strip - (NTAPS - 1), tb.t, acc);
         cp_async_wait_all();
         __syncthreads();                               // tile k+1 has landed; nobody reads x any more
         if (last) {

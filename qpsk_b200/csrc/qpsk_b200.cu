@@ -48,9 +48,15 @@ struct qpsk_b200_fft;
 
 static const double kTau = 2.0 * 3.14159265358979323846;
 
-// constant-bank taps belong to the context that uploaded them last; ids are never reused
-static long long g_taps_owner = -1;
 static long long g_next_id = 0;
+
+// the taps of a context as the kernels take them: a __grid_constant__ parameter (see TapBank, rx_front.cuh)
+template <int NTAPS>
+static TapBank<NTAPS> tap_bank(const float* taps) {
+    TapBank<NTAPS> tb;
+    for (int i = 0; i < NTAPS; i++) tb.t[i] = make_float2(taps[i], taps[i]);
+    return tb;
+}
 
 // ---------------------------------------------------------------------------------------------
 struct qpsk_b200_rx {
@@ -153,13 +159,13 @@ static int rx_free(qpsk_b200_rx* rx) {
 extern "C" int qpsk_b200_rx_destroy(qpsk_b200_rx* rx) { return rx_free(rx); }
 
 template <int NTAPS, int SPS, int MODE>
-static cudaError_t launch_front(const RxFrontArgs& a, int grid, cudaStream_t s) {
+static cudaError_t launch_front(const RxFrontArgs& a, const float* taps, int grid, cudaStream_t s) {
     const size_t smem = sizeof(RxFrontSmem<SPS>);
     cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<NTAPS, SPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(rx_front_kernel<NTAPS, SPS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    rx_front_kernel<NTAPS, SPS, MODE><<<grid, QPSK_FRONT_THREADS, smem, s>>>(a);
+    rx_front_kernel<NTAPS, SPS, MODE><<<grid, QPSK_FRONT_THREADS, smem, s>>>(a, tap_bank<NTAPS>(taps));
     return cudaGetLastError();
 }
 
@@ -273,36 +279,22 @@ extern "C" int qpsk_b200_rx_reset(qpsk_b200_rx* rx) {
     return QPSK_B200_OK;
 }
 
-static int upload_taps(const qpsk_b200_rx* rx, cudaStream_t s) {
-    float2 t2[QPSK_MAX_TAPS];
-    for (int i = 0; i < rx->cfg.ntaps; i++) t2[i] = make_float2(rx->taps[i], rx->taps[i]);
-    CU(cudaMemcpyToSymbolAsync(c_taps2, t2, sizeof(float2) * rx->cfg.ntaps, 0, cudaMemcpyHostToDevice, s));
-    CU(cudaStreamSynchronize(s));   // t2 is on the stack
-    return 0;
-}
-
 
 
 // ---- bit-stage helpers shared by the receiver and the standalone entry points -----------------
-static long long g_keystream_nbytes = -1;
-
-static int upload_keystream(int nbytes, cudaStream_t s) {
-    if (g_keystream_nbytes == nbytes) return 0;
-    unsigned words[16] = { 0 };
+static Keystream make_keystream(int nbytes) {
+    Keystream ks;
+    memset(&ks, 0, sizeof ks);
     uint16_t reg = (uint16_t)QPSK_SCRAMBLE_SEED;                 // bit-scramble.c:46-55, reset per frame
-    for (int bit = 0; bit < nbytes * 8; bit++) words[bit >> 5] |= lfsr_step(reg) << (bit & 31);
-    CU(cudaMemcpyToSymbolAsync(c_keystream_words, words, sizeof words, 0, cudaMemcpyHostToDevice, s));
-    CU(cudaStreamSynchronize(s));
-    g_keystream_nbytes = nbytes;
-    return 0;
+    for (int bit = 0; bit < nbytes * 8; bit++) ks.w[bit >> 5] |= lfsr_step(reg) << (bit & 31);
+    return ks;
 }
 
 static int launch_frame_decode(int nbytes, const unsigned* dibits_t, unsigned* frames_t, uint8_t* crc_ok_t, uint8_t* rotation_t,
                                unsigned long long* counters, int c0, int C, int Cpad, int F, cudaStream_t s) {
     if (nbytes != 16 && nbytes != 32) return fail(QPSK_B200_ERR_ARG, "frame decode supports 16- and 32-byte frames, got %d", nbytes);
-    int rc = upload_keystream(nbytes, s);
-    if (rc) return rc;
     FrameDecodeArgs a;
+    a.ks = make_keystream(nbytes);
     a.dibits_t = dibits_t; a.frames_t = frames_t; a.crc_ok_t = crc_ok_t; a.rotation_t = rotation_t; a.counters = counters; a.C = C; a.Cpad = Cpad; a.F = F; a.c0 = c0;
     dim3 grid((C - c0 + 127) / 128, F);
     if (nbytes == 32) frame_decode_kernel<32><<<grid, 128, 0, s>>>(a);
@@ -313,11 +305,6 @@ static int launch_frame_decode(int nbytes, const unsigned* dibits_t, unsigned* f
 
 // ---- one process call = begin (taps, phasor table) + one or more channel slices + end ----------
 static int rx_begin_call(qpsk_b200_rx* rx, int F, cudaStream_t s) {
-    if (g_taps_owner != rx->id) {
-        int rc = upload_taps(rx, s);
-        if (rc) return rc;
-        g_taps_owner = rx->id;
-    }
     // K0: mixer phasors of this call.  If the previous call already evaluated a table for this frame count on the
     // side stream, just wait for it; otherwise evaluate it now.
     const int nxt = rx->ph_cur ^ 1;
@@ -419,8 +406,8 @@ static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, 
     if (timed) CU(cudaEventRecord(rx->ev[0], s));
     cudaError_t e;
     const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
-    if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, grid, s) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, grid, s);
-    else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, grid, s) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, grid, s);
+    if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, rx->taps, grid, s) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, rx->taps, grid, s);
+    else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, rx->taps, grid, s) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, rx->taps, grid, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
     if (timed) CU(cudaEventRecord(rx->ev[1], s));
 
@@ -854,19 +841,21 @@ static cudaError_t launch_fir(qpsk_b200_fir* f, FirArgs a, cudaStream_t s) {
     const int per_sm = smem <= 112 * 1024 ? 2 : 1;
     fir_time_blocks(groups, ntiles, Smem::HT, f->sm_count * per_sm, &a.nblocks, &a.tiles_per_block);
     if (a.nblocks > 1) {
-        const size_t need = (size_t)a.C * (a.nblocks - 1) * (NTAPS - 1);
+        // one halo slot per time block: slot 0 is a copy of the delay line, so that no CTA of the main kernel reads
+        // `state` while the CTA of the last time block rewrites it (block dispatch order is not a guarantee)
+        const size_t need = (size_t)a.C * a.nblocks * (NTAPS - 1);
         if (f->halo_elems < need) {
             if (f->d_halo) { cudaFree(f->d_halo); f->d_halo = nullptr; f->halo_elems = 0; }
             e = cudaMalloc((void**)&f->d_halo, need * sizeof(float2));
             if (e != cudaSuccess) return e;
             f->halo_elems = need;
         }
-        fir_save_halo_kernel<<<dim3(a.C, a.nblocks - 1), 128, 0, s>>>(a.data, f->d_halo, a.T, NTAPS - 1, a.nblocks, a.tiles_per_block * Smem::TILE);
+        fir_save_halo_kernel<<<dim3(a.C, a.nblocks), 128, 0, s>>>(a.data, a.state, f->d_halo, a.T, NTAPS - 1, a.nblocks, a.tiles_per_block * Smem::TILE);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
     a.halo = f->d_halo;
-    fir_kernel<NTAPS, MODE, NW><<<dim3(groups, a.nblocks), 32 * NW, smem, s>>>(a);
+    fir_kernel<NTAPS, MODE, NW><<<dim3(groups, a.nblocks), 32 * NW, smem, s>>>(a, tap_bank<NTAPS>(f->taps));
     return cudaGetLastError();
 }
 
@@ -881,13 +870,6 @@ extern "C" int qpsk_b200_fir_process_device(qpsk_b200_fir* f, float* d_samples, 
 }
 
 static int fir_run(qpsk_b200_fir* f, float* d_samples, int c0, int nc, int nsamples, cudaStream_t s, bool timed) {
-    if (g_taps_owner != f->id) {
-        float2 t2[QPSK_MAX_TAPS];
-        for (int i = 0; i < f->ntaps; i++) t2[i] = make_float2(f->taps[i], f->taps[i]);
-        CU(cudaMemcpyToSymbolAsync(c_taps2, t2, sizeof(float2) * f->ntaps, 0, cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));
-        g_taps_owner = f->id;
-    }
     FirArgs a;
     a.data = reinterpret_cast<float2*>(d_samples); a.state = f->d_state + (size_t)c0 * f->ntaps; a.C = nc; a.T = nsamples;
     if (timed) CU(cudaEventRecord(f->ev[0], s));
@@ -1022,28 +1004,9 @@ extern "C" int qpsk_b200_fft_create(int n, int device, qpsk_b200_fft** out) {
     memset(f, 0, sizeof *f);
     f->n = n; f->log2n = lg; f->device = device;
     cudaDeviceGetAttribute(&f->nsm, cudaDevAttrMultiProcessorCount, device);
-    // per-stage twiddles exp(-2 pi i m k / (ns r)), evaluated in double on the host (fft.c:55-56) and rounded once;
-    // the stage sequence mirrors FftCfg / fft_stages: radix = min(points per thread, remaining length)
-    const int pmax = qpsk_fft_points_per_thread(n);
-    int ntw = 0;
-    for (int ns = 1; ns < n;) { const int rem = n / ns, r = qpsk_fft_radix(rem, pmax); if (ns > 1) ntw += (r - 1) * ns; ns *= r; }
-    if (ntw < 1) ntw = 1;
+    const int ntw = qpsk_fft_tw_count(n);
     float2* tw = new float2[ntw];
-    tw[0] = make_float2(1.0f, 0.0f);
-    {
-        int pos = 0;
-        for (int ns = 1; ns < n;) {
-            const int rem = n / ns, r = qpsk_fft_radix(rem, pmax);
-            if (ns > 1) {
-                for (int m = 1; m < r; m++)
-                    for (int k = 0; k < ns; k++) {
-                        const double ang = kTau * (double)m * (double)k / ((double)ns * (double)r);
-                        tw[pos++] = make_float2((float)cos(ang), (float)(-sin(ang)));
-                    }
-            }
-            ns *= r;
-        }
-    }
+    qpsk_fft_make_twiddles(n, tw);
     cudaError_t e = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
     for (auto& ev : f->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_tw, sizeof(float2) * ntw);
@@ -1054,20 +1017,29 @@ extern "C" int qpsk_b200_fft_create(int n, int device, qpsk_b200_fft** out) {
     return QPSK_B200_OK;
 }
 
-template <int LOG2N>
-static cudaError_t launch_fft_n(const FftArgs& a, int nsm, cudaStream_t s) {
+template <int LOG2N, bool GEN>
+static cudaError_t launch_fft_g(const FftArgs& a, int nsm, cudaStream_t s) {
     using Cfg = FftCfg<LOG2N>;
-    cudaError_t e = cudaFuncSetAttribute(fft_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(fft_kernel<LOG2N, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fft_kernel<LOG2N, GEN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_kernel<LOG2N>, Cfg::THREADS, Cfg::SMEM);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_kernel<LOG2N, GEN>, Cfg::THREADS, Cfg::SMEM);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const int passes = (a.nbursts + Cfg::FPB - 1) / Cfg::FPB;
     int grid = nsm * per_sm;                      // persistent: a multiple of the SM count
     if (grid > passes) grid = passes;
-    fft_kernel<LOG2N><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(a);
+    fft_kernel<LOG2N, GEN><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(a);
     return cudaGetLastError();
+}
+
+// the estimator call (forward, argmax only) has its own lean instantiation
+template <int LOG2N>
+static cudaError_t launch_fft_n(const FftArgs& a, int nsm, cudaStream_t s) {
+    if (a.spectrum == nullptr && a.bin != nullptr && a.im_sign > 0.0f) return launch_fft_g<LOG2N, false>(a, nsm, s);
+    return launch_fft_g<LOG2N, true>(a, nsm, s);
 }
 
 static cudaError_t launch_fft(int log2n, const FftArgs& a, int nsm, cudaStream_t s) {
@@ -1089,6 +1061,7 @@ static int fft_run(qpsk_b200_fft* f, const float* d_in, float* d_out, int nburst
     a.bin = d_bin; a.mag2 = d_mag2; a.tw = f->d_tw; a.nbursts = nbursts;
     a.im_sign = inverse ? -1.0f : 1.0f;
     a.scale = inverse ? 1.0f : 1.0f / (float)f->n;           // fft.c:105-107 vs fft.c:130-136
+    fft_consts_host(a.kbase);
     CU(cudaEventRecord(f->ev[0], s));
     cudaError_t e = launch_fft(f->log2n, a, f->nsm, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "FFT kernel launch failed: %s", cudaGetErrorString(e));
@@ -1273,10 +1246,9 @@ static int frames_codec(const uint8_t* h_in, int nbytes, int nchan, int nframes,
     dim3 tgrid((nchan + 31) / 32, (rows + 31) / 32), tblock(32, 8);
     transpose_from_channel_major<<<tgrid, tblock>>>((const unsigned*)cm.p, (unsigned*)a.p, rows, nchan, Cpad);
     CU(cudaGetLastError());
-    rc = upload_keystream(nbytes, 0);
-    if (rc) return rc;
     if (encode) {
         FrameEncodeArgs ea;
+        ea.ks = make_keystream(nbytes);
         ea.payload_t = (const unsigned*)a.p; ea.dibits_t = (unsigned*)b.p; ea.C = nchan; ea.Cpad = Cpad; ea.F = nframes;
         dim3 grid((nchan + 127) / 128, nframes);
         if (nbytes == 32) frame_encode_kernel<32><<<grid, 128>>>(ea); else frame_encode_kernel<16><<<grid, 128>>>(ea);
@@ -1441,13 +1413,13 @@ extern "C" int qpsk_b200_channel_awgn_device(int16_t* d_pcm, int nchan, long lon
 }
 
 template <int SPS>
-static cudaError_t launch_tx(const TxArgs& a, cudaStream_t s) {
+static cudaError_t launch_tx(const TxArgs& a, const float* taps, cudaStream_t s) {
     const size_t smem = sizeof(TxSmem<SPS>);
     cudaError_t e = cudaFuncSetAttribute(tx_kernel<127, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(tx_kernel<127, SPS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    tx_kernel<127, SPS><<<a.Cpad / QPSK_GROUP, 256, smem, s>>>(a);
+    tx_kernel<127, SPS><<<a.Cpad / QPSK_GROUP, 256, smem, s>>>(a, tap_bank<127>(taps));
     return cudaGetLastError();
 }
 
@@ -1457,17 +1429,10 @@ static int tx_run(qpsk_b200_tx* tx, const uint8_t* d_symbols, const float2* d_sy
     if (nsym < ts || nsym % ts != 0) return fail(QPSK_B200_ERR_ARG, "nsym %d must be a positive multiple of %d", nsym, ts);
     CU(cudaSetDevice(tx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : tx->stream;
-    if (g_taps_owner != tx->id) {
-        float2 t2[QPSK_MAX_TAPS];
-        for (int i = 0; i < tx->ntaps; i++) t2[i] = make_float2(tx->taps[i], tx->taps[i]);
-        CU(cudaMemcpyToSymbolAsync(c_taps2, t2, sizeof(float2) * tx->ntaps, 0, cudaMemcpyHostToDevice, s));
-        CU(cudaStreamSynchronize(s));
-        g_taps_owner = tx->id;
-    }
     TxArgs a;
     a.symbols = d_symbols; a.symbols_cf = d_symbols_cf; a.pcm = d_pcm; a.phase_state = tx->d_phase; a.rect = tx->d_rect; a.sym_hist = tx->d_hist;
     a.C = tx->C; a.Cpad = tx->Cpad; a.nsym = nsym; a.packet_samples = tx->packet_samples; a.sample_pos = tx->sample_pos;
-    cudaError_t e = tx->sps == 4 ? launch_tx<4>(a, s) : launch_tx<8>(a, s);
+    cudaError_t e = tx->sps == 4 ? launch_tx<4>(a, tx->taps, s) : launch_tx<8>(a, tx->taps, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "tx kernel launch failed: %s", cudaGetErrorString(e));
     tx->sample_pos = (tx->sample_pos + nsym * tx->sps) % tx->packet_samples;
     return QPSK_B200_OK;

@@ -17,8 +17,14 @@
 enum { QPSK_MODE_EXACT = 0, QPSK_MODE_FAST = 1 };
 enum { QPSK_UB_ALIAS = 0, QPSK_UB_CLAMP = 1, QPSK_UB_PHASE = 2 };
 
-// taps duplicated into both halves of a 64-bit constant: the packed-FP32 multiplier operand
-__constant__ float2 c_taps2[QPSK_MAX_TAPS];
+// Taps duplicated into both halves of a 64-bit constant: the packed-FP32 multiplier operand.  The bank is a
+// __grid_constant__ kernel parameter, i.e. it lives in the launch's own slice of the constant bank: every
+// context (receiver, filter bank, transmitter) launches with its own taps, on any device and any stream, and
+// nothing process-wide has to be re-uploaded or ordered against kernels still in flight.
+template <int NTAPS>
+struct TapBank {
+    float2 t[NTAPS];
+};
 
 // --------------------------------------------------------------------------------------------
 // K0: the mixer phasor sequence of qpsk.c:115,120.  It is a data-independent recurrence
@@ -60,8 +66,8 @@ __global__ void phasor_table_kernel(const float2* __restrict__ prev_table, int p
 // order of rrc_fir.c:22-26.
 // --------------------------------------------------------------------------------------------
 template <int MODE>
-__device__ __forceinline__ void fir_tap(u64& acc, const u64 xv, const int i) {
-    const u64 cc = *reinterpret_cast<const u64*>(&c_taps2[i]);
+__device__ __forceinline__ void fir_tap(u64& acc, const u64 xv, const float2* __restrict__ taps2, const int i) {
+    const u64 cc = *reinterpret_cast<const u64*>(&taps2[i]);
     if (MODE == QPSK_MODE_EXACT) acc = add2(acc, mul2_exact(xv, cc));
     else acc = fma2(xv, cc, acc);
 }
@@ -73,7 +79,7 @@ __device__ __forceinline__ void fir_tap(u64& acc, const u64 xv, const int i) {
 // code at R = 16) stays resident in the instruction cache -- the fully unrolled 70 KB version spent
 // 9 % of its issue slots waiting for instruction fetch (profiles/r01_rx_front_v2).
 template <int NTAPS, int R, int MODE>
-__device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[R]) {
+__device__ __forceinline__ void fir_strip(const u64* __restrict__ x, const float2* __restrict__ taps2, u64 (&acc)[R]) {
     constexpr int STEADY = NTAPS - R + 1;            // d = R-1 .. NTAPS-1
     constexpr int TRIPS = STEADY / R, REM = STEADY % R;
 #pragma unroll
@@ -82,7 +88,7 @@ __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[
     for (int d = 0; d < R - 1; d++) {                // head
         const u64 xv = x[d];
 #pragma unroll
-        for (int r = 0; r <= d; r++) fir_tap<MODE>(acc[r], xv, d - r);
+        for (int r = 0; r <= d; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r);
     }
 #pragma unroll 1
     for (int m = 0; m < TRIPS; m++) {                // steady, rolled
@@ -91,20 +97,20 @@ __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, u64 (&acc)[
         for (int e = 0; e < R; e++) {
             const u64 xv = x[d0 + e];
 #pragma unroll
-            for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, d0 + e - r);
+            for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d0 + e - r);
         }
     }
 #pragma unroll
     for (int d = R - 1 + TRIPS * R; d < R - 1 + TRIPS * R + REM; d++) {   // steady remainder
         const u64 xv = x[d];
 #pragma unroll
-        for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, d - r);
+        for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r);
     }
 #pragma unroll
     for (int d = NTAPS; d < NTAPS - 1 + R; d++) {    // tail
         const u64 xv = x[d];
 #pragma unroll
-        for (int r = d - (NTAPS - 1); r < R; r++) fir_tap<MODE>(acc[r], xv, d - r);
+        for (int r = d - (NTAPS - 1); r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r);
     }
 }
 
@@ -209,7 +215,7 @@ enum { BAR_ROWS = 1,      // FIR warps: sample rows of the tile are in shared me
 // loop of the previous frame when the CTA owns whole streams.  The second CTA on the SM fills the pipe slots
 // this one leaves at its barriers and fill phases.
 template <int NTAPS, int SPS, int MODE>
-__global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const RxFrontArgs a) {
+__global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const __grid_constant__ RxFrontArgs a, const __grid_constant__ TapBank<NTAPS> tb) {
     static_assert(NTAPS - 1 <= QPSK_CHUNK - 2, "halo must fit in one previous tile");
     constexpr int R = 16;
     constexpr int NSYM = 512 / SPS, TILE_SYMS = QPSK_CHUNK / SPS;
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const R
 
             // matched filter: rrc_fir.c:22-28
             u64 acc[R];
-            fir_strip<NTAPS, R, MODE>(xcur - (NTAPS - 1), acc);
+            fir_strip<NTAPS, R, MODE>(xcur - (NTAPS - 1), tb.t, acc);
             // sm.out is a single tile: wait until the timing warps have taken the previous one
             if (k > 0) bar_sync(BAR_EMPTY, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
             // raw sums go to shared memory; the output gain (a double multiply behind two conversions on the

@@ -9,7 +9,7 @@
 #pragma once
 
 #include "common.cuh"
-#include "rx_front.cuh"   // c_taps2
+#include "rx_front.cuh"   // TapBank
 
 struct TxArgs {
     const uint8_t* symbols;   // [C][nsym] constellation index per symbol: (tx_bits[2k] << 1) | tx_bits[2k+1]
@@ -32,7 +32,7 @@ struct TxSmem {
 };
 
 template <int NTAPS, int SPS>
-__global__ void __launch_bounds__(256, 3) tx_kernel(const TxArgs a) {
+__global__ void __launch_bounds__(256, 3) tx_kernel(const __grid_constant__ TxArgs a, const __grid_constant__ TapBank<NTAPS> tb) {
     constexpr int R = 16, TS = QPSK_CHUNK / SPS, SPT = TS / 8;   // SPT symbols loaded per thread per tile
     static_assert(TS % 8 == 0 && (NTAPS - 1) <= QPSK_CHUNK, "tile geometry");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256, 3) tx_kernel(const TxArgs a) {
             for (int r = 0; r < R; r++) {
                 const int i = SPS * dq - r + (NTAPS - 1);
                 if (i >= 0 && i < NTAPS) {
-                    const u64 cc = *reinterpret_cast<const u64*>(&c_taps2[i]);
+                    const u64 cc = *reinterpret_cast<const u64*>(&tb.t[i]);
                     acc[r] = add2(acc[r], mul2_exact(sv, cc));
                 }
             }

