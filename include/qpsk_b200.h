@@ -3,9 +3,10 @@
  *
  * Plain C: opaque handles, plain pointers and sizes, int status returns (0 = success, negative
  * = error, text from qpsk_b200_last_error()).  A context is not thread-safe and its calls must be
- * stream-ordered; the filter taps live in one process-wide constant bank, so contexts with
- * different taps must not run concurrently from different host threads (one process per GPU is
- * the intended deployment).  No CPU fallback exists: every entry point that
+ * stream-ordered; contexts are independent of each other (taps, keystream and every other constant
+ * travel with each kernel launch, nothing is process-wide), so several contexts -- on one device
+ * or on several -- may be driven from one host thread or from one thread each.  The intended
+ * deployment is one process per GPU.  No CPU fallback exists: every entry point that
  * computes fails with QPSK_B200_ERR_CUDA when no sm_100 device is usable.
  *
  * The reference (MonsieurETM/QPSK) handles exactly one channel through file-scope singletons;
@@ -68,8 +69,11 @@ enum {                              /* cfg.flags */
     QPSK_B200_ESTIMATE_TIMING = 128,/* extension, not the reference: per frame the symbol-rate line of the squared matched-filter output,
                                        S = sum_n y_n^2 e^{-2 pi i n / CYCLES} (Oerder & Meyr), accumulated by the timing warps next to the
                                        reference's amplitude histogram; OUT_TIMING_SUM / OUT_TIMING_TAU.  The decisions do not use it */
-    QPSK_B200_RESOLVE_ROTATION = 16 /* with DECODE_FRAMES: a frame whose CRC fails is retried with its dibits turned back
+    QPSK_B200_RESOLVE_ROTATION = 16,/* with DECODE_FRAMES: a frame whose CRC fails is retried with its dibits turned back
                                        by 90, 180 and 270 degrees (the loop's phase ambiguity); first match wins */
+    QPSK_B200_NO_CHUNK = 256        /* never cut a call into frame chunks (with few channels a long call is processed as
+                                       chunks of frames so that the Costas loop of one chunk runs under the front end of
+                                       the next; results are identical either way) */
 };
 
 typedef struct {
@@ -126,7 +130,45 @@ int qpsk_b200_rx_process_device(qpsk_b200_rx *rx, const int16_t *d_pcm, int nfra
 /* PCM in host memory (pinned for best speed): copies in, runs, copies the packed dibits out
  * (h_dibits may be NULL) and returns when done. */
 int qpsk_b200_rx_process_host(qpsk_b200_rx *rx, const int16_t *h_pcm, int nframes, uint8_t *h_dibits);
+/* The same call split in two, for a continuous receiver (the reference's read loop, qpsk.c:339-354, reads the next
+ * 512 samples only after rx_frame returned): submit enqueues the copies and kernels of one batch and returns at once,
+ * wait blocks until the OLDEST submitted batch is complete (its dibits are in h_dibits).  Up to two batches may be in
+ * flight, so the host can read batch k+1 from its file or socket while the GPU works on batch k.  h_pcm and h_dibits
+ * must stay valid (and should be page-locked) until the matching wait.  After an error the context needs
+ * qpsk_b200_rx_reset(): some channels may have advanced and others not. */
+int qpsk_b200_rx_submit_host(qpsk_b200_rx *rx, const int16_t *h_pcm, int nframes, uint8_t *h_dibits);
+int qpsk_b200_rx_wait(qpsk_b200_rx *rx);
+/* measurement aid: the host<->device copies of qpsk_b200_rx_process_host (same slices, streams and events) with no
+ * kernel launched -- the copy ceiling an end-to-end rate is quoted against.  Channel state is not touched. */
+int qpsk_b200_rx_probe_copy_host(qpsk_b200_rx *rx, const int16_t *h_pcm, int nframes, uint8_t *h_scratch_out);
 int qpsk_b200_rx_sync(qpsk_b200_rx *rx);
+
+/* page-locked host memory for the buffers of the host entry points (cudaHostAlloc / cudaFreeHost) */
+int qpsk_b200_host_alloc(size_t bytes, void **out);
+int qpsk_b200_host_free(void *p);
+
+/* Continuous receiver over raw s16le PCM files, one file per channel -- the reference's on-disk format (TX_FILENAME,
+ * qpsk.h:14) and read loop (qpsk.c:339-354: 512 samples per fread, stop at the first short read), for every channel of
+ * `rx` at once.  Batches of frames_per_batch frames (<= the receiver's max_frames) are read by a few host threads
+ * into page-locked buffers while the GPU works on the previous batch; `sink` receives every completed batch in order:
+ * packed dibits uint8 [C][nframes * nsym / 4] (valid until it returns; return non-zero to stop).  Files are cut to the
+ * shortest one; a tail that does not fill a frame is ignored.  frame_size and nsym are the receiver's (512 and
+ * 512 / CYCLES). */
+typedef struct qpsk_b200_stream qpsk_b200_stream;
+typedef int (*qpsk_b200_stream_sink)(void *user, long long first_frame, int nframes, const uint8_t *dibits);
+typedef struct {
+    long long frames;        /* frames per channel processed */
+    double seconds;          /* wall time of the run */
+    double read_seconds;     /* of which: reading the files */
+    double wait_seconds;     /* of which: waiting for the GPU */
+    int readers;             /* reader threads */
+} qpsk_b200_stream_stats;
+int qpsk_b200_stream_open(qpsk_b200_rx *rx, const char *const *paths, int nchan, int frames_per_batch, int frame_size, int nsym,
+                          qpsk_b200_stream **out);
+long long qpsk_b200_stream_frames(const qpsk_b200_stream *st);
+int qpsk_b200_stream_run(qpsk_b200_stream *st, qpsk_b200_stream_sink sink, void *user, qpsk_b200_stream_stats *stats);
+int qpsk_b200_stream_close(qpsk_b200_stream *st);
+
 /* the loop's gains and limits (set_alpha/set_beta/set_min_freq/set_max_freq of costas_loop.h:26-32), all channels */
 int qpsk_b200_rx_set_loop(qpsk_b200_rx *rx, float alpha, float beta, float min_freq, float max_freq);
 /* per-channel (d_phase, d_freq) pairs, float [C][2] (set_phase/set_frequency/get_phase/get_frequency) */

@@ -20,9 +20,16 @@ class RxConfig(C.Structure):
                 ("ub_mode", C.c_int), ("flags", C.c_int), ("device", C.c_int)]
 
 
+class StreamStats(C.Structure):
+    _fields_ = [("frames", C.c_longlong), ("seconds", C.c_double), ("read_seconds", C.c_double), ("wait_seconds", C.c_double),
+                ("readers", C.c_int)]
+
+
+STREAM_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_uint8))
+
 MODE_EXACT, MODE_FAST = 0, 1
 UB_ALIAS, UB_CLAMP, UB_PHASE = 0, 1, 2
-KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL, ESTIMATE_OFFSET, ESTIMATE_TIMING = 1, 2, 4, 8, 16, 32, 64, 128
+KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL, ESTIMATE_OFFSET, ESTIMATE_TIMING, NO_CHUNK = 1, 2, 4, 8, 16, 32, 64, 128, 256
 OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK, OUT_ROTATION, OUT_OFFSET_BIN, OUT_OFFSET_HZ, OUT_TIMING_SUM, OUT_TIMING_TAU = range(14)
 
 _lib = None
@@ -44,6 +51,16 @@ def lib():
     L.qpsk_b200_rx_reset.argtypes = [C.c_void_p]
     L.qpsk_b200_rx_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     L.qpsk_b200_rx_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.qpsk_b200_rx_submit_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.qpsk_b200_rx_wait.argtypes = [C.c_void_p]
+    L.qpsk_b200_rx_probe_copy_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.qpsk_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.qpsk_b200_host_free.argtypes = [C.c_void_p]
+    L.qpsk_b200_stream_open.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.qpsk_b200_stream_frames.argtypes = [C.c_void_p]
+    L.qpsk_b200_stream_frames.restype = C.c_longlong
+    L.qpsk_b200_stream_run.argtypes = [C.c_void_p, STREAM_SINK, C.c_void_p, C.POINTER(StreamStats)]
+    L.qpsk_b200_stream_close.argtypes = [C.c_void_p]
     L.qpsk_b200_rx_sync.argtypes = [C.c_void_p]
     L.qpsk_b200_rx_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.qpsk_b200_rx_output_bytes.argtypes = [C.c_void_p, C.c_int]

@@ -27,8 +27,14 @@
 
 // points per thread = largest radix: 32 where it saves a pass through shared memory (512 = 32 x 16, 1024 = 32 x 32 inside
 // one warp, 4096 = 32 x 32 x 4, 8192 = 32 x 32 x 8).  2048 stays 16 x 16 x 8 (fewer registers, more resident warps).
+#ifndef QPSK_FFT_P4096
+#define QPSK_FFT_P4096 32
+#endif
+#ifndef QPSK_FFT_P8192
+#define QPSK_FFT_P8192 32
+#endif
 __host__ __device__ constexpr int qpsk_fft_points_per_thread(int n) {
-    return (n >= 512 && n != 2048) ? 32 : ((n >= 256) ? 16 : ((n >= 8) ? 8 : n));
+    return n >= 8192 ? QPSK_FFT_P8192 : (n >= 4096 ? QPSK_FFT_P4096 : ((n >= 512 && n != 2048) ? 32 : ((n >= 256) ? 16 : ((n >= 8) ? 8 : n))));
 }
 // radix of the stage that still has `rem` points to combine: the largest one, except that 2 P is split evenly
 // (P/4 x P/4 for P = 32) instead of ending in a radix-2 pass
@@ -70,17 +76,21 @@ inline void qpsk_fft_make_twiddles(int n, float2* tw) {
     }
 }
 
-// resident CTAs per SM the register allocation of each kernel family is capped for (tools/fft_bench.cu sweeps them)
-#ifndef QPSK_FFT_MINB_8192
-#define QPSK_FFT_MINB_8192 2
+// registers per thread each kernel family is capped at (through __launch_bounds__' resident-CTA argument);
+// tools/fft_bench.cu sweeps them
+#ifndef QPSK_FFT_REGS_P32
+#define QPSK_FFT_REGS_P32 102
 #endif
-#ifndef QPSK_FFT_MINB_P32
-#define QPSK_FFT_MINB_P32 4
+#ifndef QPSK_FFT_REGS_P16
+#define QPSK_FFT_REGS_P16 72
 #endif
-#ifndef QPSK_FFT_MINB_P16
-#define QPSK_FFT_MINB_P16 6
+#ifndef QPSK_FFT_L2_AHEAD
+#define QPSK_FFT_L2_AHEAD 1
 #endif
-#define QPSK_FFT_MINB(n, p) ((n) >= 8192 ? QPSK_FFT_MINB_8192 : ((p) >= 32 ? QPSK_FFT_MINB_P32 : ((n) >= 256 ? QPSK_FFT_MINB_P16 : 4)))
+#ifndef QPSK_FFT_TW_SMEM_MAX
+#define QPSK_FFT_TW_SMEM_MAX 4096
+#endif
+#define QPSK_FFT_MINB(threads, p) ((p) >= 32 ? 65536 / ((threads) * QPSK_FFT_REGS_P32) : ((p) >= 16 ? 65536 / ((threads) * QPSK_FFT_REGS_P16) : 4))
 
 template <int LOG2N>
 struct FftCfg {
@@ -95,8 +105,11 @@ struct FftCfg {
     static constexpr int TW = qpsk_fft_tw_count(N);
     static constexpr bool LIN = (N >= 256);                        // linear skew offsets (static_asserted per stage)
     // resident CTAs per SM the register allocation is capped for
-    static constexpr int MINB = QPSK_FFT_MINB(N, P);
-    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + sizeof(float2) * TW + sizeof(float) * 64 + sizeof(int) * 64;
+    static constexpr int MINB = QPSK_FFT_MINB(THREADS, P) > 0 ? QPSK_FFT_MINB(THREADS, P) : 1;
+    // large twiddle tables stay in global memory and are read through L1 (same latency as shared memory, and they no
+    // longer cost resident CTAs)
+    static constexpr bool TW_SMEM = (TW <= QPSK_FFT_TW_SMEM_MAX);
+    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + (TW_SMEM ? sizeof(float2) * TW : 0) + sizeof(float) * 64 + sizeof(int) * 64;
 };
 
 // Tolerance-mode arithmetic (1e-5) on packed FP32 pairs: one complex value per 64-bit register.  FADD2/FMUL2/FFMA2 take
@@ -302,7 +315,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
     if (NS > 1) {
         const int k = j % KT;
 #pragma unroll
-        for (int m = 1; m < R; m++) tw[m - 1] = stw[(m - 1) * KT + k];
+        for (int m = 1; m < R; m++) tw[m - 1] = Cfg::TW_SMEM ? stw[(m - 1) * KT + k] : __ldg(stw + (m - 1) * KT + k);
     }
 #pragma unroll
     for (int t = 0; t < NB; t++) {
@@ -427,12 +440,13 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, FPB = Cfg::FPB;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c64* sdat = reinterpret_cast<c64*>(smem_raw);
-    c64* stw = sdat + Cfg::SKEW_PTS;
-    float* red_mag = reinterpret_cast<float*>(stw + Cfg::TW);
+    c64* stw_s = sdat + Cfg::SKEW_PTS;
+    float* red_mag = reinterpret_cast<float*>(stw_s + (Cfg::TW_SMEM ? Cfg::TW : 0));
     int* red_idx = reinterpret_cast<int*>(red_mag + 64);
+    const c64* stw = Cfg::TW_SMEM ? stw_s : reinterpret_cast<const c64*>(a.tw);
 
-    for (int i = threadIdx.x; i < Cfg::TW; i += blockDim.x) stw[i] = reinterpret_cast<const c64*>(a.tw)[i];
-    if (threadIdx.x < 64) red_idx[threadIdx.x] = 0x7fffffff;
+    if (Cfg::TW_SMEM)
+        for (int i = threadIdx.x; i < Cfg::TW; i += blockDim.x) stw_s[i] = reinterpret_cast<const c64*>(a.tw)[i];
     __syncthreads();
 
     const int fl = threadIdx.x / TPF, j = threadIdx.x % TPF;
@@ -444,11 +458,26 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
         kc.bp[r] = *reinterpret_cast<const c64*>(&a.kbase[r]);
         kc.bm[r] = *reinterpret_cast<const c64*>(&a.kbase[4 + r]);
     }
+    int pass = 0;
     for (int b0 = blockIdx.x * FPB; b0 < a.nbursts; b0 += gridDim.x * FPB) {
         const int b = b0 + fl;
         const bool active = b < a.nbursts;
         // an inactive slot of the last pass recomputes the last burst; only its stores are masked
         const c64* gin = reinterpret_cast<const c64*>(a.in) + (size_t)(active ? b : a.nbursts - 1) * N;
+        // The burst this slot transforms QPSK_FFT_L2_AHEAD passes from now starts its way from HBM to L2 here: two
+        // instructions per thread and no registers, and the loads of that pass then wait for L2 instead of DRAM
+        // (waiting for stage 0's loads was the largest single stall: profiles/r02_fft4096_v1.summary.csv).
+        if (QPSK_FFT_L2_AHEAD > 0) {
+            const long long bn = (long long)b + (long long)QPSK_FFT_L2_AHEAD * gridDim.x * FPB;
+            if (bn < a.nbursts) {
+                const char* nx = reinterpret_cast<const char*>(a.in + (size_t)bn * N);
+#pragma unroll
+                for (int l = 0; l < (N * 8 / 128 + TPF - 1) / TPF; l++) {
+                    const int line = j + l * TPF;
+                    if (N * 8 / 128 >= TPF || line < N * 8 / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)line * 128));
+                }
+            }
+        }
         c64 pts[P];
         fft_stages<LOG2N, 1, true, GEN>(pts, sdat, stw, gin, j, base, a.im_sign, kc);
 
@@ -514,41 +543,47 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
 #pragma unroll
                 for (int i = 0; i < w; i++) red[i] = fmaxf(red[i], red[i + w]);
             const float lmax = red[0];
+            // per warp (or per transform when it is narrower than a warp): the maximum, then the lowest bin that holds it
             constexpr int W = (TPF < 32) ? TPF : 32;
             float g = lmax;
 #pragma unroll
             for (int off = W / 2; off > 0; off >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, off, W));
-            if (TPF > 32) {
-                const int wib = threadIdx.x >> 5;
-                if ((threadIdx.x & 31) == 0) red_mag[wib] = g;
-                __syncthreads();
-                constexpr int WPF = (TPF > 32) ? TPF / 32 : 1;
-#pragma unroll
-                for (int w = 0; w < WPF; w++) g = fmaxf(g, red_mag[fl * WPF + w]);
-            }
-            // first strict maximum: the lowest bin among the points equal to the maximum
             int cand = 0x7fffffff;
             if (lmax == g) {
 #pragma unroll
                 for (int i = 0; i < P; i++)
                     if (mg[i] == g) cand = min(cand, fft_out_index<LOG2N>(j, i));
             }
-            if (TPF <= 32) {
 #pragma unroll
-                for (int off = W / 2; off > 0; off >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, off, W));
+            for (int off = W / 2; off > 0; off >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, off, W));
+            if (TPF <= 32) {
                 if (j == 0 && active) { a.bin[b] = cand; if (a.mag2) a.mag2[b] = g * scale2; }
             } else {
-                if (cand != 0x7fffffff) atomicMin(&red_idx[fl], cand);
+                // one shared-memory hop across the warps of the transform (FPB == 1 here); the slots alternate between
+                // passes, so the only barrier is the one that also closes the pass
+                constexpr int WPF = (TPF > 32) ? TPF / 32 : 1;
+                const int wib = threadIdx.x >> 5;
+                float* rm = red_mag + 32 * (pass & 1);
+                int* ri = red_idx + 32 * (pass & 1);
+                if ((threadIdx.x & 31) == 0) { rm[wib] = g; ri[wib] = cand; }
                 __syncthreads();
-                if (j == 0) {
-                    if (active) { a.bin[b] = red_idx[fl]; if (a.mag2) a.mag2[b] = g * scale2; }
-                    red_idx[fl] = 0x7fffffff;          // the next pass's atomics come after at least one more barrier
+                if (threadIdx.x == 0 && active) {
+                    float bm = rm[0];
+                    int bi = ri[0];
+#pragma unroll
+                    for (int w = 1; w < WPF; w++) {
+                        const float om = rm[w];
+                        const int oi = ri[w];
+                        if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+                    }
+                    a.bin[b] = bi;
+                    if (a.mag2) a.mag2[b] = bm * scale2;
                 }
             }
         }
-        // the next pass's stage-0 writes must not race with this pass's last-stage reads: the last
-        // stage read shared memory before its registers were final, and every thread passed the
-        // barrier inside the previous stage's write phase; one more barrier closes the loop
-        fft_sync<TPF>();
+        // The next pass's stage-0 writes must not race with this pass's last-stage reads of shared memory.  With more than
+        // one warp per transform the estimator epilogue's barrier came after those reads; otherwise close the pass here.
+        if (GEN || TPF <= 32) fft_sync<TPF>();
+        pass++;
     }
 }

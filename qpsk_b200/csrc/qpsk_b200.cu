@@ -38,6 +38,24 @@ static int fail(int code, const char* fmt, ...) {
 
 extern "C" const char* qpsk_b200_last_error(void) { return g_err; }
 
+// for the C host files of the library (host/stream.c): one error text per thread, whoever set it
+extern "C" int qpsk_b200_stream_set_error(const char* text) {
+    snprintf(g_err, sizeof g_err, "%s", text ? text : "");
+    return 0;
+}
+
+extern "C" int qpsk_b200_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(QPSK_B200_ERR_ARG, "bad argument");
+    *out = nullptr;
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_host_free(void* p) {
+    if (p) CU(cudaFreeHost(p));
+    return QPSK_B200_OK;
+}
+
 extern "C" int qpsk_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -49,6 +67,7 @@ struct qpsk_b200_fft;
 static const double kTau = 2.0 * 3.14159265358979323846;
 
 static long long g_next_id = 0;
+#define QPSK_MAX_CHUNKS 16      // frame chunks per call (rx_plan_chunks)
 
 // the taps of a context as the kernels take them: a __grid_constant__ parameter (see TapBank, rx_front.cuh)
 template <int NTAPS>
@@ -67,7 +86,8 @@ struct qpsk_b200_rx {
     float2 rect, rot45;
     qpsk_host_loop loop;
     cudaStream_t stream;
-    cudaEvent_t ev[4];
+    cudaEvent_t ev_fr[2 * QPSK_MAX_CHUNKS], ev_lp[2 * QPSK_MAX_CHUNKS];   // around K1 / K3 of every frame chunk of the last call
+    int timed_chunks;  bool timed_loop;
     bool timed, last_fused, no_fuse;
     long long launches;
     // device state
@@ -97,9 +117,16 @@ struct qpsk_b200_rx {
     unsigned long long* d_counters;   // [2]
     int16_t* d_pcm_stage2[2];   // host path: double-buffered PCM slices (lazy)
     unsigned* d_out_stage2[2];  // host path: double-buffered transposed dibit slices
-    size_t stage_slice_bytes;
+    size_t stage_pcm_bytes, stage_out_bytes;
     cudaStream_t s_in, s_out;
-    cudaEvent_t ev_in[2], ev_cmp[2], ev_out[2];
+    cudaEvent_t ev_in[2], ev_cmp[2], ev_res[2], ev_out[2], ev_done[2];
+    unsigned long long job_seq, call_seq;   // host path: jobs and calls enqueued so far (staging buffer = seq & 1)
+    int inflight;                           // submitted host calls not yet waited for (at most 2)
+    bool needs_reset;                       // a host call failed half way
+    bool no_chunk;                          // QPSK_B200_NO_CHUNK
+    cudaStream_t s_loop;                    // the loop of frame chunk k runs here, under the front end of chunk k+1
+    cudaEvent_t ev_front;
+    int nsm, sm_clock_khz;                  // launch policy inputs, read from the device
     float* d_front_scratch; // front-end per-CTA frame scratch (lazy, grow-only)
     size_t front_scratch_bytes;
     qpsk_b200_fft* est_fft; int est_fft_n;   // estimator extension (lazy)
@@ -120,12 +147,12 @@ extern "C" void qpsk_b200_rx_default_config(qpsk_b200_rx_config* cfg) {
     cfg->ub_mode = QPSK_B200_UB_ALIAS;
 }
 
-__global__ void save_pcm_tail_kernel(const int16_t* __restrict__ pcm, int16_t* __restrict__ tail, int C, size_t row) {
-    // last 128 samples of every channel row; 16 threads x 16 bytes per channel
+__global__ void save_pcm_tail_kernel(const int16_t* __restrict__ pcm, int16_t* __restrict__ tail, int C, size_t row_stride, size_t row_len) {
+    // last 128 of the row_len samples at the start of every channel row; 16 threads x 16 bytes per channel
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int c = t >> 4, q = t & 15;
     if (c >= C) return;
-    const uint4* src = reinterpret_cast<const uint4*>(pcm + (size_t)c * row + row - QPSK_CHUNK) + q;
+    const uint4* src = reinterpret_cast<const uint4*>(pcm + (size_t)c * row_stride + row_len - QPSK_CHUNK) + q;
     reinterpret_cast<uint4*>(tail + (size_t)c * QPSK_CHUNK)[q] = *src;
 }
 
@@ -140,14 +167,19 @@ static int rx_free(qpsk_b200_rx* rx) {
                      rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, rx->d_est_bursts, rx->d_est_bins, rx->d_est_mag, rx->d_timing_t,
                      rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch };
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (auto& e : rx->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : rx->ev_fr) if (e) cudaEventDestroy(e);
+    for (auto& e : rx->ev_lp) if (e) cudaEventDestroy(e);
     for (int b = 0; b < 2; b++) {
         if (rx->ev_in[b]) cudaEventDestroy(rx->ev_in[b]);
         if (rx->ev_cmp[b]) cudaEventDestroy(rx->ev_cmp[b]);
+        if (rx->ev_res[b]) cudaEventDestroy(rx->ev_res[b]);
+        if (rx->ev_done[b]) cudaEventDestroy(rx->ev_done[b]);
         if (rx->ev_out[b]) cudaEventDestroy(rx->ev_out[b]);
     }
     if (rx->ev_k0_done) cudaEventDestroy(rx->ev_k0_done);
     if (rx->ev_call_start) cudaEventDestroy(rx->ev_call_start);
+    if (rx->ev_front) cudaEventDestroy(rx->ev_front);
+    if (rx->s_loop) cudaStreamDestroy(rx->s_loop);
     if (rx->s_k0) cudaStreamDestroy(rx->s_k0);
     if (rx->s_in) cudaStreamDestroy(rx->s_in);
     if (rx->s_out) cudaStreamDestroy(rx->s_out);
@@ -192,6 +224,11 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     memset(rx, 0, sizeof *rx);
     rx->cfg = *cfg;
     rx->no_fuse = (cfg->flags & QPSK_B200_NO_FUSE) != 0;
+    rx->no_chunk = (cfg->flags & QPSK_B200_NO_CHUNK) != 0;
+    rx->nsm = prop.multiProcessorCount;
+    rx->sm_clock_khz = 0;
+    cudaDeviceGetAttribute(&rx->sm_clock_khz, cudaDevAttrClockRate, cfg->device);      // the device's own boost clock
+    if (rx->sm_clock_khz <= 0) rx->sm_clock_khz = 1965000;
     rx->id = g_next_id++;
     rx->C = nchan;
     rx->Cpad = (nchan + QPSK_GROUP - 1) / QPSK_GROUP * QPSK_GROUP;
@@ -214,7 +251,8 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes); };
     if (cudaStreamCreateWithFlags(&rx->stream, cudaStreamNonBlocking) != cudaSuccess) e = cudaGetLastError();
-    for (auto& ev : rx->ev) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    for (auto& ev : rx->ev_fr) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+    for (auto& ev : rx->ev_lp) if (e == cudaSuccess) e = cudaEventCreate(&ev);
     alloc((void**)&rx->d_pcm_tail, Cp * QPSK_CHUNK * sizeof(int16_t));
     alloc((void**)&rx->d_phasor2[0], (QPSK_CHUNK + F * N) * sizeof(float2));
     alloc((void**)&rx->d_phasor2[1], (QPSK_CHUNK + F * N) * sizeof(float2));
@@ -222,6 +260,18 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&rx->s_k0, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_k0_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_call_start, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&rx->s_loop, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_front, cudaEventDisableTiming);
+    // the front end's per-CTA frame scratch, for the largest grid a call can ask for (every group x every frame, capped
+    // at eight waves: the policy never cuts finer than that), so nothing is allocated inside a stream-ordered call
+    if (e == cudaSuccess) {
+        long long ctas = (long long)(rx->Cpad / QPSK_GROUP) * max_frames;
+        const long long cap = (long long)(rx->Cpad / QPSK_GROUP) > 16LL * rx->nsm ? (long long)(rx->Cpad / QPSK_GROUP) : 16LL * rx->nsm;
+        if (ctas > cap) ctas = cap;
+        rx->front_scratch_bytes = (size_t)ctas * 512 * 2 * QPSK_GROUP * sizeof(float);
+        e = cudaMalloc((void**)&rx->d_front_scratch, rx->front_scratch_bytes);
+        if (e != cudaSuccess) rx->front_scratch_bytes = 0;
+    }
     alloc((void**)&rx->d_dec_ring, (F + 1) * S * Cp * sizeof(float2));
     alloc((void**)&rx->d_index_t, F * Cp * sizeof(int));
     alloc((void**)&rx->d_loop_state, Cp * sizeof(float2));
@@ -255,6 +305,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
 extern "C" int qpsk_b200_rx_reset(qpsk_b200_rx* rx) {
     if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
     CU(cudaSetDevice(rx->cfg.device));
+    CU(cudaDeviceSynchronize());                 // nothing of an earlier call may still be in flight on any stream
     const size_t Cp = rx->Cpad, S = rx->nsym;
     cudaStream_t s = rx->stream;
     CU(cudaMemsetAsync(rx->d_pcm_tail, 0, Cp * QPSK_CHUNK * sizeof(int16_t), s));
@@ -276,6 +327,8 @@ extern "C" int qpsk_b200_rx_reset(qpsk_b200_rx* rx) {
     CU(cudaStreamSynchronize(s));
     rx->slot_base = 0;
     rx->lastF = 0;
+    rx->inflight = 0;
+    rx->needs_reset = false;
     return QPSK_B200_OK;
 }
 
@@ -303,10 +356,10 @@ static int launch_frame_decode(int nbytes, const unsigned* dibits_t, unsigned* f
     return 0;
 }
 
-// ---- one process call = begin (taps, phasor table) + one or more channel slices + end ----------
-static int rx_begin_call(qpsk_b200_rx* rx, int F, cudaStream_t s) {
-    // K0: mixer phasors of this call.  If the previous call already evaluated a table for this frame count on the
-    // side stream, just wait for it; otherwise evaluate it now.
+// ---- one process call = frame chunks x channel slices; every (chunk, slice) is one RxJob ----------
+// K0: the mixer phasors of the next `F` frames (see phasor_table_kernel).  If the previous chunk already evaluated a
+// table for this frame count on the side stream, just wait for it; otherwise evaluate it now.
+static int rx_begin_chunk(qpsk_b200_rx* rx, int F, cudaStream_t s) {
     const int nxt = rx->ph_cur ^ 1;
     if (rx->ph_spec_valid && rx->ph_spec_frames == F) {
         CU(cudaStreamWaitEvent(s, rx->ev_k0_done, 0));
@@ -315,10 +368,11 @@ static int rx_begin_call(qpsk_b200_rx* rx, int F, cudaStream_t s) {
         phasor_table_kernel<<<1, QPSK_CHUNK, 0, s>>>(rx->d_phasor2[rx->ph_cur], rx->ph_cur_frames, rx->d_ph_state2 + rx->ph_cur,
                                                      rx->d_phasor2[nxt], rx->d_ph_state2 + nxt, rx->rect, F, rx->N);
         CU(cudaGetLastError());
+        rx->launches += 1;
     }
     rx->ph_cur = nxt; rx->ph_cur_frames = F; rx->ph_spec_valid = false;
-    // the table of a next call with the same frame count, evaluated on the side stream while this call runs; it
-    // overwrites the other slot, which the previous call's kernels (all enqueued before this point on `s`) still read
+    // the table of a next chunk with the same frame count, evaluated on the side stream while this one runs; it
+    // overwrites the other slot, which the previous chunk's kernels (all enqueued before this point on `s`) still read
     CU(cudaEventRecord(rx->ev_call_start, s));
     CU(cudaStreamWaitEvent(rx->s_k0, rx->ev_call_start, 0));
     phasor_table_kernel<<<1, QPSK_CHUNK, 0, rx->s_k0>>>(rx->d_phasor2[rx->ph_cur], F, rx->d_ph_state2 + rx->ph_cur,
@@ -329,6 +383,8 @@ static int rx_begin_call(qpsk_b200_rx* rx, int F, cudaStream_t s) {
     rx->launches += 1;
     return 0;
 }
+
+static void rx_end_chunk(qpsk_b200_rx* rx, int F) { rx->slot_base = (rx->slot_base + F) % rx->nslots; }
 
 __global__ void symbol_power4_kernel(const float2* __restrict__ ring, float2* __restrict__ bursts, int c_begin, int c_end, int Cpad, int nsym,
                                      int nslots, int first_slot, int n);
@@ -342,134 +398,229 @@ static int est_burst_length(const qpsk_b200_rx* rx, int F) {
     return n;
 }
 
-// channels [c0, c0 + nc) of the call; d_pcm holds exactly those rows.  c0 must be a multiple of 32.
-static int rx_run_slice(qpsk_b200_rx* rx, const int16_t* d_pcm, int c0, int nc, int F, cudaStream_t s, bool timed) {
-    const int N = rx->N;
-    RxFrontArgs fa;
-    fa.pcm = d_pcm; fa.pcm_tail = rx->d_pcm_tail; fa.phasor = rx->d_phasor2[rx->ph_cur];
-    fa.dec_ring = rx->d_dec_ring; fa.index_t = rx->d_index_t; fa.fir_dbg = rx->d_fir_dbg; fa.timing_t = rx->d_timing_t;
-    fa.C = rx->C; fa.Cpad = rx->Cpad; fa.F = F; fa.N = N; fa.chan_base = c0; fa.chan_count = nc;
-    fa.slot_base = rx->slot_base; fa.nslots = rx->nslots; fa.ub_mode = rx->cfg.ub_mode;
-    const int ngroups = (nc + QPSK_GROUP - 1) / QPSK_GROUP;
-    // enough CTAs for a few waves over the SMs: split the frames of a channel group when channels are few
-    int nsm = 148;
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, rx->cfg.device);
-    // How many frame blocks per channel group?  One block (the CTA owns whole streams) lets the Costas loop ride along
-    // in the CTA's spare warp; more blocks fill the machine when channels are few, or when the groups are an awkward
-    // number of waves (16,384 channels = 512 CTAs = 1.73 waves of 2 x nsm), at the price of the loop as its own kernel.
-    // Costs in units of one frame of one resident CTA (~83 us at 2400 baud), from profiles/r01_notes.md: the front end
-    // without the loop runs ~3 % faster, a block start costs about a third of a frame, the stand-alone loop needs
-    // max(latency of one stream at ~520 cycles per symbol, its share of 2.9 ms per 65,536 channels x 64 frames).
+// Launch policy, in units of "one frame of one resident front-end CTA".  Nothing here is a measured constant of one
+// particular box: the unit follows from the filter's arithmetic (2 CTAs share an SM's FP32 pipe at ~80 % of 32 / 64
+// complex tap-updates per clock) and the device's own SM count and clock, read at context creation.
+struct RxCostModel {
+    int slots;          // resident front-end CTAs: 2 per SM
+    double unit_us;     // one frame (512 samples x 32 channels x 127 taps) for one of two CTAs sharing an SM
+    double sym_us;      // latency of one Costas-loop symbol for one stream (~540 dependent cycles)
+    double loop_us_per_sym_chan;   // throughput cost of the stand-alone loop kernel per symbol and channel, machine-wide
+};
+static RxCostModel rx_cost_model(const qpsk_b200_rx* rx) {
+    RxCostModel m;
+    const double clk_hz = rx->sm_clock_khz * 1e3;
+    const double taps_per_clk_sm = (rx->cfg.mode == QPSK_B200_MODE_FAST ? 64.0 : 32.0) * 0.8;
+    m.slots = 2 * rx->nsm;
+    m.unit_us = 2.0 * QPSK_GROUP * 512.0 * 127.0 / (taps_per_clk_sm * clk_hz) * 1e6;
+    m.sym_us = 540.0 / clk_hz * 1e6;
+    // ~105 instructions per symbol and lane, one warp instruction per scheduler and clock, 4 schedulers per SM, ~50 % issue
+    // efficiency for a latency-bound kernel: 105 / (32 lanes x 4 x nsm x 0.5) clocks per symbol and channel
+    m.loop_us_per_sym_chan = 105.0 / (32.0 * 4.0 * rx->nsm * 0.5) / clk_hz * 1e6;
+    return m;
+}
+
+struct RxJob {
+    const int16_t* d_pcm;   // rows of channels [c0, c0 + nc), the job's F frames at the start of each row
+    size_t pcm_row;         // row stride in samples
+    int c0, nc;             // channel slice; c0 is a multiple of 32
+    int F, f_off;           // frames of this job and their position in the call (outputs are indexed by call frame)
+};
+
+// How many frame blocks per channel group?  One block (the CTA owns whole streams) lets the Costas loop ride along in
+// the CTA's spare warp; more blocks fill the machine when channels are few, or when the groups are an awkward number of
+// waves (16,384 channels = 512 CTAs = 1.73 waves of 2 x nsm), at the price of the loop as its own kernel: a block start
+// costs about a third of a frame, the front end without the loop runs ~3 % faster, the stand-alone loop needs
+// max(latency of one stream, its share of the machine).
+static int rx_frame_blocks(const qpsk_b200_rx* rx, int ngroups, int nc, int F, bool loop_overlapped) {
+    const RxCostModel m = rx_cost_model(rx);
     int fblocks = 1;
-    {
-        const int slots = 2 * nsm;
-        const double unit_us = 82.8;
-        const double loop_units = fmax((double)F * rx->nsym * 520.0 / 1965.0 / unit_us,
-                                       2900.0 / unit_us * ((double)nc * F / (65536.0 * 64.0)));
-        double best = rx->no_fuse ? 1e30 : (double)((ngroups + slots - 1) / slots) * F;
-        for (int fb = rx->no_fuse ? 1 : 2; fb <= F; fb++) {              // fb = 1 with the loop fused is `best` already
-            const int fpb = (F + fb - 1) / fb, nb = (F + fpb - 1) / fpb;
-            if (nb != fb) continue;                                     // same split as a smaller fb
-            const double waves = (double)(((long long)ngroups * nb + slots - 1) / slots);
-            const double t = waves * (fpb + 0.3) * 0.97 + loop_units;
-            if (t < best * 0.98) { best = t; fblocks = nb; }            // 2 % hysteresis in favour of fewer blocks
-        }
+    const double loop_units = loop_overlapped ? 0.0
+        : fmax((double)F * rx->nsym * m.sym_us, m.loop_us_per_sym_chan * (double)nc * F * rx->nsym) / m.unit_us;
+    double best = rx->no_fuse ? 1e30 : (double)((ngroups + m.slots - 1) / m.slots) * F;
+    for (int fb = rx->no_fuse ? 1 : 2; fb <= F; fb++) {              // fb = 1 with the loop fused is `best` already
+        const int fpb = (F + fb - 1) / fb, nb = (F + fpb - 1) / fpb;
+        if (nb != fb) continue;                                     // same split as a smaller fb
+        const double waves = (double)(((long long)ngroups * nb + m.slots - 1) / m.slots);
+        const double t = waves * (fpb + 0.3) * 0.97 + loop_units;
+        if (t < best * 0.98) { best = t; fblocks = nb; }            // 2 % hysteresis in favour of fewer blocks
     }
-    fa.frames_per_block = (F + fblocks - 1) / fblocks;
-    fblocks = (F + fa.frames_per_block - 1) / fa.frames_per_block;
-    const int grid = ngroups * fblocks;
-    // per-CTA frame scratch (512 samples x 2 components x 32 lanes of float); rewritten every frame, so it lives in L2
-    {
-        const size_t need = (size_t)grid * 512 * 2 * QPSK_GROUP * sizeof(float);
-        if (rx->front_scratch_bytes < need) {
-            CU(cudaStreamSynchronize(s));
-            if (rx->d_front_scratch) { cudaFree(rx->d_front_scratch); rx->d_front_scratch = nullptr; rx->front_scratch_bytes = 0; }
-            CU(cudaMalloc((void**)&rx->d_front_scratch, need));
-            rx->front_scratch_bytes = need;
-        }
-        fa.scratch = rx->d_front_scratch;
-    }
+    return fblocks;
+}
 
-    // K3 arguments: the Costas loop + slicer, fused into K1 when every CTA owns whole streams
-    CostasArgs ca;
-    ca.dec_ring = rx->d_dec_ring; ca.index_t = rx->d_index_t; ca.loop_state = rx->d_loop_state;
-    ca.dibits_t = rx->d_dibits_t; ca.costas_dbg = rx->d_costas_dbg; ca.track_t = rx->d_track_t;
-    ca.C = rx->C; ca.Cpad = rx->Cpad; ca.F = F; ca.nsym = rx->nsym; ca.sps = rx->sps; ca.N = N;
-    ca.c0 = c0; ca.c1 = (c0 + nc < rx->C) ? c0 + nc : rx->C;
-    ca.slot_base = rx->slot_base; ca.nslots = rx->nslots; ca.ub_mode = rx->cfg.ub_mode;
-    ca.alpha = rx->loop.alpha; ca.beta = rx->loop.beta; ca.max_freq = rx->loop.max_freq; ca.min_freq = rx->loop.min_freq;
-    ca.rot45 = rx->rot45;
-    const bool fused = (fblocks == 1) && !rx->no_fuse;
-    fa.fuse_costas = fused ? 1 : 0;
-    fa.costas = ca;
-
-    if (timed) CU(cudaEventRecord(rx->ev[0], s));
-    cudaError_t e;
-    const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
-    if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, rx->taps, grid, s) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, rx->taps, grid, s);
-    else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, rx->taps, grid, s) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, rx->taps, grid, s);
-    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
-    if (timed) CU(cudaEventRecord(rx->ev[1], s));
-
-    // carry the last 128 PCM samples of every channel (the next call's filter history)
-    const int live = ca.c1 - c0;
-    save_pcm_tail_kernel<<<(live * 16 + 255) / 256, 256, 0, s>>>(d_pcm, rx->d_pcm_tail + (size_t)c0 * QPSK_CHUNK, live, (size_t)F * N);
-    CU(cudaGetLastError());
-
-    if (timed) CU(cudaEventRecord(rx->ev[2], s));
-    if (!fused) {
-        costas_kernel<<<(live + 127) / 128, 128, 0, s>>>(ca);
-        CU(cudaGetLastError());
-        rx->launches += 1;
-    }
-    if (timed) CU(cudaEventRecord(rx->ev[3], s));
-    rx->last_fused = fused;
-
-    if (rx->d_frames_t) {   // K4: descramble -> de-interleave -> CRC16 per frame
-        int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t, rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, c0, ca.c1, rx->Cpad, F, s);
-        if (rc) return rc;
-        rx->launches += 1;
-    }
-    if (rx->est_on) {       // FFT frequency estimator on this slice's channels: 4th power -> n-point FFT -> argmax
-        const int n = est_burst_length(rx, F);
-        if (!rx->est_fft || rx->est_fft_n != n) {
-            if (rx->est_fft) { CU(cudaStreamSynchronize(s)); qpsk_b200_fft_destroy(rx->est_fft); rx->est_fft = nullptr; }
-            int rc = qpsk_b200_fft_create(n, rx->cfg.device, &rx->est_fft);
-            if (rc) return rc;
-            rx->est_fft_n = n;
-        }
-        rx->est_call_n = n;
-        dim3 grid((ca.c1 - c0 + 31) / 32, (n + 31) / 32), block(32, 8);
-        symbol_power4_kernel<<<grid, block, 0, s>>>(rx->d_dec_ring, rx->d_est_bursts, c0, ca.c1, rx->Cpad, rx->nsym, rx->nslots,
-                                                   (rx->slot_base + 1) % rx->nslots, n);
-        CU(cudaGetLastError());
-        int rc = qpsk_b200_fft_argmax_device(rx->est_fft, reinterpret_cast<const float*>(rx->d_est_bursts + (size_t)c0 * n), ca.c1 - c0,
-                                             rx->d_est_bins + c0, rx->d_est_mag + c0, s);
-        if (rc) return rc;
-        rx->launches += 2;
-    }
-    rx->launches += 2;
-    if (timed) rx->timed = true;
+static int rx_ensure_front_scratch(qpsk_b200_rx* rx, int grid) {
+    // per-CTA frame scratch (512 samples x 2 components x 32 lanes of float); rewritten every frame, so it lives in L2.
+    // Sized once for the largest grid any call can ask for (every channel group x every frame), so no allocation ever
+    // happens in the middle of a stream-ordered call.
+    const size_t need = (size_t)grid * 512 * 2 * QPSK_GROUP * sizeof(float);
+    if (rx->front_scratch_bytes >= need) return 0;
+    CU(cudaDeviceSynchronize());
+    if (rx->d_front_scratch) { cudaFree(rx->d_front_scratch); rx->d_front_scratch = nullptr; rx->front_scratch_bytes = 0; }
+    CU(cudaMalloc((void**)&rx->d_front_scratch, need));
+    rx->front_scratch_bytes = need;
     return 0;
 }
 
-static void rx_end_call(qpsk_b200_rx* rx, int F) {
-    rx->slot_base = (rx->slot_base + F) % rx->nslots;
+static CostasArgs rx_costas_args(const qpsk_b200_rx* rx, const RxJob& j) {
+    const size_t Cp = rx->Cpad, S = rx->nsym, fo = j.f_off;
+    CostasArgs ca;
+    ca.dec_ring = rx->d_dec_ring; ca.index_t = rx->d_index_t + fo * Cp; ca.loop_state = rx->d_loop_state;
+    ca.dibits_t = rx->d_dibits_t + fo * (S / 16) * Cp;
+    ca.costas_dbg = rx->d_costas_dbg ? rx->d_costas_dbg + fo * S * Cp : nullptr;
+    ca.track_t = rx->d_track_t + fo * Cp;
+    ca.C = rx->C; ca.Cpad = rx->Cpad; ca.F = j.F; ca.nsym = rx->nsym; ca.sps = rx->sps; ca.N = rx->N;
+    ca.c0 = j.c0; ca.c1 = (j.c0 + j.nc < rx->C) ? j.c0 + j.nc : rx->C;
+    ca.slot_base = rx->slot_base; ca.nslots = rx->nslots; ca.ub_mode = rx->cfg.ub_mode;
+    ca.alpha = rx->loop.alpha; ca.beta = rx->loop.beta; ca.max_freq = rx->loop.max_freq; ca.min_freq = rx->loop.min_freq;
+    ca.rot45 = rx->rot45;
+    return ca;
+}
+
+// K1 (+ the fused loop) and the PCM tail of one job on stream s.  *fused tells the caller whether K3 is still to run.
+static int rx_launch_front(qpsk_b200_rx* rx, const RxJob& j, bool loop_overlapped, cudaStream_t s, bool* fused_out, int timed_chunk = -1) {
+    const int N = rx->N;
+    const size_t Cp = rx->Cpad;
+    RxFrontArgs fa;
+    fa.pcm = j.d_pcm; fa.pcm_row = j.pcm_row; fa.pcm_tail = rx->d_pcm_tail; fa.phasor = rx->d_phasor2[rx->ph_cur];
+    fa.dec_ring = rx->d_dec_ring; fa.index_t = rx->d_index_t + (size_t)j.f_off * Cp; fa.fir_dbg = rx->d_fir_dbg;
+    fa.timing_t = rx->d_timing_t ? rx->d_timing_t + (size_t)j.f_off * Cp : nullptr;
+    fa.C = rx->C; fa.Cpad = rx->Cpad; fa.F = j.F; fa.N = N; fa.chan_base = j.c0; fa.chan_count = j.nc;
+    fa.slot_base = rx->slot_base; fa.nslots = rx->nslots; fa.ub_mode = rx->cfg.ub_mode;
+    const int ngroups = (j.nc + QPSK_GROUP - 1) / QPSK_GROUP;
+    int fblocks = rx_frame_blocks(rx, ngroups, j.nc, j.F, loop_overlapped);
+    fa.frames_per_block = (j.F + fblocks - 1) / fblocks;
+    fblocks = (j.F + fa.frames_per_block - 1) / fa.frames_per_block;
+    const int grid = ngroups * fblocks;
+    int rc = rx_ensure_front_scratch(rx, grid);      // a no-op after creation (sized for Cpad/32 x maxF CTAs)
+    if (rc) return rc;
+    fa.scratch = rx->d_front_scratch;
+    const bool fused = (fblocks == 1) && !rx->no_fuse;
+    fa.fuse_costas = fused ? 1 : 0;
+    fa.costas = rx_costas_args(rx, j);
+    cudaError_t e;
+    const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
+    if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_fr[2 * timed_chunk], s));
+    if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, rx->taps, grid, s) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, rx->taps, grid, s);
+    else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, rx->taps, grid, s) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, rx->taps, grid, s);
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
+    if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_fr[2 * timed_chunk + 1], s));
+    // carry the last 128 PCM samples of every channel (the next chunk's filter history)
+    const int live = fa.costas.c1 - j.c0;
+    save_pcm_tail_kernel<<<(live * 16 + 255) / 256, 256, 0, s>>>(j.d_pcm, rx->d_pcm_tail + (size_t)j.c0 * QPSK_CHUNK, live, j.pcm_row, (size_t)j.F * N);
+    CU(cudaGetLastError());
+    rx->launches += 2;
+    rx->last_fused = fused;
+    *fused_out = fused;
+    return 0;
+}
+
+// K3 (when it did not ride along in K1) and K4 of one job on stream s
+static int rx_launch_loop_and_decode(qpsk_b200_rx* rx, const RxJob& j, bool fused, cudaStream_t s, int timed_chunk = -1) {
+    const CostasArgs ca = rx_costas_args(rx, j);
+    const int live = ca.c1 - j.c0;
+    if (!fused) {
+        if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_lp[2 * timed_chunk], s));
+        costas_kernel<<<(live + 127) / 128, 128, 0, s>>>(ca);
+        CU(cudaGetLastError());
+        if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_lp[2 * timed_chunk + 1], s));
+        rx->launches += 1;
+    }
+    if (rx->d_frames_t) {   // K4: descramble -> de-interleave -> CRC16 per frame
+        const size_t Cp = rx->Cpad, W = rx->nsym / 16, fo = j.f_off;
+        int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t + fo * W * Cp, rx->d_frames_t + fo * W * Cp, rx->d_crc_ok_t + fo * Cp,
+                                     rx->d_rotation_t ? rx->d_rotation_t + fo * Cp : nullptr, rx->d_counters, j.c0, ca.c1, rx->Cpad, j.F, s);
+        if (rc) return rc;
+        rx->launches += 1;
+    }
+    return 0;
+}
+
+// the FFT frequency estimator over channels [c0, c1) of a call of F frames whose first frame sits in ring slot first_slot
+static int rx_launch_estimator(qpsk_b200_rx* rx, int c0, int c1, int F, int first_slot, cudaStream_t s) {
+    const int n = est_burst_length(rx, F);
+    if (!rx->est_fft || rx->est_fft_n != n) {
+        if (rx->est_fft) { CU(cudaDeviceSynchronize()); qpsk_b200_fft_destroy(rx->est_fft); rx->est_fft = nullptr; }
+        int rc = qpsk_b200_fft_create(n, rx->cfg.device, &rx->est_fft);
+        if (rc) return rc;
+        rx->est_fft_n = n;
+    }
+    rx->est_call_n = n;
+    dim3 grid((c1 - c0 + 31) / 32, (n + 31) / 32), block(32, 8);
+    symbol_power4_kernel<<<grid, block, 0, s>>>(rx->d_dec_ring, rx->d_est_bursts, c0, c1, rx->Cpad, rx->nsym, rx->nslots, first_slot, n);
+    CU(cudaGetLastError());
+    int rc = qpsk_b200_fft_argmax_device(rx->est_fft, reinterpret_cast<const float*>(rx->d_est_bursts + (size_t)c0 * n), c1 - c0,
+                                         rx->d_est_bins + c0, rx->d_est_mag + c0, s);
+    if (rc) return rc;
+    rx->launches += 2;
+    return 0;
+}
+
+// Frame chunks of a call.  With few channels the loop cannot ride along in the front end (a CTA would have to own whole
+// streams and there are too few CTAs for that), and as one kernel after the front end it is a pure latency chain:
+// 1,024 streams x 16,384 symbols x ~540 cycles = 4.7 ms behind a 2.3 ms front end.  Cutting the call into frame chunks
+// lets the loop of chunk k run on a second stream under the front end of chunks k+1.., and lets the host path copy
+// chunk k+1 in and chunk k-1 out meanwhile.  State carries between chunks exactly as between calls.
+static int rx_plan_chunks(const qpsk_b200_rx* rx, int nc, int F) {
+    if (rx->d_fir_dbg || rx->d_costas_dbg || rx->no_chunk) return F;         // debug taps are indexed by the call's frames
+    const int ngroups = (nc + QPSK_GROUP - 1) / QPSK_GROUP;
+    if (F < 32) return F;
+    if (rx_frame_blocks(rx, ngroups, nc, F, false) == 1) return F;            // the fused kernel is the better plan
+    int fc = (F + 15) / 16;
+    if (fc < 8) fc = 8;
+    return fc;
+}
+
+// The device-resident call: frame chunks on `s`, the loop of a chunked call on the loop stream.  CUDA events bracket K1
+// and K3 of every chunk (qpsk_b200_rx_last_kernel_ms sums them).
+static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, int F, cudaStream_t s) {
+    const int fc = rx_plan_chunks(rx, rx->C, F);
+    const bool chunked = fc < F;
+    const int first_slot = (rx->slot_base + 1) % rx->nslots;
+    bool loop_stream_used = false;
+    int k = 0;
+    rx->timed_loop = false;
+    for (int f0 = 0; f0 < F; f0 += fc, k++) {
+        RxJob j;
+        j.d_pcm = d_pcm + (size_t)f0 * rx->N; j.pcm_row = pcm_row; j.c0 = 0; j.nc = rx->C; j.F = (F - f0 < fc) ? F - f0 : fc; j.f_off = f0;
+        int rc = rx_begin_chunk(rx, j.F, s);
+        if (rc) return rc;
+        bool fused = false;
+        rc = rx_launch_front(rx, j, chunked, s, &fused, k);
+        if (rc) return rc;
+        cudaStream_t sl = s;
+        if (chunked && !fused) {
+            sl = rx->s_loop;
+            CU(cudaEventRecord(rx->ev_front, s));
+            CU(cudaStreamWaitEvent(sl, rx->ev_front, 0));
+            loop_stream_used = true;
+        }
+        if (!fused) rx->timed_loop = true;
+        rc = rx_launch_loop_and_decode(rx, j, fused, sl, k);
+        if (rc) return rc;
+        rx_end_chunk(rx, j.F);
+    }
+    rx->timed_chunks = k;
+    if (loop_stream_used) {
+        CU(cudaEventRecord(rx->ev_front, rx->s_loop));
+        CU(cudaStreamWaitEvent(s, rx->ev_front, 0));
+    }
+    if (rx->est_on) {
+        int rc = rx_launch_estimator(rx, 0, rx->C, F, first_slot, s);
+        if (rc) return rc;
+    }
     rx->lastF = F;
+    rx->timed = true;
+    return 0;
 }
 
 extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pcm, int nframes, void* cuda_stream) {
     if (!rx || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
     if (nframes < 1 || nframes > rx->maxF) return fail(QPSK_B200_ERR_ARG, "nframes %d outside 1..%d", nframes, rx->maxF);
     if ((reinterpret_cast<uintptr_t>(d_pcm) & 15) != 0) return fail(QPSK_B200_ERR_ARG, "d_pcm must be 16-byte aligned");
+    if (rx->inflight > 0) return fail(QPSK_B200_ERR_STATE, "%d submitted host call(s) not waited for (qpsk_b200_rx_wait)", rx->inflight);
     CU(cudaSetDevice(rx->cfg.device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : rx->stream;
-    int rc = rx_begin_call(rx, nframes, s);
-    if (rc) return rc;
-    rc = rx_run_slice(rx, d_pcm, 0, rx->C, nframes, s, true);
-    if (rc) return rc;
-    rx_end_call(rx, nframes);
-    return QPSK_B200_OK;
+    return rx_run_call(rx, d_pcm, (size_t)nframes * rx->N, nframes, s);
 }
 
 extern "C" int qpsk_b200_rx_set_loop(qpsk_b200_rx* rx, float alpha, float beta, float min_freq, float max_freq) {
@@ -504,10 +655,18 @@ extern "C" int qpsk_b200_rx_sync(qpsk_b200_rx* rx) {
 extern "C" long long qpsk_b200_rx_launch_count(const qpsk_b200_rx* rx) { return rx ? rx->launches : 0; }
 
 extern "C" int qpsk_b200_rx_last_kernel_ms(qpsk_b200_rx* rx, float* front_ms, float* costas_ms) {
-    if (!rx || !rx->timed) return fail(QPSK_B200_ERR_STATE, "no process call yet");
-    CU(cudaEventSynchronize(rx->ev[3]));
-    if (front_ms) CU(cudaEventElapsedTime(front_ms, rx->ev[0], rx->ev[1]));
-    if (costas_ms) CU(cudaEventElapsedTime(costas_ms, rx->ev[2], rx->ev[3]));
+    if (!rx || !rx->timed) return fail(QPSK_B200_ERR_STATE, "no device-resident process call yet");
+    CU(cudaSetDevice(rx->cfg.device));
+    CU(cudaDeviceSynchronize());
+    float fr = 0.0f, lp = 0.0f;
+    for (int k = 0; k < rx->timed_chunks; k++) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, rx->ev_fr[2 * k], rx->ev_fr[2 * k + 1]));
+        fr += ms;
+        if (rx->timed_loop) { CU(cudaEventElapsedTime(&ms, rx->ev_lp[2 * k], rx->ev_lp[2 * k + 1])); lp += ms; }
+    }
+    if (front_ms) *front_ms = fr;
+    if (costas_ms) *costas_ms = lp;
     return QPSK_B200_OK;
 }
 
@@ -649,74 +808,176 @@ extern "C" int qpsk_b200_rx_device_dibits(qpsk_b200_rx* rx, const uint32_t** d_p
     return QPSK_B200_OK;
 }
 
-// Host-buffer entry point.  Large calls are cut into channel slices that flow through three streams
-// (H2D copy, compute, transposed D2H copy of the packed dibits) with double-buffered staging, so the
-// PCIe transfers of one slice overlap the kernels of its neighbours.
-extern "C" int qpsk_b200_rx_process_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, uint8_t* h_dibits) {
+// Host-buffer entry points.  A call is cut into jobs -- channel slices when channels are plentiful (each slice keeps
+// the fused kernel busy for several waves), frame chunks when they are few (rx_plan_chunks) -- that flow through the
+// copy-in stream, the compute stream(s) and the copy-out stream with double-buffered staging, so the PCIe transfers of
+// one job overlap the kernels of its neighbours.  qpsk_b200_rx_submit_host only enqueues (up to two calls may be in
+// flight: reading the next batch of PCM overlaps the GPU working on this one); qpsk_b200_rx_wait completes the oldest.
+static int rx_host_streams(qpsk_b200_rx* rx) {
+    if (rx->s_in) return 0;
+    CU(cudaStreamCreateWithFlags(&rx->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&rx->s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CU(cudaEventCreateWithFlags(&rx->ev_in[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&rx->ev_cmp[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&rx->ev_res[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&rx->ev_out[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&rx->ev_done[b], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// after an error in the middle of a host call: nothing may still read or write the caller's buffers on return
+static int rx_host_abort(qpsk_b200_rx* rx, int rc) {
+    cudaStreamSynchronize(rx->s_in);
+    cudaStreamSynchronize(rx->stream);
+    cudaStreamSynchronize(rx->s_loop);
+    cudaStreamSynchronize(rx->s_out);
+    rx->inflight = 0;
+    rx->needs_reset = true;      // some jobs of the call ran, others did not: channel state is inconsistent
+    return rc;
+}
+
+static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, uint8_t* h_dibits, bool copy_only) {
     if (!rx || !h_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
     if (nframes < 1 || nframes > rx->maxF) return fail(QPSK_B200_ERR_ARG, "nframes %d outside 1..%d", nframes, rx->maxF);
+    if (rx->needs_reset) return fail(QPSK_B200_ERR_STATE, "an earlier call failed half way: qpsk_b200_rx_reset() first");
+    if (rx->inflight >= 2) return fail(QPSK_B200_ERR_STATE, "two calls already in flight: qpsk_b200_rx_wait() first");
     CU(cudaSetDevice(rx->cfg.device));
-    const int F = nframes, N = rx->N, C = rx->C;
+    int rc = rx_host_streams(rx);
+    if (rc) return rc;
+    const int F = nframes, N = rx->N, C = rx->C, W = rx->nsym / 16;
     const size_t row_bytes = (size_t)F * N * sizeof(int16_t);
-    const int words = F * (rx->nsym / 16);
-    // slice size: ~256 MiB of PCM, a whole number of 32-channel groups, at least 4 SM-waves of CTAs when possible
-    int slice = (int)((256ull << 20) / row_bytes);
-    slice = slice / QPSK_GROUP * QPSK_GROUP;
-    if (slice < 4 * 148 * QPSK_GROUP) slice = 4 * 148 * QPSK_GROUP;
+    // channel slices: ~256 MiB of PCM, whole 32-channel groups, at least 4 waves of fused CTAs (2 per SM) when possible
+    int slice = (int)((256ull << 20) / row_bytes) / QPSK_GROUP * QPSK_GROUP;
+    const int slice_floor = 4 * 2 * rx->nsm * QPSK_GROUP / 2;
+    if (slice < slice_floor) slice = slice_floor;
     if (slice > C) slice = C;
     const int nslices = (C + slice - 1) / slice;
-    if (rx->stage_slice_bytes < (size_t)slice * row_bytes) {
+    const int fc = nslices == 1 ? rx_plan_chunks(rx, C, F) : F;
+    const bool chunked = fc < F;
+    // staging for one job: slice x fc frames of PCM in, slice x fc frames of packed dibits out
+    const size_t pcm_job = (size_t)slice * fc * N * sizeof(int16_t), out_job = (size_t)slice * fc * W * sizeof(unsigned);
+    if (rx->stage_pcm_bytes < pcm_job || rx->stage_out_bytes < out_job) {
+        CU(cudaDeviceSynchronize());
         for (int b = 0; b < 2; b++) {
             if (rx->d_pcm_stage2[b]) { cudaFree(rx->d_pcm_stage2[b]); rx->d_pcm_stage2[b] = nullptr; }
             if (rx->d_out_stage2[b]) { cudaFree(rx->d_out_stage2[b]); rx->d_out_stage2[b] = nullptr; }
         }
-        rx->stage_slice_bytes = 0;
+        rx->stage_pcm_bytes = rx->stage_out_bytes = 0;
         for (int b = 0; b < 2; b++) {
-            CU(cudaMalloc((void**)&rx->d_pcm_stage2[b], (size_t)slice * rx->maxF * N * sizeof(int16_t)));
-            CU(cudaMalloc((void**)&rx->d_out_stage2[b], (size_t)slice * rx->maxF * (rx->nsym / 16) * sizeof(unsigned)));
+            CU(cudaMalloc((void**)&rx->d_pcm_stage2[b], pcm_job));
+            CU(cudaMalloc((void**)&rx->d_out_stage2[b], out_job));
         }
-        rx->stage_slice_bytes = (size_t)slice * rx->maxF * N * sizeof(int16_t);
-    }
-    if (!rx->s_in) {
-        CU(cudaStreamCreateWithFlags(&rx->s_in, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&rx->s_out, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
-            CU(cudaEventCreateWithFlags(&rx->ev_in[b], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&rx->ev_cmp[b], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&rx->ev_out[b], cudaEventDisableTiming));
-        }
+        rx->stage_pcm_bytes = pcm_job; rx->stage_out_bytes = out_job;
     }
     cudaStream_t sc = rx->stream;
-    int rc = rx_begin_call(rx, F, sc);
-    if (rc) return rc;
-    for (int i = 0; i < nslices; i++) {
-        const int b = i & 1, c0 = i * slice, nc = (c0 + slice <= C) ? slice : C - c0;
-        // staging buffer b was last read by the kernels of slice i-2
-        if (i >= 2) CU(cudaStreamWaitEvent(rx->s_in, rx->ev_cmp[b], 0));
-        CU(cudaMemcpyAsync(rx->d_pcm_stage2[b], h_pcm + (size_t)c0 * F * N, (size_t)nc * row_bytes, cudaMemcpyHostToDevice, rx->s_in));
-        CU(cudaEventRecord(rx->ev_in[b], rx->s_in));
-        CU(cudaStreamWaitEvent(sc, rx->ev_in[b], 0));
-        rc = rx_run_slice(rx, rx->d_pcm_stage2[b], c0, nc, F, sc, i == 0);
-        if (rc) return rc;
-        if (h_dibits) {
-            // output buffer b was last drained by the D2H copy of slice i-2
-            if (i >= 2) CU(cudaStreamWaitEvent(sc, rx->ev_out[b], 0));
-            dim3 grid((nc + 31) / 32, (words + 31) / 32), block(32, 8);
-            transpose_to_channel_major<unsigned><<<grid, block, 0, sc>>>(rx->d_dibits_t + c0, rx->d_out_stage2[b], words, nc, rx->Cpad);
-            CU(cudaGetLastError());
-            rx->launches += 1;
+    const int first_slot = (rx->slot_base + 1) % rx->nslots;
+    bool loop_stream_used = false;
+    for (int f0 = 0; f0 < F; f0 += fc) {
+        const int Fj = (F - f0 < fc) ? F - f0 : fc;
+        if (!copy_only) {
+            rc = rx_begin_chunk(rx, Fj, sc);
+            if (rc) return rx_host_abort(rx, rc);
         }
-        CU(cudaEventRecord(rx->ev_cmp[b], sc));
-        if (h_dibits) {
-            CU(cudaStreamWaitEvent(rx->s_out, rx->ev_cmp[b], 0));
-            CU(cudaMemcpyAsync(h_dibits + (size_t)c0 * words * 4, rx->d_out_stage2[b], (size_t)nc * words * 4, cudaMemcpyDeviceToHost, rx->s_out));
-            CU(cudaEventRecord(rx->ev_out[b], rx->s_out));
+        for (int i = 0; i < nslices; i++) {
+            const unsigned long long seq = rx->job_seq++;
+            const int b = (int)(seq & 1), c0 = i * slice, nc = (c0 + slice <= C) ? slice : C - c0;
+            // PCM staging buffer b was last read by the front end of job seq-2
+            if (seq >= 2) CU(cudaStreamWaitEvent(rx->s_in, rx->ev_cmp[b], 0));
+            cudaError_t e;
+            if (!chunked) e = cudaMemcpyAsync(rx->d_pcm_stage2[b], h_pcm + (size_t)c0 * F * N, (size_t)nc * row_bytes, cudaMemcpyHostToDevice, rx->s_in);
+            else e = cudaMemcpy2DAsync(rx->d_pcm_stage2[b], (size_t)Fj * N * 2, h_pcm + (size_t)c0 * F * N + (size_t)f0 * N, row_bytes,
+                                       (size_t)Fj * N * 2, nc, cudaMemcpyHostToDevice, rx->s_in);
+            if (e != cudaSuccess) return rx_host_abort(rx, fail(QPSK_B200_ERR_CUDA, "PCM upload failed: %s", cudaGetErrorString(e)));
+            CU(cudaEventRecord(rx->ev_in[b], rx->s_in));
+            CU(cudaStreamWaitEvent(sc, rx->ev_in[b], 0));
+            RxJob j;
+            j.d_pcm = rx->d_pcm_stage2[b]; j.pcm_row = (size_t)Fj * N; j.c0 = c0; j.nc = nc; j.F = Fj; j.f_off = f0;
+            cudaStream_t sr = sc;                               // the stream the job's results appear on
+            if (!copy_only) {
+                bool fused = false;
+                rc = rx_launch_front(rx, j, chunked, sc, &fused);
+                if (rc) return rx_host_abort(rx, rc);
+                CU(cudaEventRecord(rx->ev_cmp[b], sc));         // the PCM staging buffer is free again
+                if (chunked && !fused) {
+                    sr = rx->s_loop;
+                    CU(cudaStreamWaitEvent(sr, rx->ev_cmp[b], 0));
+                    loop_stream_used = true;
+                }
+                rc = rx_launch_loop_and_decode(rx, j, fused, sr);
+                if (rc) return rx_host_abort(rx, rc);
+            } else {
+                CU(cudaEventRecord(rx->ev_cmp[b], sc));
+            }
+            if (h_dibits) {
+                // output staging buffer b was last drained by the D2H copy of job seq-2
+                if (seq >= 2) CU(cudaStreamWaitEvent(sr, rx->ev_out[b], 0));
+                const int words = Fj * W;
+                if (!copy_only) {
+                    dim3 grid((nc + 31) / 32, (words + 31) / 32), block(32, 8);
+                    transpose_to_channel_major<unsigned><<<grid, block, 0, sr>>>(rx->d_dibits_t + (size_t)f0 * W * rx->Cpad + c0, rx->d_out_stage2[b], words, nc, rx->Cpad);
+                    CU(cudaGetLastError());
+                    rx->launches += 1;
+                }
+                CU(cudaEventRecord(rx->ev_res[b], sr));
+                CU(cudaStreamWaitEvent(rx->s_out, rx->ev_res[b], 0));
+                uint8_t* dst = h_dibits + ((size_t)c0 * F * W + (size_t)f0 * W) * 4;
+                if (!chunked) e = cudaMemcpyAsync(dst, rx->d_out_stage2[b], (size_t)nc * words * 4, cudaMemcpyDeviceToHost, rx->s_out);
+                else e = cudaMemcpy2DAsync(dst, (size_t)F * W * 4, rx->d_out_stage2[b], (size_t)words * 4, (size_t)words * 4, nc, cudaMemcpyDeviceToHost, rx->s_out);
+                if (e != cudaSuccess) return rx_host_abort(rx, fail(QPSK_B200_ERR_CUDA, "dibit download failed: %s", cudaGetErrorString(e)));
+                CU(cudaEventRecord(rx->ev_out[b], rx->s_out));
+            }
         }
+        if (!copy_only) rx_end_chunk(rx, Fj);
     }
-    rx_end_call(rx, F);
-    CU(cudaStreamSynchronize(sc));
-    CU(cudaStreamSynchronize(rx->s_out));
+    if (loop_stream_used) {                                     // the compute stream joins the loop stream at the end of the call
+        CU(cudaEventRecord(rx->ev_front, rx->s_loop));
+        CU(cudaStreamWaitEvent(sc, rx->ev_front, 0));
+    }
+    if (rx->est_on && !copy_only) {
+        rc = rx_launch_estimator(rx, 0, C, F, first_slot, sc);
+        if (rc) return rx_host_abort(rx, rc);
+    }
+    // completion of this call = its last compute work and its last copy out
+    const int slot = (int)(rx->call_seq++ & 1);
+    CU(cudaEventRecord(rx->ev_front, sc));
+    CU(cudaStreamWaitEvent(rx->s_out, rx->ev_front, 0));
+    CU(cudaEventRecord(rx->ev_done[slot], rx->s_out));
+    rx->inflight += 1;
+    if (!copy_only) rx->lastF = F;
     return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, uint8_t* h_dibits) {
+    return rx_submit_host(rx, h_pcm, nframes, h_dibits, false);
+}
+
+extern "C" int qpsk_b200_rx_wait(qpsk_b200_rx* rx) {
+    if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
+    if (rx->inflight <= 0) return QPSK_B200_OK;
+    CU(cudaSetDevice(rx->cfg.device));
+    const int slot = (int)((rx->call_seq - (unsigned long long)rx->inflight) & 1);      // the oldest call in flight
+    cudaError_t e = cudaEventSynchronize(rx->ev_done[slot]);
+    if (e != cudaSuccess) return rx_host_abort(rx, fail(QPSK_B200_ERR_CUDA, "waiting for a submitted call failed: %s", cudaGetErrorString(e)));
+    rx->inflight -= 1;
+    return QPSK_B200_OK;
+}
+
+extern "C" int qpsk_b200_rx_process_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, uint8_t* h_dibits) {
+    if (rx && rx->inflight > 0) return fail(QPSK_B200_ERR_STATE, "%d submitted call(s) not waited for (qpsk_b200_rx_wait)", rx->inflight);
+    int rc = rx_submit_host(rx, h_pcm, nframes, h_dibits, false);
+    if (rc) return rc;
+    return qpsk_b200_rx_wait(rx);
+}
+
+// Measurement aid: exactly the host<->device traffic of qpsk_b200_rx_process_host -- same slices, same streams, same
+// events -- with no kernel launched, so the end-to-end rate can be quoted against the copy ceiling of the same run.
+extern "C" int qpsk_b200_rx_probe_copy_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, uint8_t* h_scratch_out) {
+    if (rx && rx->inflight > 0) return fail(QPSK_B200_ERR_STATE, "%d submitted call(s) not waited for (qpsk_b200_rx_wait)", rx->inflight);
+    int rc = rx_submit_host(rx, h_pcm, nframes, h_scratch_out, true);
+    if (rc) return rc;
+    return qpsk_b200_rx_wait(rx);
 }
 
 // =============================================================================================

@@ -115,7 +115,8 @@ __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, const float
 }
 
 struct RxFrontArgs {
-    const int16_t* pcm;        // [C][F*N] s16 PCM, channel-major
+    const int16_t* pcm;        // [C][pcm_row] s16 PCM, channel-major; the F*N samples of this launch start each row
+    size_t pcm_row;            // row stride in samples (>= F*N: a frame chunk of a longer call, or a staged slice)
     const int16_t* pcm_tail;   // [C][QPSK_CHUNK] the 128 samples before frame 0 (zeros at stream start)
     const float2*  phasor;     // [QPSK_CHUNK + F*N] from phasor_table_kernel
     float2* dec_ring;          // [nslots][nsym][Cpad] decimated symbols, channel-fastest
@@ -240,8 +241,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
 
     if (w < 8) {
         // =================================== FIR warps ===================================
-        const size_t row = (size_t)a.F * N;
-        const int16_t* pcm_row = a.pcm + (size_t)(chl - a.chan_base) * row;
+        const int16_t* pcm_row = a.pcm + (size_t)(chl - a.chan_base) * a.pcm_row;
         const int strip = w * R;                     // this thread's 16 samples inside a tile
         u64* xrow = &sm.x[lane][0];
         u64* xcur = xrow + QPSK_CHUNK + strip;

@@ -13,7 +13,8 @@ from . import _capi as capi
 
 class Receiver:
     def __init__(self, nchan, max_frames, rs=2400.0, mode=capi.MODE_EXACT, ub_mode=capi.UB_ALIAS,
-                 keep_fir=False, keep_symbols=False, decode_frames=False, no_fuse=False, resolve_rotation=False, slice_diagonal=False, estimate_offset=False, estimate_timing=False, device=0, loop_bw=None, center=1500.0):
+                 keep_fir=False, keep_symbols=False, decode_frames=False, no_fuse=False, resolve_rotation=False, slice_diagonal=False, estimate_offset=False, estimate_timing=False, device=0, loop_bw=None, center=1500.0,
+                 no_chunk=False):
         self.L = capi.lib()
         cfg = capi.RxConfig()
         self.L.qpsk_b200_rx_default_config(C.byref(cfg))
@@ -24,7 +25,8 @@ class Receiver:
         cfg.flags = ((capi.KEEP_FIR if keep_fir else 0) | (capi.KEEP_SYMBOLS if keep_symbols else 0)
                      | (capi.DECODE_FRAMES if decode_frames else 0) | (capi.NO_FUSE if no_fuse else 0)
                      | (capi.RESOLVE_ROTATION if resolve_rotation else 0) | (capi.SLICE_DIAGONAL if slice_diagonal else 0)
-                     | (capi.ESTIMATE_OFFSET if estimate_offset else 0) | (capi.ESTIMATE_TIMING if estimate_timing else 0))
+                     | (capi.ESTIMATE_OFFSET if estimate_offset else 0) | (capi.ESTIMATE_TIMING if estimate_timing else 0)
+                     | (capi.NO_CHUNK if no_chunk else 0))
         cfg.device = device
         if loop_bw is not None:
             cfg.loop_bw = loop_bw
@@ -72,6 +74,18 @@ class Receiver:
                                                     out.ctypes.data_as(C.c_void_p) if want_dibits else None))
         self.last_frames = F
         return out
+
+    def submit(self, pcm, out):
+        """Asynchronous rx_frames: enqueue one batch (pcm int16 [C, F*frame_size], out uint8 [C, F*nsym/4], both C-contiguous
+        and alive until the matching wait(); page-locked buffers overlap best).  Up to two batches may be in flight."""
+        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and out.dtype == np.uint8 and out.flags.c_contiguous
+        F = pcm.shape[1] // self.frame_size
+        capi.check(self.L.qpsk_b200_rx_submit_host(self.h, pcm.ctypes.data_as(C.c_void_p), F, out.ctypes.data_as(C.c_void_p)))
+        self.last_frames = F
+
+    def wait(self):
+        """Block until the oldest submitted batch is complete."""
+        capi.check(self.L.qpsk_b200_rx_wait(self.h))
 
     def read(self, what):
         F, Cn, S, N = self.last_frames, self.nchan, self.nsym, self.frame_size

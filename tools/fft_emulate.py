@@ -10,7 +10,12 @@ with numpy.fft.  It proves the structure; the arithmetic itself is checked on th
 import numpy as np
 
 
+P_BIG = {4096: 32, 8192: 32}      # QPSK_FFT_P4096 / QPSK_FFT_P8192
+
+
 def ppt(n):
+    if n in P_BIG:
+        return P_BIG[n]
     return 32 if (n >= 512 and n != 2048) else (16 if n >= 256 else (8 if n >= 8 else n))
 
 
@@ -118,6 +123,13 @@ def main():
     for K in range(32):
         assert abs(w32_table(K) - np.exp(-2j * np.pi * K / 32)) < 1e-12, K
     rng = np.random.default_rng(0)
+    for pbig in (16, 32):
+        P_BIG[4096] = P_BIG[8192] = pbig
+        for n in (4096, 8192):
+            x = rng.normal(size=n) + 1j * rng.normal(size=n)
+            err = np.max(np.abs(emulate(n, x) - np.fft.fft(x))) / np.max(np.abs(np.fft.fft(x)))
+            assert err < 1e-10, (n, pbig, err)
+            print("n = %5d  P = %d ok" % (n, pbig))
     for lg in range(1, 14):
         n = 1 << lg
         x = rng.normal(size=n) + 1j * rng.normal(size=n)
