@@ -15,6 +15,7 @@ def declared_functions():
         text = open(path).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         text = re.sub(r"//[^\n]*", "", text)
+        text = re.sub(r"^typedef[^;]*\(\s*\*[^;]*;", "", text, flags=re.M)   # function-pointer typedefs
         for m in re.finditer(r"^[A-Za-z_][\w\s\*]*?\b(\w+)\s*\([^;{]*\)\s*;", text, flags=re.M):
             if m.group(1) not in ("defined",):
                 names.append((os.path.basename(path), m.group(1)))
