@@ -292,6 +292,11 @@ int qpsk_b200_tx_symbols_host(qpsk_b200_tx *tx, const float *h_symbols, int nsym
  * +-rs/8.  h_bin (may be NULL) receives the raw argmax bins. */
 int qpsk_b200_rx_estimate_offset(qpsk_b200_rx *rx, int log2n, float *h_offset_hz, int32_t *h_bin);
 
+/* measurement aid: the FP32 pipe's own ceiling on `device`, in complex tap-updates per second machine-wide (one rounded
+ * multiply + one rounded add per component, rrc_fir.c:22-26), for the exact (FMUL2 + FADD2, fused = 0) or the fast
+ * (FFMA2, fused = 1) formulation of the filters -- the denominator of the FP32 roofline bench.py reports */
+int qpsk_b200_probe_fp32(int device, int fused, double *tap_updates_per_s, float *kernel_ms);
+
 /* test hook: the device NCO (the restated glibc sinf/cosf the Costas kernel uses) evaluated over n host floats */
 int qpsk_b200_debug_nco(const float *h_in, float *h_sin, float *h_cos, int n, int device);
 

@@ -70,6 +70,7 @@ def lib():
     L.qpsk_b200_rx_launch_count.restype = C.c_longlong
     L.qpsk_b200_rx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.qpsk_b200_rx_estimate_offset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.qpsk_b200_probe_fp32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     _bind_fir(L)
     _bind_fft(L)
     _bind_bits(L)
@@ -77,6 +78,13 @@ def lib():
     _bind_channel(L)
     _lib = L
     return L
+
+
+def probe_fp32(device=0, fused=False):
+    """Measured FP32-pipe ceiling of the device: complex tap-updates per second (exact = FMUL2+FADD2, fused = FFMA2)."""
+    rate, ms = C.c_double(), C.c_float()
+    check(lib().qpsk_b200_probe_fp32(device, 1 if fused else 0, C.byref(rate), C.byref(ms)))
+    return rate.value
 
 
 def check(rc):

@@ -17,6 +17,7 @@
 #include "fft.cuh"
 #include "bits.cuh"
 #include "tx.cuh"
+#include "probe.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -1853,5 +1854,52 @@ extern "C" int qpsk_b200_rx_estimate_offset(qpsk_b200_rx* rx, int log2n, float* 
     }
     delete[] hb;
     rx->launches += 2;
+    return QPSK_B200_OK;
+}
+
+// =============================================================================================
+// measurement aid: the FP32 pipe's own ceiling on this device (csrc/probe.cuh)
+// =============================================================================================
+extern "C" int qpsk_b200_probe_fp32(int device, int fused, double* tap_updates_per_s, float* kernel_ms) {
+    if (!tap_updates_per_s) return fail(QPSK_B200_ERR_ARG, "null argument");
+    int rc = check_device(device);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int threads = 256, grid = prop.multiProcessorCount * 4, iters = 2000;
+    float2 hx[1024];
+    float ht[QPSK_PROBE_TAPS];
+    for (int i = 0; i < 1024; i++) hx[i] = make_float2(0.001f * (i % 97) - 0.04f, 0.002f * (i % 89) - 0.08f);
+    for (int i = 0; i < QPSK_PROBE_TAPS; i++) ht[i] = 0.01f * (i % 13) - 0.05f;
+    DevBuf x, t, o;
+    CU(cudaMalloc(&x.p, sizeof hx));
+    CU(cudaMalloc(&t.p, sizeof ht));
+    CU(cudaMalloc(&o.p, (size_t)grid * threads * QPSK_PROBE_R * sizeof(float2)));
+    CU(cudaMemcpy(x.p, hx, sizeof hx, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t.p, ht, sizeof ht, cudaMemcpyHostToDevice));
+    cudaStream_t s;
+    CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    cudaError_t e = cudaSuccess;
+    for (int rep = 0; rep < 6 && e == cudaSuccess; rep++) {          // rep 0 is the warm-up
+        cudaEventRecord(e0, s);
+        if (fused) fp32_pipe_probe_kernel<1><<<grid, threads, 0, s>>>((const float2*)x.p, (const float*)t.p, (float2*)o.p, rep ? iters : 10);
+        else       fp32_pipe_probe_kernel<0><<<grid, threads, 0, s>>>((const float2*)x.p, (const float*)t.p, (float2*)o.p, rep ? iters : 10);
+        e = cudaGetLastError();
+        cudaEventRecord(e1, s);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(s);
+    if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "FP32 pipe probe failed: %s", cudaGetErrorString(e));
+    *tap_updates_per_s = (double)grid * threads * (double)iters * QPSK_PROBE_TAPS * QPSK_PROBE_R / (best * 1e-3);
+    if (kernel_ms) *kernel_ms = best;
     return QPSK_B200_OK;
 }
