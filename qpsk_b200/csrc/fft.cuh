@@ -26,30 +26,53 @@
 #include "common.cuh"
 
 // points per thread = largest radix: 32 where it saves a pass through shared memory (512 = 32 x 16, 1024 = 32 x 32 inside
-// one warp, 4096 = 32 x 32 x 4, 8192 = 32 x 32 x 8).  2048 stays 16 x 16 x 8 (fewer registers, more resident warps).
+// one warp).  2048, 4096 and 8192 take 64 points per thread (2048 = 64 x 32 inside one warp, 4096 = 64 x 64, 8192 = 64 x 64 x 2):
+// one crossing of shared memory instead of two for 2048 and 4096, and every thread has its 64 loads in flight at once.
+#ifndef QPSK_FFT_P2048
+#define QPSK_FFT_P2048 64
+#endif
 #ifndef QPSK_FFT_P4096
-#define QPSK_FFT_P4096 32
+#define QPSK_FFT_P4096 64
 #endif
 #ifndef QPSK_FFT_P8192
-#define QPSK_FFT_P8192 32
+#define QPSK_FFT_P8192 64
 #endif
 __host__ __device__ constexpr int qpsk_fft_points_per_thread(int n) {
-    return n >= 8192 ? QPSK_FFT_P8192 : (n >= 4096 ? QPSK_FFT_P4096 : ((n >= 512 && n != 2048) ? 32 : ((n >= 256) ? 16 : ((n >= 8) ? 8 : n))));
+    return n >= 8192 ? QPSK_FFT_P8192 : (n >= 4096 ? QPSK_FFT_P4096 : (n == 2048 ? QPSK_FFT_P2048 : ((n >= 512) ? 32 : ((n >= 256) ? 16 : ((n >= 8) ? 8 : n)))));
 }
 // radix of the stage that still has `rem` points to combine: the largest one, except that 2 P is split evenly
-// (P/4 x P/4 for P = 32) instead of ending in a radix-2 pass
+// (P/4 x P/4) for P = 32 instead of ending in a radix-2 pass; P = 64 keeps 64 x 2 (the radix-2 pass is the cheap one)
 __host__ __device__ constexpr int qpsk_fft_radix(int rem, int p) {
-    return (p >= 32 && rem == 2 * p) ? p / 4 : (rem >= p ? p : rem);
+    return (p == 32 && rem == 2 * p) ? p / 4 : (rem >= p ? p : rem);
 }
-// entries per twiddle index m of the stage (ns, r) of an n-point transform with tpf threads: a remainder stage whose
-// sub-transform length exceeds the thread count keeps only the first tpf columns (the rest are constant multiples)
-__host__ __device__ constexpr int qpsk_fft_tw_cols(int ns, int tpf) { return ns < tpf ? ns : tpf; }
+// entries per twiddle index m of the stage (ns, r) of an n-point transform with tpf threads of p points: a remainder
+// stage whose sub-transform length exceeds the thread count keeps only the first tpf columns (the rest are constant
+// multiples: powers of W32, so only for p <= 32; p = 64 keeps whole rows)
+__host__ __device__ constexpr int qpsk_fft_tw_cols(int ns, int tpf, int p) { return (ns < tpf || p > 32) ? ns : tpf; }
+// p = 64: the twiddles of the first crossing are applied by the producer, to the outputs of stage 0 as they are stored
+// (output q of butterfly jj, which stage 1 reads as input r' = jj R R' / n of its butterfly q, takes w^(q r')): the loads
+// and multiplies then overlap the tail of the first 64-point DFT instead of sitting between the barrier and the second.
+// That stage's table is laid out [q - 1][r'], (ns - 1) x r entries.
+#ifndef QPSK_FFT_TW_ON_STORE
+#define QPSK_FFT_TW_ON_STORE 0      // measured slower on B200 (4096: 0.60 -> 0.55 of HBM; registers hit the cap): off
+#endif
+__host__ __device__ constexpr bool qpsk_fft_tw_on_store(int ns, int p) { return QPSK_FFT_TW_ON_STORE && p >= 64 && ns == p; }
+// p = 64: the 63 twiddles a thread needs for a radix-64 stage, z^m with z = w^k, come from 14 table entries, z^(8a) and
+// z^b (a, b = 1..7), as z^(8a + b) = z^(8a) z^b: the whole 64 x 64 table (32 KB) does not fit what six resident CTAs
+// leave of the L1, and 63 L2 round trips per thread and burst were the kernel's largest stall; 14 x 64 entries (7 KB) do fit.
+__host__ __device__ constexpr bool qpsk_fft_tw_two_level(int ns, int r, int p) { return p >= 64 && ns == 64 && r == 64 && !qpsk_fft_tw_on_store(ns, p); }
+// ... and the single twiddle of a final radix-2 stage, w^(j + t tpf), is w^j times a compile-time power of W64
+__host__ __device__ constexpr bool qpsk_fft_tw_fact64(int ns, int r, int tpf, int p) { return p >= 64 && r == 2 && ns > tpf && (2 * ns) / tpf == 64; }
+__host__ __device__ constexpr int qpsk_fft_tw_entries(int ns, int r, int tpf, int p) {
+    return ns <= 1 ? 0 : (qpsk_fft_tw_on_store(ns, p) ? (ns - 1) * r : (qpsk_fft_tw_two_level(ns, r, p) ? 14 * 64
+                        : (qpsk_fft_tw_fact64(ns, r, tpf, p) ? tpf : (r - 1) * qpsk_fft_tw_cols(ns, tpf, p))));
+}
 __host__ __device__ constexpr int qpsk_fft_tw_count(int n) {
     const int p = qpsk_fft_points_per_thread(n), tpf = n / p;
     int ns = 1, tot = 0;
     while (ns < n) {
         const int r = qpsk_fft_radix(n / ns, p);
-        if (ns > 1) tot += (r - 1) * qpsk_fft_tw_cols(ns, tpf);
+        tot += qpsk_fft_tw_entries(ns, r, tpf, p);
         ns *= r;
     }
     return tot > 0 ? tot : 1;
@@ -64,8 +87,21 @@ inline void qpsk_fft_make_twiddles(int n, float2* tw) {
     int pos = 0;
     for (int ns = 1; ns < n;) {
         const int r = qpsk_fft_radix(n / ns, p);
-        if (ns > 1) {
-            const int cols = qpsk_fft_tw_cols(ns, tpf);
+        if (qpsk_fft_tw_on_store(ns, p)) {
+            for (int q = 1; q < ns; q++)
+                for (int k = 0; k < r; k++) {
+                    const double ang = 2.0 * 3.14159265358979323846 * (double)q * (double)k / ((double)ns * (double)r);
+                    tw[pos++] = make_float2((float)cos(ang), (float)(-sin(ang)));
+                }
+        } else if (qpsk_fft_tw_two_level(ns, r, p)) {
+            for (int i = 0; i < 14; i++)
+                for (int k = 0; k < 64; k++) {
+                    const int e = (i < 7) ? 8 * (i + 1) : (i - 6);
+                    const double ang = 2.0 * 3.14159265358979323846 * (double)e * (double)k / ((double)ns * (double)r);
+                    tw[pos++] = make_float2((float)cos(ang), (float)(-sin(ang)));
+                }
+        } else if (ns > 1) {
+            const int cols = qpsk_fft_tw_fact64(ns, r, tpf, p) ? tpf : qpsk_fft_tw_cols(ns, tpf, p);
             for (int m = 1; m < r; m++)
                 for (int k = 0; k < cols; k++) {
                     const double ang = 2.0 * 3.14159265358979323846 * (double)m * (double)k / ((double)ns * (double)r);
@@ -84,32 +120,42 @@ inline void qpsk_fft_make_twiddles(int n, float2* tw) {
 #ifndef QPSK_FFT_REGS_P16
 #define QPSK_FFT_REGS_P16 72
 #endif
+#ifndef QPSK_FFT_REGS_P64
+#define QPSK_FFT_REGS_P64 168
+#endif
 #ifndef QPSK_FFT_L2_AHEAD
 #define QPSK_FFT_L2_AHEAD 1
 #endif
 #ifndef QPSK_FFT_TW_SMEM_MAX
 #define QPSK_FFT_TW_SMEM_MAX 4096
 #endif
-#define QPSK_FFT_MINB(threads, p) ((p) >= 32 ? 65536 / ((threads) * QPSK_FFT_REGS_P32) : ((p) >= 16 ? 65536 / ((threads) * QPSK_FFT_REGS_P16) : 4))
+#define QPSK_FFT_MINB(threads, p) ((p) >= 64 ? 65536 / ((threads) * QPSK_FFT_REGS_P64) : (p) >= 32 ? 65536 / ((threads) * QPSK_FFT_REGS_P32) : ((p) >= 16 ? 65536 / ((threads) * QPSK_FFT_REGS_P16) : 4))
 
 template <int LOG2N>
 struct FftCfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int P = qpsk_fft_points_per_thread(N);
     static constexpr int TPF = N / P;                              // threads per transform
-    static constexpr int THREADS = (TPF >= 128) ? TPF : 128;
+    // a transform wider than a warp is a CTA of its own where that leaves >= 64 threads (its barriers are then plain
+    // __syncthreads: barriers named per transform inside a larger CTA measured 25 % slower at n = 4096)
+    static constexpr int THREADS = (P >= 64 && TPF >= 64) ? TPF : ((TPF >= 128) ? TPF : 128);
     static constexpr int FPB = THREADS / TPF;                      // transforms per CTA pass
     static constexpr int PTS = FPB * N;
-    static constexpr int SKEW = (P >= 32) ? 32 : 16;               // one pad slot per SKEW points: unit-stride and stride-P accesses are conflict-free
-    static constexpr int SKEW_PTS = PTS + PTS / SKEW;              // float2 elements
+    static constexpr int SKEW = (P >= 64) ? 64 : ((P >= 32) ? 32 : 16);   // one pad slot per SKEW points: unit-stride and stride-P accesses are conflict-free
+    static constexpr int PADW = (P >= 64) ? 2 : 1;                 // pad slots per SKEW points (two = 16 bytes: rows stay aligned for bulk copies and 128-bit stores)
+    static constexpr int SKEW_PTS = PTS + PADW * (PTS / SKEW);     // float2 elements
+    // 64 points per thread: the burst comes in through the bulk-copy engine (cp.async.bulk, one 512-byte row per thread,
+    // completion on an mbarrier) straight into the skewed layout of the work buffer, issued as soon as the previous
+    // burst's last stage has read the buffer, so the transfer runs under that stage's arithmetic and the epilogue
+    static constexpr bool TMA_IN = (P >= 64);
     static constexpr int TW = qpsk_fft_tw_count(N);
     static constexpr bool LIN = (N >= 256);                        // linear skew offsets (static_asserted per stage)
     // resident CTAs per SM the register allocation is capped for
     static constexpr int MINB = QPSK_FFT_MINB(THREADS, P) > 0 ? QPSK_FFT_MINB(THREADS, P) : 1;
     // large twiddle tables stay in global memory and are read through L1 (same latency as shared memory, and they no
     // longer cost resident CTAs)
-    static constexpr bool TW_SMEM = (TW <= QPSK_FFT_TW_SMEM_MAX);
-    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + (TW_SMEM ? sizeof(float2) * TW : 0) + sizeof(float) * 64 + sizeof(int) * 64;
+    static constexpr bool TW_SMEM = (TW <= QPSK_FFT_TW_SMEM_MAX) && (P < 64);
+    static constexpr size_t SMEM = sizeof(float2) * SKEW_PTS + (TW_SMEM ? sizeof(float2) * TW : 0) + sizeof(float) * 64 + sizeof(int) * 64 + 8 * 8;
 };
 
 // Tolerance-mode arithmetic (1e-5) on packed FP32 pairs: one complex value per 64-bit register.  FADD2/FMUL2/FFMA2 take
@@ -148,13 +194,18 @@ __host__ __device__ constexpr float qpsk_sin32(int k) { return qpsk_cos32(k - 8)
 struct FftConsts {
     c64 bp[4];     // (c, s)
     c64 bm[4];     // (c, -s)
+    c64 bp64[4];   // the same for the odd powers of W64: (cos, sin)(2 pi r / 64), r = 1, 3, 5, 7 (used by the 64-point DFT only)
+    c64 bm64[4];
 };
 // the host fills FftArgs::kbase with (c, s) x 4 then (c, -s) x 4; arriving as kernel arguments the pairs are whole
 // 64-bit uniform-register operands, opaque to the optimiser (which would otherwise fold them back into immediates)
-inline void fft_consts_host(float2 (&kb)[8]) {
+inline void fft_consts_host(float2 (&kb)[16]) {
     for (int r = 1; r <= 4; r++) {
         kb[r - 1] = make_float2(qpsk_cos32(r), qpsk_sin32(r));
         kb[4 + r - 1] = make_float2(qpsk_cos32(r), -qpsk_sin32(r));
+        const double ang = 2.0 * 3.14159265358979323846 * (double)(2 * r - 1) / 64.0;
+        kb[8 + r - 1] = make_float2((float)cos(ang), (float)sin(ang));
+        kb[12 + r - 1] = make_float2((float)cos(ang), (float)(-sin(ang)));
     }
 }
 // a * W, W = SGN * (SW ? swap(base) : base)
@@ -190,6 +241,30 @@ __device__ __forceinline__ c64 cmul_w32(c64 v, const FftConsts& kc) {
         else if constexpr (q == 1) return cmul_base<0, -1>(v, kc.bp[i]);   // (-c, -s)
         else if constexpr (q == 2) return cmul_base<1, 1>(v, kc.bm[i]);    // (-s,  c)
         else return cmul_base<0, 1>(v, kc.bp[i]);                          // ( c,  s)
+    }
+}
+
+// v * W64^K: even powers are powers of W32, odd ones use the second constant set the same way
+template <int K>
+__device__ __forceinline__ c64 cmul_w64(c64 v, const FftConsts& kc) {
+    constexpr int k = K & 63;
+    if constexpr ((k & 1) == 0) {
+        return cmul_w32<k / 2>(v, kc);
+    } else {
+        constexpr int q = k / 16, r = k % 16;
+        if constexpr (r < 8) {                        // W64^r = (c, -s); times (-i)^q
+            constexpr int i = (r - 1) / 2;
+            if constexpr (q == 0) return cmul_base<0, 1>(v, kc.bm64[i]);
+            else if constexpr (q == 1) return cmul_base<1, -1>(v, kc.bp64[i]);
+            else if constexpr (q == 2) return cmul_base<0, -1>(v, kc.bm64[i]);
+            else return cmul_base<1, 1>(v, kc.bp64[i]);
+        } else {                                      // W64^r = (s', -c') with (c', s') the pair of 16 - r
+            constexpr int i = (16 - r - 1) / 2;
+            if constexpr (q == 0) return cmul_base<1, -1>(v, kc.bm64[i]);
+            else if constexpr (q == 1) return cmul_base<0, -1>(v, kc.bp64[i]);
+            else if constexpr (q == 2) return cmul_base<1, 1>(v, kc.bm64[i]);
+            else return cmul_base<0, 1>(v, kc.bp64[i]);
+        }
     }
 }
 
@@ -268,20 +343,89 @@ __device__ __forceinline__ void dft_small<32>(c64 (&v)[32], const FftConsts& kc)
     }
 }
 
+template <int N1, int K2>
+__device__ __forceinline__ void dft64_twiddle_row(c64 (&a)[8][8], const FftConsts& kc) {
+    if constexpr (K2 < 8) {
+        a[N1][K2] = cmul_w64<N1 * K2>(a[N1][K2], kc);
+        dft64_twiddle_row<N1, K2 + 1>(a, kc);
+    }
+}
+template <int N1>
+__device__ __forceinline__ void dft64_twiddle(c64 (&a)[8][8], const FftConsts& kc) {
+    if constexpr (N1 < 8) {
+        dft64_twiddle_row<N1, 1>(a, kc);
+        dft64_twiddle<N1 + 1>(a, kc);
+    }
+}
+template <>
+__device__ __forceinline__ void dft_small<64>(c64 (&v)[64], const FftConsts& kc) {
+    // 64 = 8 x 8 with n = n1 + 8 n2, k = 8 k1 + k2:  W64^(n k) = W8^(n2 k2) W64^(n1 k2) W8^(n1 k1)
+    c64 a[8][8];
+#pragma unroll
+    for (int n1 = 0; n1 < 8; n1++) {
+        c64 t[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) t[n2] = v[n1 + 8 * n2];
+        dft_small<8>(t, kc);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) a[n1][k2] = t[k2];
+    }
+    dft64_twiddle<1>(a, kc);
+#pragma unroll
+    for (int k2 = 0; k2 < 8; k2++) {
+        c64 t[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) t[n1] = a[n1][k2];
+        dft_small<8>(t, kc);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) v[8 * k1 + k2] = t[k1];
+    }
+}
+
 template <int SKEW>
-__host__ __device__ constexpr int fft_skew(int i) { return i + i / SKEW; }
+__host__ __device__ constexpr int fft_skew(int i) { return i + (SKEW >= 64 ? 2 : 1) * (i / SKEW); }
 
 // Offset of a compile-time displacement c from a per-thread base whose skewed address is already known:
 // skew(base + c) = skew(base) + fft_off(c), provided the low parts never carry into another pad slot
 // (proved per stage at compile time by fft_stage_linear_ok).
 template <int SKEW>
-__host__ __device__ constexpr int fft_off(int c) { return c + c / SKEW; }
+__host__ __device__ constexpr int fft_off(int c) { return c + (SKEW >= 64 ? 2 : 1) * (c / SKEW); }
+
+// ---- bulk-copy engine + mbarrier (the burst's way into shared memory for the 64-points-per-thread kernels)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    asm volatile("{\n .reg .pred p;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra LAB_DONE;\n bra LAB_WAIT;\n LAB_DONE:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// what a thread needs to fetch its row of the transform's next burst
+struct FftFeed {
+    unsigned long long* bar;    // the transform's mbarrier
+    c64* dst;                   // this thread's 64-point row in the work buffer
+    const c64* next_src;        // its source row in the next burst, nullptr when there is none
+    int parity;                 // phase of the current burst
+};
+__device__ __forceinline__ void fft_feed_issue(const FftFeed& fd, const c64* src) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the buffer's earlier generic-proxy accesses come first
+    mbar_arrive_expect_tx(fd.bar, 64 * 8);
+    bulk_copy_g2s(fd.dst, src, 64 * 8, fd.bar);
+}
 
 // the threads of one transform exchange data between passes: a warp-level barrier is enough when a transform lives
 // inside one warp (n / points-per-thread <= 32)
-template <int TPF>
-__device__ __forceinline__ void fft_sync() {
+template <int TPF, int THREADS>
+__device__ __forceinline__ void fft_sync(int fl) {
     if (TPF <= 32) __syncwarp();
+    else if (TPF < THREADS) asm volatile("bar.sync %0, %1;" ::"r"(fl + 1), "n"(TPF) : "memory");      // the transform's own warps only
     else __syncthreads();
 }
 
@@ -294,28 +438,56 @@ struct FftArgs {
     int nbursts;
     float im_sign;         // +1 forward, -1 inverse (inverse = conj(FFT(conj(x))))
     float scale;           // 1/N forward (fft.c:105-107), 1 inverse (fft.c:122-128)
-    float2 kbase[8];       // (cos, sin) and (cos, -sin) of 2 pi r / 32, r = 1..4, see FftConsts
+    float2 kbase[16];      // (cos, sin) and (cos, -sin) of 2 pi r / 32, r = 1..4, then of 2 pi r / 64, r = 1, 3, 5, 7: see FftConsts
 };
 
 // One Stockham stage for the P points a thread owns: radix R, sub-transform length NS already done.
 // GEN: the general entry points (inverse through conjugation); the estimator instantiation loads plain.
 template <int LOG2N, int R, int NS, bool FIRST, bool LAST, bool GEN>
-__device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw, const c64* gin, int j, int base, float imsgn,
-                                          const FftConsts& kc) {
+__device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw, const c64* gin, int j, int base, int fl, float imsgn,
+                                          const FftConsts& kc, const FftFeed& fd) {
     using Cfg = FftCfg<LOG2N>;
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R, S = Cfg::SKEW;   // NB butterflies per thread
     constexpr int STRIDE = N / R;
-    constexpr int KT = qpsk_fft_tw_cols(NS, TPF);        // twiddle columns of this stage
-    constexpr bool FACT = LAST && NS > TPF;              // w^(m k), k = j + t TPF  =  table[m][j] * W_P^(m t)
+    constexpr int KT = qpsk_fft_tw_cols(NS, TPF, P);     // twiddle columns of this stage
+    constexpr bool FACT = LAST && NS > TPF && P <= 32;   // w^(m k), k = j + t TPF  =  table[m][j] * W_P^(m t)
+    constexpr bool FACT64 = qpsk_fft_tw_fact64(NS, R, TPF, P);      // the same for a radix-2 remainder stage of the 64-point kernels
+    constexpr bool TW2L = qpsk_fft_tw_two_level(NS, R, P);          // z^(8a + b) = z^(8a) z^b from 14 entries per thread
+    constexpr bool PERBF = NS > TPF && !FACT && !FACT64; // whole rows in the table: butterfly t reads column j + t TPF
+    constexpr bool PRETW = qpsk_fft_tw_on_store(NS, P);  // this stage's inputs were twiddled by their producer
+    constexpr bool TWOUT = FIRST && !LAST && qpsk_fft_tw_on_store(R, P);   // ... and this is that producer
+    constexpr int RNEXT = LAST ? 1 : qpsk_fft_radix(N / (NS * R), P);
+    static_assert(!TWOUT || (NB == 1 && NS == 1 && (N / RNEXT) % R == 0), "twiddle-on-store assumes one first-stage butterfly per thread");
+    constexpr bool PRELOAD = NS > 1 && !PRETW && !PERBF && !TW2L && NB > 1; // the same R - 1 twiddles serve every butterfly of the thread
+    constexpr bool SMEM_IN = !FIRST || Cfg::TMA_IN;      // inputs come from the work buffer
+    constexpr bool RELEASE = LAST && Cfg::TMA_IN;        // the last reader of the buffer hands it to the next burst's copy
     static_assert(LAST || NS <= TPF, "only a remainder stage may have more sub-transform columns than threads");
     static_assert(!FACT || (N / TPF == P && 32 % P == 0), "factored twiddles assume n / tpf == P, a divisor of 32");
 
     const c64* rd = sdat + fft_skew<S>(base + j);
-    c64 tw[(NS > 1) ? R - 1 : 1];
-    if (NS > 1) {
-        const int k = j % KT;
+    constexpr int KTE = FACT64 ? TPF : KT;
+    const c64* twp = stw + ((PERBF || FACT64) ? j : j % KT);
+    c64 tw[PRELOAD ? R - 1 : 1];
+    c64 tw2[TW2L ? 14 : 1];
+    if (TW2L) {
 #pragma unroll
-        for (int m = 1; m < R; m++) tw[m - 1] = Cfg::TW_SMEM ? stw[(m - 1) * KT + k] : __ldg(stw + (m - 1) * KT + k);
+        for (int i = 0; i < 14; i++) tw2[i] = Cfg::TW_SMEM ? stw[i * 64 + j % 64] : __ldg(stw + i * 64 + j % 64);
+    }
+    if (PRELOAD) {
+#pragma unroll
+        for (int m = 1; m < R; m++) tw[m - 1] = Cfg::TW_SMEM ? twp[(m - 1) * KTE] : __ldg(twp + (m - 1) * KTE);
+    }
+    if (FIRST && Cfg::TMA_IN) mbar_wait(fd.bar, fd.parity);       // the burst has landed
+    if (RELEASE) {
+        // all of the thread's inputs first, so that the buffer can be given away before the arithmetic starts
+#pragma unroll
+        for (int t = 0; t < NB; t++)
+#pragma unroll
+            for (int r = 0; r < R; r++) pts[t * R + r] = rd[fft_off<S>(t * TPF + r * STRIDE)];
+#pragma unroll
+        for (int i = 0; i < P; i++) asm volatile("" ::"l"(pts[i]));      // the loads have completed ...
+        fft_sync<TPF, Cfg::THREADS>(fl);                                 // ... in every thread of the transform
+        if (fd.next_src != nullptr) fft_feed_issue(fd, fd.next_src);
     }
 #pragma unroll
     for (int t = 0; t < NB; t++) {
@@ -323,22 +495,45 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int c = t * TPF + r * STRIDE;          // butterfly j + t TPF, input r
-            if (FIRST) {
+            if (RELEASE) {
+                v[r] = pts[t * R + r];
+            } else if (!SMEM_IN) {
                 v[r] = gin[j + c];
-                if (GEN) v[r] = cconj_if(v[r], imsgn);    // inverse = conj(FFT(conj x))
             } else if (Cfg::LIN) {
                 v[r] = rd[fft_off<S>(c)];
             } else {
                 v[r] = sdat[fft_skew<S>(base + j + c)];
             }
+            if (FIRST && GEN) v[r] = cconj_if(v[r], imsgn);    // inverse = conj(FFT(conj x))
         }
-        if (NS > 1) {
+        if (TW2L) {
 #pragma unroll
             for (int m = 1; m < R; m++) {
-                v[m] = cmul(v[m], tw[m - 1]);
+                if (m / 8 > 0) v[m] = cmul(v[m], tw2[m / 8 - 1]);
+                if (m % 8 > 0) v[m] = cmul(v[m], tw2[7 + m % 8 - 1]);
+            }
+        } else if (NS > 1 && !PRETW) {
+#pragma unroll
+            for (int m = 1; m < R; m++) {
+                c64 w;
+                if (PRELOAD) w = tw[m - 1];
+                else w = Cfg::TW_SMEM ? twp[(m - 1) * KTE + (PERBF ? t * TPF : 0)] : __ldg(twp + (m - 1) * KTE + (PERBF ? t * TPF : 0));
+                v[m] = cmul(v[m], w);
+                if (FACT64 && t > 0) {
+                    switch (t & 63) {
+#define QPSK_W64_CASE(K) case K: v[m] = cmul_w64<K>(v[m], kc); break;
+                        QPSK_W64_CASE(1) QPSK_W64_CASE(2) QPSK_W64_CASE(3) QPSK_W64_CASE(4) QPSK_W64_CASE(5) QPSK_W64_CASE(6) QPSK_W64_CASE(7)
+                        QPSK_W64_CASE(8) QPSK_W64_CASE(9) QPSK_W64_CASE(10) QPSK_W64_CASE(11) QPSK_W64_CASE(12) QPSK_W64_CASE(13) QPSK_W64_CASE(14)
+                        QPSK_W64_CASE(15) QPSK_W64_CASE(16) QPSK_W64_CASE(17) QPSK_W64_CASE(18) QPSK_W64_CASE(19) QPSK_W64_CASE(20) QPSK_W64_CASE(21)
+                        QPSK_W64_CASE(22) QPSK_W64_CASE(23) QPSK_W64_CASE(24) QPSK_W64_CASE(25) QPSK_W64_CASE(26) QPSK_W64_CASE(27) QPSK_W64_CASE(28)
+                        QPSK_W64_CASE(29) QPSK_W64_CASE(30) QPSK_W64_CASE(31)
+#undef QPSK_W64_CASE
+                        default: break;
+                    }
+                }
                 if (FACT && t > 0) {
                     // W_P^(m t) as a power of W32
-                    switch ((m * t * (32 / P)) & 31) {
+                    switch ((m * t * (32 / (P <= 32 ? P : 32))) & 31) {
 #define QPSK_W32_CASE(K) case K: v[m] = cmul_w32<K>(v[m], kc); break;
                         QPSK_W32_CASE(1) QPSK_W32_CASE(2) QPSK_W32_CASE(3) QPSK_W32_CASE(4) QPSK_W32_CASE(5) QPSK_W32_CASE(6) QPSK_W32_CASE(7)
                         QPSK_W32_CASE(8) QPSK_W32_CASE(9) QPSK_W32_CASE(10) QPSK_W32_CASE(11) QPSK_W32_CASE(12) QPSK_W32_CASE(13) QPSK_W32_CASE(14)
@@ -352,24 +547,37 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
             }
         }
         dft_small<R>(v, kc);
+        if (TWOUT) {
+            // output q of butterfly j is input r' = j R RNEXT / N of the next stage's butterfly q: times w^(q r'), table [q - 1][r']
+            const c64* two = stw + (j * (R * RNEXT)) / N;
+#pragma unroll
+            for (int q = 1; q < R; q++) v[q] = cmul(v[q], Cfg::TW_SMEM ? two[(q - 1) * RNEXT] : __ldg(two + (q - 1) * RNEXT));
+        }
 #pragma unroll
         for (int q = 0; q < R; q++) pts[t * R + q] = v[q];
     }
     if (!LAST) {
-        if (!FIRST) fft_sync<TPF>();                 // everyone has read this stage's inputs
+        if (SMEM_IN) fft_sync<TPF, Cfg::THREADS>(fl);  // everyone has read this stage's inputs
         // butterfly jj = j + t TPF writes o + q NS, o = (jj / NS) NS R + jj % NS
         const int dyn = (NS == 1) ? j * R : (j / NS) * NS * R + (j % NS);
         c64* wr = sdat + fft_skew<S>(base + dyn);
 #pragma unroll
         for (int t = 0; t < NB; t++) {
+            if (NS == 1 && Cfg::PADW == 2 && Cfg::LIN) {
+                // the butterfly's R outputs are contiguous and 16-byte aligned: 128-bit stores, two points each
 #pragma unroll
-            for (int q = 0; q < R; q++) {
-                const int c = t * TPF * R + q * NS;
-                if (Cfg::LIN) wr[fft_off<S>(c)] = pts[t * R + q];
-                else sdat[fft_skew<S>(base + dyn + c)] = pts[t * R + q];
+                for (int q = 0; q < R; q += 2)
+                    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(smem_u32(wr + fft_off<S>(t * TPF * R + q))), "l"(pts[t * R + q]), "l"(pts[t * R + q + 1]) : "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < R; q++) {
+                    const int c = t * TPF * R + q * NS;
+                    if (Cfg::LIN) wr[fft_off<S>(c)] = pts[t * R + q];
+                    else sdat[fft_skew<S>(base + dyn + c)] = pts[t * R + q];
+                }
             }
         }
-        fft_sync<TPF>();
+        fft_sync<TPF, Cfg::THREADS>(fl);
     }
 }
 
@@ -380,7 +588,7 @@ __host__ __device__ constexpr bool fft_stage_linear_ok() {
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R, S = Cfg::SKEW;
     if (!Cfg::LIN) return true;
     if ((Cfg::N % S) != 0) return false;                               // transform bases are multiples of S
-    if (!FIRST) {                                                      // reads: base + j + c
+    if (!FIRST || Cfg::TMA_IN) {                                       // reads: base + j + c
         for (int t = 0; t < NB; t++)
             for (int r = 0; r < R; r++) {
                 const int c = t * TPF + r * (N / R);
@@ -402,17 +610,17 @@ __host__ __device__ constexpr bool fft_stage_linear_ok() {
 }
 
 template <int LOG2N, int NS, bool FIRST, bool GEN>
-__device__ __forceinline__ void fft_stages(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw, const c64* gin, int j, int base, float imsgn,
-                                           const FftConsts& kc) {
+__device__ __forceinline__ void fft_stages(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw, const c64* gin, int j, int base, int fl, float imsgn,
+                                           const FftConsts& kc, const FftFeed& fd) {
     constexpr int N = FftCfg<LOG2N>::N;
     constexpr int REM = N / NS;
     constexpr int RMAX = FftCfg<LOG2N>::P;
     constexpr int R = qpsk_fft_radix(REM, RMAX);
     constexpr bool LAST = (NS * R == N);
     static_assert(fft_stage_linear_ok<LOG2N, R, NS, FIRST, LAST>(), "skewed shared-memory offsets of this stage are not linear");
-    fft_stage<LOG2N, R, NS, FIRST, LAST, GEN>(pts, sdat, stw, gin, j, base, imsgn, kc);
+    fft_stage<LOG2N, R, NS, FIRST, LAST, GEN>(pts, sdat, stw, gin, j, base, fl, imsgn, kc, fd);
     if constexpr (!LAST)
-        fft_stages<LOG2N, NS * R, false, GEN>(pts, sdat, stw + (NS > 1 ? (R - 1) * qpsk_fft_tw_cols(NS, FftCfg<LOG2N>::TPF) : 0), gin, j, base, imsgn, kc);
+        fft_stages<LOG2N, NS * R, false, GEN>(pts, sdat, stw + qpsk_fft_tw_entries(NS, R, FftCfg<LOG2N>::TPF, FftCfg<LOG2N>::P), gin, j, base, fl, imsgn, kc, fd);
 }
 
 // output index of pts[i] after the last stage (radix RLAST, sub-transform length NSL = N / RLAST)
@@ -457,6 +665,21 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
     for (int r = 0; r < 4; r++) {
         kc.bp[r] = *reinterpret_cast<const c64*>(&a.kbase[r]);
         kc.bm[r] = *reinterpret_cast<const c64*>(&a.kbase[4 + r]);
+        kc.bp64[r] = *reinterpret_cast<const c64*>(&a.kbase[8 + r]);
+        kc.bm64[r] = *reinterpret_cast<const c64*>(&a.kbase[12 + r]);
+    }
+    constexpr int WPF = (TPF > 32) ? TPF / 32 : 1;      // warps per transform
+    const int wib = threadIdx.x >> 5;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(red_idx + 64) + fl;      // one per transform of the CTA
+    FftFeed fd;
+    fd.bar = mbar; fd.dst = sdat + fft_skew<Cfg::SKEW>(base + j * 64); fd.next_src = nullptr; fd.parity = 0;
+    if (Cfg::TMA_IN) {
+        if (j == 0) mbar_init(mbar, TPF);                // every thread of the transform arrives once per burst, with its row
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+        const int bfirst = blockIdx.x * FPB + fl;
+        if (blockIdx.x * FPB < a.nbursts)
+            fft_feed_issue(fd, reinterpret_cast<const c64*>(a.in) + (size_t)(bfirst < a.nbursts ? bfirst : a.nbursts - 1) * N + j * 64);
     }
     int pass = 0;
     for (int b0 = blockIdx.x * FPB; b0 < a.nbursts; b0 += gridDim.x * FPB) {
@@ -464,10 +687,16 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
         const bool active = b < a.nbursts;
         // an inactive slot of the last pass recomputes the last burst; only its stores are masked
         const c64* gin = reinterpret_cast<const c64*>(a.in) + (size_t)(active ? b : a.nbursts - 1) * N;
+        if (Cfg::TMA_IN) {
+            const long long bn0 = (long long)b0 + (long long)gridDim.x * FPB;
+            const long long bn = bn0 + fl;
+            fd.next_src = bn0 < a.nbursts ? reinterpret_cast<const c64*>(a.in) + (size_t)(bn < a.nbursts ? bn : a.nbursts - 1) * N + j * 64 : nullptr;
+            fd.parity = pass & 1;
+        }
         // The burst this slot transforms QPSK_FFT_L2_AHEAD passes from now starts its way from HBM to L2 here: two
         // instructions per thread and no registers, and the loads of that pass then wait for L2 instead of DRAM
         // (waiting for stage 0's loads was the largest single stall: profiles/r02_fft4096_v1.summary.csv).
-        if (QPSK_FFT_L2_AHEAD > 0) {
+        if (QPSK_FFT_L2_AHEAD > 0 && !Cfg::TMA_IN) {
             const long long bn = (long long)b + (long long)QPSK_FFT_L2_AHEAD * gridDim.x * FPB;
             if (bn < a.nbursts) {
                 const char* nx = reinterpret_cast<const char*>(a.in + (size_t)bn * N);
@@ -479,7 +708,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
             }
         }
         c64 pts[P];
-        fft_stages<LOG2N, 1, true, GEN>(pts, sdat, stw, gin, j, base, a.im_sign, kc);
+        fft_stages<LOG2N, 1, true, GEN>(pts, sdat, stw, gin, j, base, fl, a.im_sign, kc, fd);
 
         if constexpr (GEN) {
             // ---- general epilogue: scale, optional spectrum store, |X|^2 argmax
@@ -508,8 +737,6 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
                 if (TPF <= 32) {
                     if (j == 0 && active) { a.bin[b] = besti; if (a.mag2) a.mag2[b] = best; }
                 } else {
-                    constexpr int WPF = TPF / 32;            // warps per transform (FPB == 1 whenever TPF > 32)
-                    const int wib = threadIdx.x >> 5;
                     if ((threadIdx.x & 31) == 0) { red_mag[wib] = best; red_idx[32 + wib] = besti; }
                     __syncthreads();
                     if (j == 0 && active) {
@@ -527,53 +754,72 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
             }
         } else {
             // ---- estimator epilogue: |X|^2 of the unscaled outputs (the 1/n is a power of two: it commutes with every
-            // rounding and is applied once to the winner), maximum first, bin second
-            float mg[P];
+            // rounding and is applied once to the winner), maximum first, bin second.  The maxima of groups of eight points
+            // stay in registers; only the thread(s) holding the transform's maximum go back for the bin, and only into
+            // the group(s) that hold it, recomputing the (bitwise identical) magnitudes there.
+            constexpr int NG = (P >= 8) ? P / 8 : 1, GS = P / NG;
+            float gm[NG];
 #pragma unroll
-            for (int i = 0; i < P; i++) {
-                float x, y;
-                unpack2(mul2(pts[i], pts[i]), x, y);
-                mg[i] = __fadd_rn(x, y);
+            for (int gI = 0; gI < NG; gI++) {
+                float mx = -1.0f;
+#pragma unroll
+                for (int i = 0; i < GS; i++) {
+                    float x, y;
+                    unpack2(mul2(pts[gI * GS + i], pts[gI * GS + i]), x, y);
+                    mx = fmaxf(mx, __fadd_rn(x, y));
+                }
+                gm[gI] = mx;
             }
-            float red[P];
+            float lmax = gm[0];
 #pragma unroll
-            for (int i = 0; i < P; i++) red[i] = mg[i];
-#pragma unroll
-            for (int w = P / 2; w > 0; w >>= 1)
-#pragma unroll
-                for (int i = 0; i < w; i++) red[i] = fmaxf(red[i], red[i + w]);
-            const float lmax = red[0];
+            for (int gI = 1; gI < NG; gI++) lmax = fmaxf(lmax, gm[gI]);
             // per warp (or per transform when it is narrower than a warp): the maximum, then the lowest bin that holds it
             constexpr int W = (TPF < 32) ? TPF : 32;
             float g = lmax;
+            if (W == 32) {
+                // |X|^2 >= 0: the bit patterns order like the values, so the warp maximum is one integer REDUX
+                g = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(lmax)));
+            } else {
 #pragma unroll
-            for (int off = W / 2; off > 0; off >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, off, W));
+                for (int off = W / 2; off > 0; off >>= 1) g = fmaxf(g, __shfl_xor_sync(0xffffffffu, g, off, W));
+            }
             int cand = 0x7fffffff;
             if (lmax == g) {
 #pragma unroll
-                for (int i = 0; i < P; i++)
-                    if (mg[i] == g) cand = min(cand, fft_out_index<LOG2N>(j, i));
-            }
+                for (int gI = 0; gI < NG; gI++) {
+                    if (gm[gI] == g) {
 #pragma unroll
-            for (int off = W / 2; off > 0; off >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, off, W));
+                        for (int i = 0; i < GS; i++) {
+                            float x, y;
+                            unpack2(mul2(pts[gI * GS + i], pts[gI * GS + i]), x, y);
+                            if (__fadd_rn(x, y) == g) cand = min(cand, fft_out_index<LOG2N>(j, gI * GS + i));
+                        }
+                    }
+                }
+            }
+            if (W == 32) {
+                cand = __reduce_min_sync(0xffffffffu, cand);
+            } else {
+#pragma unroll
+                for (int off = W / 2; off > 0; off >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, off, W));
+            }
             if (TPF <= 32) {
                 if (j == 0 && active) { a.bin[b] = cand; if (a.mag2) a.mag2[b] = g * scale2; }
             } else {
-                // one shared-memory hop across the warps of the transform (FPB == 1 here); the slots alternate between
-                // passes, so the only barrier is the one that also closes the pass
-                constexpr int WPF = (TPF > 32) ? TPF / 32 : 1;
-                const int wib = threadIdx.x >> 5;
+                // one shared-memory hop across the warps of the transform; the slots alternate between passes, so the only
+                // barrier is the one that also closes the pass
                 float* rm = red_mag + 32 * (pass & 1);
                 int* ri = red_idx + 32 * (pass & 1);
                 if ((threadIdx.x & 31) == 0) { rm[wib] = g; ri[wib] = cand; }
-                __syncthreads();
-                if (threadIdx.x == 0 && active) {
-                    float bm = rm[0];
-                    int bi = ri[0];
+                fft_sync<TPF, Cfg::THREADS>(fl);
+                if (j == 0 && active) {
+                    const int w0 = fl * WPF;
+                    float bm = rm[w0];
+                    int bi = ri[w0];
 #pragma unroll
                     for (int w = 1; w < WPF; w++) {
-                        const float om = rm[w];
-                        const int oi = ri[w];
+                        const float om = rm[w0 + w];
+                        const int oi = ri[w0 + w];
                         if (om > bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
                     }
                     a.bin[b] = bi;
@@ -583,7 +829,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
         }
         // The next pass's stage-0 writes must not race with this pass's last-stage reads of shared memory.  With more than
         // one warp per transform the estimator epilogue's barrier came after those reads; otherwise close the pass here.
-        if (GEN || TPF <= 32) fft_sync<TPF>();
+        if (GEN || TPF <= 32) fft_sync<TPF, Cfg::THREADS>(fl);
         pass++;
     }
 }

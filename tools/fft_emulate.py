@@ -10,21 +10,21 @@ with numpy.fft.  It proves the structure; the arithmetic itself is checked on th
 import numpy as np
 
 
-P_BIG = {4096: 32, 8192: 32}      # QPSK_FFT_P4096 / QPSK_FFT_P8192
+P_BIG = {2048: 64, 4096: 64, 8192: 64}      # QPSK_FFT_P2048 / QPSK_FFT_P4096 / QPSK_FFT_P8192
 
 
 def ppt(n):
     if n in P_BIG:
         return P_BIG[n]
-    return 32 if (n >= 512 and n != 2048) else (16 if n >= 256 else (8 if n >= 8 else n))
+    return 32 if n >= 512 else (16 if n >= 256 else (8 if n >= 8 else n))
 
 
 def radix(rem, p):
-    return p // 4 if (p >= 32 and rem == 2 * p) else (p if rem >= p else rem)
+    return p // 4 if (p == 32 and rem == 2 * p) else (p if rem >= p else rem)
 
 
-def tw_cols(ns, tpf):
-    return min(ns, tpf)
+def tw_cols(ns, tpf, p):
+    return ns if (ns < tpf or p > 32) else tpf
 
 
 def cos32(k):
@@ -51,7 +51,7 @@ def w32_table(K):
 def emulate(n, x):
     p = ppt(n)
     tpf = n // p
-    S = 32 if p >= 32 else 16
+    S = 64 if p >= 64 else (32 if p >= 32 else 16)
     lin = n >= 256
     skew = lambda i: i + i // S
     off = lambda c: c + c // S
@@ -62,9 +62,16 @@ def emulate(n, x):
         stages.append((ns, r))
         ns *= r
     tables = {}
+    tws = lambda ns_: p >= 64 and ns_ == p
     for (ns, r) in stages:
-        if ns > 1:
-            cols = tw_cols(ns, tpf)
+        if tws(ns):
+            tables[ns] = np.array([[np.exp(-2j * np.pi * q * k / (ns * r)) for k in range(r)] for q in range(1, ns)])
+        elif p >= 64 and ns == 64 and r == 64:
+            tables[ns] = np.array([[np.exp(-2j * np.pi * ((8 * (i + 1)) if i < 7 else (i - 6)) * k / (ns * r)) for k in range(64)] for i in range(14)])
+        elif p >= 64 and r == 2 and ns > tpf and (2 * ns) // tpf == 64:
+            tables[ns] = np.array([[np.exp(-2j * np.pi * k / (ns * r)) for k in range(tpf)]])
+        elif ns > 1:
+            cols = tw_cols(ns, tpf, p)
             tables[ns] = np.array([[np.exp(-2j * np.pi * m * k / (ns * r)) for k in range(cols)] for m in range(1, r)])
     base = 0
     sdat = np.zeros(skew(n) + 8, complex)
@@ -72,8 +79,9 @@ def emulate(n, x):
     for si, (ns, r) in enumerate(stages):
         first, last = si == 0, ns * r == n
         nb, stride = p // r, n // r
-        kt = tw_cols(ns, tpf)
-        fact = last and ns > tpf
+        kt = tw_cols(ns, tpf, p)
+        fact = last and ns > tpf and p <= 32
+        perbf = ns > tpf and not fact
         for j in range(tpf):
             rd = skew(base + j)
             for t in range(nb):
@@ -87,13 +95,27 @@ def emulate(n, x):
                         v[rr] = sdat[rd + off(c)]
                     else:
                         v[rr] = sdat[skew(base + j + c)]
-                if ns > 1:
-                    k = j % kt
+                if p >= 64 and ns == 64 and r == 64 and not tws(ns):
+                    for m in range(1, r):
+                        if m // 8:
+                            v[m] *= tables[ns][m // 8 - 1][j % 64]
+                        if m % 8:
+                            v[m] *= tables[ns][7 + m % 8 - 1][j % 64]
+                elif p >= 64 and r == 2 and ns > tpf and (2 * ns) // tpf == 64:
+                    v[1] *= tables[ns][0][j] * np.exp(-2j * np.pi * t / 64)
+                elif ns > 1 and not tws(ns):
+                    k = (j + t * tpf) if perbf else j % kt
                     for m in range(1, r):
                         v[m] *= tables[ns][m - 1][k]
                         if fact and t > 0:
                             v[m] *= w32_table((m * t * (32 // p)) & 31)
-                pts[j, t * r:(t + 1) * r] = np.fft.fft(v)
+                o = np.fft.fft(v)
+                if first and not last and tws(r):
+                    rn = stages[si + 1][1]
+                    assert nb == 1
+                    for q in range(1, r):
+                        o[q] *= tables[r][q - 1][(j * r * rn) // n]
+                pts[j, t * r:(t + 1) * r] = o
         if not last:
             new = np.zeros_like(sdat)
             for j in range(tpf):
@@ -123,9 +145,9 @@ def main():
     for K in range(32):
         assert abs(w32_table(K) - np.exp(-2j * np.pi * K / 32)) < 1e-12, K
     rng = np.random.default_rng(0)
-    for pbig in (16, 32):
-        P_BIG[4096] = P_BIG[8192] = pbig
-        for n in (4096, 8192):
+    for pbig in (16, 32, 64):
+        P_BIG[2048] = P_BIG[4096] = P_BIG[8192] = pbig
+        for n in (2048, 4096, 8192):
             x = rng.normal(size=n) + 1j * rng.normal(size=n)
             err = np.max(np.abs(emulate(n, x) - np.fft.fft(x))) / np.max(np.abs(np.fft.fft(x)))
             assert err < 1e-10, (n, pbig, err)
