@@ -62,7 +62,10 @@ __host__ __device__ constexpr bool qpsk_fft_tw_on_store(int ns, int p) { return 
 // leave of the L1, and 63 L2 round trips per thread and burst were the kernel's largest stall; 14 x 64 entries (7 KB) do fit.
 __host__ __device__ constexpr bool qpsk_fft_tw_two_level(int ns, int r, int p) { return p >= 64 && ns == 64 && r == 64 && !qpsk_fft_tw_on_store(ns, p); }
 // ... and the single twiddle of a final radix-2 stage, w^(j + t tpf), is w^j times a compile-time power of W64
-__host__ __device__ constexpr bool qpsk_fft_tw_fact64(int ns, int r, int tpf, int p) { return p >= 64 && r == 2 && ns > tpf && (2 * ns) / tpf == 64; }
+#ifndef QPSK_FFT_FACT64
+#define QPSK_FFT_FACT64 1
+#endif
+__host__ __device__ constexpr bool qpsk_fft_tw_fact64(int ns, int r, int tpf, int p) { return QPSK_FFT_FACT64 && p >= 64 && r == 2 && ns > tpf && (2 * ns) / tpf == 64; }
 __host__ __device__ constexpr int qpsk_fft_tw_entries(int ns, int r, int tpf, int p) {
     return ns <= 1 ? 0 : (qpsk_fft_tw_on_store(ns, p) ? (ns - 1) * r : (qpsk_fft_tw_two_level(ns, r, p) ? 14 * 64
                         : (qpsk_fft_tw_fact64(ns, r, tpf, p) ? tpf : (r - 1) * qpsk_fft_tw_cols(ns, tpf, p))));
@@ -142,11 +145,12 @@ struct FftCfg {
     static constexpr int FPB = THREADS / TPF;                      // transforms per CTA pass
     static constexpr int PTS = FPB * N;
     static constexpr int SKEW = (P >= 64) ? 64 : ((P >= 32) ? 32 : 16);   // one pad slot per SKEW points: unit-stride and stride-P accesses are conflict-free
-    static constexpr int PADW = (P >= 64) ? 2 : 1;                 // pad slots per SKEW points (two = 16 bytes: rows stay aligned for bulk copies and 128-bit stores)
-    static constexpr int SKEW_PTS = PTS + PADW * (PTS / SKEW);     // float2 elements
-    // 64 points per thread: the burst comes in through the bulk-copy engine (cp.async.bulk, one 512-byte row per thread,
-    // completion on an mbarrier) straight into the skewed layout of the work buffer, issued as soon as the previous
-    // burst's last stage has read the buffer, so the transfer runs under that stage's arithmetic and the epilogue
+    static constexpr int SKEW_PTS = PTS + PTS / SKEW;              // float2 elements
+    // 64 points per thread: the burst comes in through the bulk-copy engine (one cp.async.bulk of the whole burst per
+    // transform, completion on an mbarrier) into the transform's work buffer, unpadded -- stage 0 reads it with unit
+    // stride across lanes, so it needs no skew, and overwrites it in the skewed layout afterwards.  The copy is issued
+    // as soon as the previous burst's last stage has read the buffer, so it runs under that stage's arithmetic and the
+    // epilogue, and no thread ever waits for HBM with its registers full.
     static constexpr bool TMA_IN = (P >= 64);
     static constexpr int TW = qpsk_fft_tw_count(N);
     static constexpr bool LIN = (N >= 256);                        // linear skew offsets (static_asserted per stage)
@@ -383,13 +387,13 @@ __device__ __forceinline__ void dft_small<64>(c64 (&v)[64], const FftConsts& kc)
 }
 
 template <int SKEW>
-__host__ __device__ constexpr int fft_skew(int i) { return i + (SKEW >= 64 ? 2 : 1) * (i / SKEW); }
+__host__ __device__ constexpr int fft_skew(int i) { return i + i / SKEW; }
 
 // Offset of a compile-time displacement c from a per-thread base whose skewed address is already known:
 // skew(base + c) = skew(base) + fft_off(c), provided the low parts never carry into another pad slot
 // (proved per stage at compile time by fft_stage_linear_ok).
 template <int SKEW>
-__host__ __device__ constexpr int fft_off(int c) { return c + (SKEW >= 64 ? 2 : 1) * (c / SKEW); }
+__host__ __device__ constexpr int fft_off(int c) { return c + c / SKEW; }
 
 // ---- bulk-copy engine + mbarrier (the burst's way into shared memory for the 64-points-per-thread kernels)
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -407,17 +411,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
     asm volatile("{\n .reg .pred p;\n LAB_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra LAB_DONE;\n bra LAB_WAIT;\n LAB_DONE:\n}"
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-// what a thread needs to fetch its row of the transform's next burst
+// what a transform needs to fetch its next burst
 struct FftFeed {
     unsigned long long* bar;    // the transform's mbarrier
-    c64* dst;                   // this thread's 64-point row in the work buffer
-    const c64* next_src;        // its source row in the next burst, nullptr when there is none
+    c64* dst;                   // the transform's work buffer
+    const c64* next_src;        // the next burst, nullptr when there is none
     int parity;                 // phase of the current burst
+    int bytes;
 };
+// one thread of the transform
 __device__ __forceinline__ void fft_feed_issue(const FftFeed& fd, const c64* src) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the buffer's earlier generic-proxy accesses come first
-    mbar_arrive_expect_tx(fd.bar, 64 * 8);
-    bulk_copy_g2s(fd.dst, src, 64 * 8, fd.bar);
+    mbar_arrive_expect_tx(fd.bar, fd.bytes);
+    bulk_copy_g2s(fd.dst, src, fd.bytes, fd.bar);
 }
 
 // the threads of one transform exchange data between passes: a warp-level barrier is enough when a transform lives
@@ -487,7 +493,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
 #pragma unroll
         for (int i = 0; i < P; i++) asm volatile("" ::"l"(pts[i]));      // the loads have completed ...
         fft_sync<TPF, Cfg::THREADS>(fl);                                 // ... in every thread of the transform
-        if (fd.next_src != nullptr) fft_feed_issue(fd, fd.next_src);
+        if (j == 0 && fd.next_src != nullptr) fft_feed_issue(fd, fd.next_src);
     }
 #pragma unroll
     for (int t = 0; t < NB; t++) {
@@ -499,6 +505,8 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
                 v[r] = pts[t * R + r];
             } else if (!SMEM_IN) {
                 v[r] = gin[j + c];
+            } else if (FIRST) {
+                v[r] = fd.dst[j + c];                     // the burst as the bulk copy left it: unpadded
             } else if (Cfg::LIN) {
                 v[r] = rd[fft_off<S>(c)];
             } else {
@@ -563,18 +571,11 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
         c64* wr = sdat + fft_skew<S>(base + dyn);
 #pragma unroll
         for (int t = 0; t < NB; t++) {
-            if (NS == 1 && Cfg::PADW == 2 && Cfg::LIN) {
-                // the butterfly's R outputs are contiguous and 16-byte aligned: 128-bit stores, two points each
 #pragma unroll
-                for (int q = 0; q < R; q += 2)
-                    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(smem_u32(wr + fft_off<S>(t * TPF * R + q))), "l"(pts[t * R + q]), "l"(pts[t * R + q + 1]) : "memory");
-            } else {
-#pragma unroll
-                for (int q = 0; q < R; q++) {
-                    const int c = t * TPF * R + q * NS;
-                    if (Cfg::LIN) wr[fft_off<S>(c)] = pts[t * R + q];
-                    else sdat[fft_skew<S>(base + dyn + c)] = pts[t * R + q];
-                }
+            for (int q = 0; q < R; q++) {
+                const int c = t * TPF * R + q * NS;
+                if (Cfg::LIN) wr[fft_off<S>(c)] = pts[t * R + q];
+                else sdat[fft_skew<S>(base + dyn + c)] = pts[t * R + q];
             }
         }
         fft_sync<TPF, Cfg::THREADS>(fl);
@@ -588,7 +589,7 @@ __host__ __device__ constexpr bool fft_stage_linear_ok() {
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R, S = Cfg::SKEW;
     if (!Cfg::LIN) return true;
     if ((Cfg::N % S) != 0) return false;                               // transform bases are multiples of S
-    if (!FIRST || Cfg::TMA_IN) {                                       // reads: base + j + c
+    if (!FIRST) {                                                      // reads: base + j + c (a first stage reads unpadded data)
         for (int t = 0; t < NB; t++)
             for (int r = 0; r < R; r++) {
                 const int c = t * TPF + r * (N / R);
@@ -672,14 +673,14 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
     const int wib = threadIdx.x >> 5;
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(red_idx + 64) + fl;      // one per transform of the CTA
     FftFeed fd;
-    fd.bar = mbar; fd.dst = sdat + fft_skew<Cfg::SKEW>(base + j * 64); fd.next_src = nullptr; fd.parity = 0;
+    fd.bar = mbar; fd.dst = sdat + fft_skew<Cfg::SKEW>(base); fd.next_src = nullptr; fd.parity = 0; fd.bytes = N * 8;
     if (Cfg::TMA_IN) {
-        if (j == 0) mbar_init(mbar, TPF);                // every thread of the transform arrives once per burst, with its row
+        if (j == 0) mbar_init(mbar, 1);                  // one thread of the transform arrives per burst, with the byte count
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncthreads();
         const int bfirst = blockIdx.x * FPB + fl;
-        if (blockIdx.x * FPB < a.nbursts)
-            fft_feed_issue(fd, reinterpret_cast<const c64*>(a.in) + (size_t)(bfirst < a.nbursts ? bfirst : a.nbursts - 1) * N + j * 64);
+        if (j == 0 && blockIdx.x * FPB < a.nbursts)
+            fft_feed_issue(fd, reinterpret_cast<const c64*>(a.in) + (size_t)(bfirst < a.nbursts ? bfirst : a.nbursts - 1) * N);
     }
     int pass = 0;
     for (int b0 = blockIdx.x * FPB; b0 < a.nbursts; b0 += gridDim.x * FPB) {
@@ -690,7 +691,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
         if (Cfg::TMA_IN) {
             const long long bn0 = (long long)b0 + (long long)gridDim.x * FPB;
             const long long bn = bn0 + fl;
-            fd.next_src = bn0 < a.nbursts ? reinterpret_cast<const c64*>(a.in) + (size_t)(bn < a.nbursts ? bn : a.nbursts - 1) * N + j * 64 : nullptr;
+            fd.next_src = bn0 < a.nbursts ? reinterpret_cast<const c64*>(a.in) + (size_t)(bn < a.nbursts ? bn : a.nbursts - 1) * N : nullptr;
             fd.parity = pass & 1;
         }
         // The burst this slot transforms QPSK_FFT_L2_AHEAD passes from now starts its way from HBM to L2 here: two
