@@ -70,7 +70,17 @@ __host__ __device__ constexpr int qpsk_fft_tw_entries(int ns, int r, int tpf, in
     return ns <= 1 ? 0 : (qpsk_fft_tw_on_store(ns, p) ? (ns - 1) * r : (qpsk_fft_tw_two_level(ns, r, p) ? 14 * 64
                         : (qpsk_fft_tw_fact64(ns, r, tpf, p) ? tpf : (r - 1) * qpsk_fft_tw_cols(ns, tpf, p))));
 }
+// n = 8192 with 64 points per thread is two 4096-point transforms side by side in one CTA (decimation in frequency:
+// even bins = FFT(x[n] + x[n + 4096]), odd bins = FFT((x[n] - x[n + 4096]) w^n)), each with ONE crossing of shared memory,
+// instead of 64 x 64 x 2 with two.  The radix-2 step happens as stage 0 reads the burst; of the odd half's factor
+// w^n = w^j W128^r (n = j + 64 r) the constant part multiplies the inputs and w^j moves into the second stage's twiddle
+// base, z = w8192^(2k + 1) instead of w8192^(2k): a second 14 x 64 table.
+#ifndef QPSK_FFT_SPLIT8192
+#define QPSK_FFT_SPLIT8192 1
+#endif
+__host__ __device__ constexpr bool qpsk_fft_split(int n) { return QPSK_FFT_SPLIT8192 && n == 8192 && qpsk_fft_points_per_thread(n) == 64 && qpsk_fft_points_per_thread(4096) == 64; }
 __host__ __device__ constexpr int qpsk_fft_tw_count(int n) {
+    if (qpsk_fft_split(n)) return 2 * 14 * 64;
     const int p = qpsk_fft_points_per_thread(n), tpf = n / p;
     int ns = 1, tot = 0;
     while (ns < n) {
@@ -88,6 +98,16 @@ inline void qpsk_fft_make_twiddles(int n, float2* tw) {
     const int p = qpsk_fft_points_per_thread(n), tpf = n / p;
     tw[0] = make_float2(1.0f, 0.0f);
     int pos = 0;
+    if (qpsk_fft_split(n)) {
+        for (int half = 0; half < 2; half++)               // z = w_n^(2k + half), entries z^(8a) (a = 1..7) then z^b (b = 1..7)
+            for (int i = 0; i < 14; i++)
+                for (int k = 0; k < 64; k++) {
+                    const int e = (i < 7) ? 8 * (i + 1) : (i - 6);
+                    const double ang = 2.0 * 3.14159265358979323846 * (double)e * (double)(2 * k + half) / (double)n;
+                    tw[pos++] = make_float2((float)cos(ang), (float)(-sin(ang)));
+                }
+        return;
+    }
     for (int ns = 1; ns < n;) {
         const int r = qpsk_fft_radix(n / ns, p);
         if (qpsk_fft_tw_on_store(ns, p)) {
@@ -203,6 +223,12 @@ struct FftConsts {
 };
 // the host fills FftArgs::kbase with (c, s) x 4 then (c, -s) x 4; arriving as kernel arguments the pairs are whole
 // 64-bit uniform-register operands, opaque to the optimiser (which would otherwise fold them back into immediates)
+inline void fft_w128_host(float2 (&w)[64]) {
+    for (int r = 0; r < 64; r++) {
+        const double ang = 2.0 * 3.14159265358979323846 * (double)r / 128.0;
+        w[r] = make_float2((float)cos(ang), (float)(-sin(ang)));
+    }
+}
 inline void fft_consts_host(float2 (&kb)[16]) {
     for (int r = 1; r <= 4; r++) {
         kb[r - 1] = make_float2(qpsk_cos32(r), qpsk_sin32(r));
@@ -445,13 +471,15 @@ struct FftArgs {
     float im_sign;         // +1 forward, -1 inverse (inverse = conj(FFT(conj(x))))
     float scale;           // 1/N forward (fft.c:105-107), 1 inverse (fft.c:122-128)
     float2 kbase[16];      // (cos, sin) and (cos, -sin) of 2 pi r / 32, r = 1..4, then of 2 pi r / 64, r = 1, 3, 5, 7: see FftConsts
+    float2 w128[64];       // exp(-2 pi i r / 128), r = 0..63 (the split 8192-point kernel's input factors)
 };
 
 // One Stockham stage for the P points a thread owns: radix R, sub-transform length NS already done.
 // GEN: the general entry points (inverse through conjugation); the estimator instantiation loads plain.
-template <int LOG2N, int R, int NS, bool FIRST, bool LAST, bool GEN>
+// SPLIT: this transform is one half (fl = 0 even bins, 1 odd bins) of a burst of 2 N points, see qpsk_fft_split().
+template <int LOG2N, int R, int NS, bool FIRST, bool LAST, bool GEN, bool SPLIT>
 __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw, const c64* gin, int j, int base, int fl, float imsgn,
-                                          const FftConsts& kc, const FftFeed& fd) {
+                                          const FftConsts& kc, const FftFeed& fd, const float2* w128) {
     using Cfg = FftCfg<LOG2N>;
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, NB = P / R, S = Cfg::SKEW;   // NB butterflies per thread
     constexpr int STRIDE = N / R;
@@ -467,6 +495,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
     constexpr bool PRELOAD = NS > 1 && !PRETW && !PERBF && !TW2L && NB > 1; // the same R - 1 twiddles serve every butterfly of the thread
     constexpr bool SMEM_IN = !FIRST || Cfg::TMA_IN;      // inputs come from the work buffer
     constexpr bool RELEASE = LAST && Cfg::TMA_IN;        // the last reader of the buffer hands it to the next burst's copy
+    static_assert(!SPLIT || (Cfg::TMA_IN && R == 64 && NB == 1), "the split kernel is built from the bulk-fed 64 x 64 transform");
     static_assert(LAST || NS <= TPF, "only a remainder stage may have more sub-transform columns than threads");
     static_assert(!FACT || (N / TPF == P && 32 % P == 0), "factored twiddles assume n / tpf == P, a divisor of 32");
 
@@ -498,10 +527,28 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
 #pragma unroll
     for (int t = 0; t < NB; t++) {
         c64 v[R];
+        if (FIRST && SPLIT) {
+            // the radix-2 step of the decimation in frequency, as the burst is read: x[n] +- x[n + N], n = j + r STRIDE
+            if (fl == 0) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    v[r] = cadd(fd.dst[j + r * STRIDE], fd.dst[j + r * STRIDE + N]);
+                    if (GEN) v[r] = cconj_if(v[r], imsgn);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    v[r] = csub(fd.dst[j + r * STRIDE], fd.dst[j + r * STRIDE + N]);
+                    if (GEN) v[r] = cconj_if(v[r], imsgn);
+                    if (r > 0) v[r] = cmul(v[r], *reinterpret_cast<const c64*>(&w128[r]));      // W128^r; w^j is in the next stage's twiddles
+                }
+            }
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int c = t * TPF + r * STRIDE;          // butterfly j + t TPF, input r
-            if (RELEASE) {
+            if (FIRST && SPLIT) {
+            } else if (RELEASE) {
                 v[r] = pts[t * R + r];
             } else if (!SMEM_IN) {
                 v[r] = gin[j + c];
@@ -512,7 +559,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
             } else {
                 v[r] = sdat[fft_skew<S>(base + j + c)];
             }
-            if (FIRST && GEN) v[r] = cconj_if(v[r], imsgn);    // inverse = conj(FFT(conj x))
+            if (FIRST && GEN && !SPLIT) v[r] = cconj_if(v[r], imsgn);    // inverse = conj(FFT(conj x))
         }
         if (TW2L) {
 #pragma unroll
@@ -610,18 +657,18 @@ __host__ __device__ constexpr bool fft_stage_linear_ok() {
     return true;
 }
 
-template <int LOG2N, int NS, bool FIRST, bool GEN>
+template <int LOG2N, int NS, bool FIRST, bool GEN, bool SPLIT>
 __device__ __forceinline__ void fft_stages(c64 (&pts)[FftCfg<LOG2N>::P], c64* sdat, const c64* stw, const c64* gin, int j, int base, int fl, float imsgn,
-                                           const FftConsts& kc, const FftFeed& fd) {
+                                           const FftConsts& kc, const FftFeed& fd, const float2* w128) {
     constexpr int N = FftCfg<LOG2N>::N;
     constexpr int REM = N / NS;
     constexpr int RMAX = FftCfg<LOG2N>::P;
     constexpr int R = qpsk_fft_radix(REM, RMAX);
     constexpr bool LAST = (NS * R == N);
     static_assert(fft_stage_linear_ok<LOG2N, R, NS, FIRST, LAST>(), "skewed shared-memory offsets of this stage are not linear");
-    fft_stage<LOG2N, R, NS, FIRST, LAST, GEN>(pts, sdat, stw, gin, j, base, fl, imsgn, kc, fd);
+    fft_stage<LOG2N, R, NS, FIRST, LAST, GEN, SPLIT>(pts, sdat, stw, gin, j, base, fl, imsgn, kc, fd, w128);
     if constexpr (!LAST)
-        fft_stages<LOG2N, NS * R, false, GEN>(pts, sdat, stw + qpsk_fft_tw_entries(NS, R, FftCfg<LOG2N>::TPF, FftCfg<LOG2N>::P), gin, j, base, fl, imsgn, kc, fd);
+        fft_stages<LOG2N, NS * R, false, GEN, SPLIT>(pts, sdat, stw + qpsk_fft_tw_entries(NS, R, FftCfg<LOG2N>::TPF, FftCfg<LOG2N>::P), gin, j, base, fl, imsgn, kc, fd, w128);
 }
 
 // output index of pts[i] after the last stage (radix RLAST, sub-transform length NSL = N / RLAST)
@@ -644,9 +691,13 @@ __device__ __forceinline__ int fft_out_index(int j, int i) {
 // GEN = false: forward transform, argmax only (a.bin required; a.spectrum, a.im_sign ignored) -- the estimator hot path.
 // GEN = true : forward or inverse, optional spectrum store, optional argmax.
 template <int LOG2N, bool GEN>
-__global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) fft_kernel(const FftArgs a) {
+__global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) fft_kernel(const __grid_constant__ FftArgs a) {
     using Cfg = FftCfg<LOG2N>;
     constexpr int N = Cfg::N, P = Cfg::P, TPF = Cfg::TPF, FPB = Cfg::FPB;
+    constexpr bool SPLIT = qpsk_fft_split(N);           // the burst is two half-length transforms side by side
+    constexpr int SL = SPLIT ? LOG2N - 1 : LOG2N;       // log2 of the length the stages work on
+    using Sub = FftCfg<SL>;
+    static_assert(!SPLIT || (Sub::P == P && Sub::TPF * 2 == TPF && FPB == 1 && !Cfg::TW_SMEM), "split kernel layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     c64* sdat = reinterpret_cast<c64*>(smem_raw);
     c64* stw_s = sdat + Cfg::SKEW_PTS;
@@ -660,6 +711,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
 
     const int fl = threadIdx.x / TPF, j = threadIdx.x % TPF;
     const int base = fl * N;
+    const int half = SPLIT ? j / Sub::TPF : 0, js = SPLIT ? j % Sub::TPF : j;      // which half, thread within it
     const float scale2 = a.scale * a.scale;
     FftConsts kc;
 #pragma unroll
@@ -691,7 +743,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
         if (Cfg::TMA_IN) {
             const long long bn0 = (long long)b0 + (long long)gridDim.x * FPB;
             const long long bn = bn0 + fl;
-            fd.next_src = bn0 < a.nbursts ? reinterpret_cast<const c64*>(a.in) + (size_t)(bn < a.nbursts ? bn : a.nbursts - 1) * N : nullptr;
+            fd.next_src = (bn0 < a.nbursts && half == 0) ? reinterpret_cast<const c64*>(a.in) + (size_t)(bn < a.nbursts ? bn : a.nbursts - 1) * N : nullptr;
             fd.parity = pass & 1;
         }
         // The burst this slot transforms QPSK_FFT_L2_AHEAD passes from now starts its way from HBM to L2 here: two
@@ -709,7 +761,9 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
             }
         }
         c64 pts[P];
-        fft_stages<LOG2N, 1, true, GEN>(pts, sdat, stw, gin, j, base, fl, a.im_sign, kc, fd);
+        fft_stages<SL, 1, true, GEN, SPLIT>(pts, sdat, stw + (SPLIT ? half * (14 * 64) : 0), gin, js, base + half * Sub::N, SPLIT ? half : fl, a.im_sign, kc, fd, a.w128);
+        // bin of pts[i]: a half of a split burst holds every other bin
+        auto out_index = [&](int i) { return SPLIT ? 2 * fft_out_index<SL>(js, i) + half : fft_out_index<SL>(js, i); };
 
         if constexpr (GEN) {
             // ---- general epilogue: scale, optional spectrum store, |X|^2 argmax
@@ -717,7 +771,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
             int besti = 0x7fffffff;
 #pragma unroll
             for (int i = 0; i < P; i++) {
-                const int idx = fft_out_index<LOG2N>(j, i);
+                const int idx = out_index(i);
                 float2 x;
                 unpack2(pts[i], x.x, x.y);
                 x.x *= a.scale;
@@ -793,7 +847,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
                         for (int i = 0; i < GS; i++) {
                             float x, y;
                             unpack2(mul2(pts[gI * GS + i], pts[gI * GS + i]), x, y);
-                            if (__fadd_rn(x, y) == g) cand = min(cand, fft_out_index<LOG2N>(j, gI * GS + i));
+                            if (__fadd_rn(x, y) == g) cand = min(cand, out_index(gI * GS + i));
                         }
                     }
                 }

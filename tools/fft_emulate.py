@@ -10,6 +10,7 @@ with numpy.fft.  It proves the structure; the arithmetic itself is checked on th
 import numpy as np
 
 
+TW_ON_STORE = False       # QPSK_FFT_TW_ON_STORE
 P_BIG = {2048: 64, 4096: 64, 8192: 64}      # QPSK_FFT_P2048 / QPSK_FFT_P4096 / QPSK_FFT_P8192
 
 
@@ -48,7 +49,15 @@ def w32_table(K):
     return sg * (u + 1j * v)
 
 
-def emulate(n, x):
+def emulate(n, x, split_half=None):
+    """split_half = None: an n-point transform.  0 / 1: the even / odd half of a 2n-point burst whose radix-2 step has
+    already been taken (x = x0 + x1 resp. x0 - x1): the odd half multiplies input r of stage 0 by W128^r and uses the
+    twiddle base w_2n^(2k + 1) in the second stage (qpsk_fft_split)."""
+    if split_half is None and n == 8192 and ppt(n) == 64 and ppt(4096) == 64:
+        out = np.zeros(n, complex)
+        out[0::2] = emulate(4096, x[:4096] + x[4096:], 0)
+        out[1::2] = emulate(4096, x[:4096] - x[4096:], 1)
+        return out
     p = ppt(n)
     tpf = n // p
     S = 64 if p >= 64 else (32 if p >= 32 else 16)
@@ -62,12 +71,13 @@ def emulate(n, x):
         stages.append((ns, r))
         ns *= r
     tables = {}
-    tws = lambda ns_: p >= 64 and ns_ == p
+    tws = lambda ns_: TW_ON_STORE and p >= 64 and ns_ == p
     for (ns, r) in stages:
         if tws(ns):
             tables[ns] = np.array([[np.exp(-2j * np.pi * q * k / (ns * r)) for k in range(r)] for q in range(1, ns)])
         elif p >= 64 and ns == 64 and r == 64:
-            tables[ns] = np.array([[np.exp(-2j * np.pi * ((8 * (i + 1)) if i < 7 else (i - 6)) * k / (ns * r)) for k in range(64)] for i in range(14)])
+            hb = 0 if split_half is None else split_half
+            tables[ns] = np.array([[np.exp(-2j * np.pi * ((8 * (i + 1)) if i < 7 else (i - 6)) * (2 * k + hb) / (2 * ns * r)) for k in range(64)] for i in range(14)])
         elif p >= 64 and r == 2 and ns > tpf and (2 * ns) // tpf == 64:
             tables[ns] = np.array([[np.exp(-2j * np.pi * k / (ns * r)) for k in range(tpf)]])
         elif ns > 1:
@@ -90,6 +100,9 @@ def emulate(n, x):
                     c = t * tpf + rr * stride
                     if first:
                         v[rr] = x[j + c]
+                        if split_half == 1:
+                            assert nb == 1 and stride == 64
+                            v[rr] *= np.exp(-2j * np.pi * rr / 128)
                     elif lin:
                         assert rd + off(c) == skew(base + j + c), (n, ns, r, j, c)
                         v[rr] = sdat[rd + off(c)]
