@@ -220,13 +220,24 @@ struct FftConsts {
     c64 bm[4];     // (c, -s)
     c64 bp64[4];   // the same for the odd powers of W64: (cos, sin)(2 pi r / 64), r = 1, 3, 5, 7 (used by the 64-point DFT only)
     c64 bm64[4];
+    c64 two;       // (2, 2): a - W b = 2 a - (a + W b)
 };
 // the host fills FftArgs::kbase with (c, s) x 4 then (c, -s) x 4; arriving as kernel arguments the pairs are whole
 // 64-bit uniform-register operands, opaque to the optimiser (which would otherwise fold them back into immediates)
-inline void fft_w128_host(float2 (&w)[64]) {
-    for (int r = 0; r < 64; r++) {
-        const double ang = 2.0 * 3.14159265358979323846 * (double)r / 128.0;
-        w[r] = make_float2((float)cos(ang), (float)(-sin(ang)));
+inline void fft_two_host(float2& t) { t = make_float2(2.0f, 2.0f); }
+// Stage 0 of the split kernel computes the 64-point DFT of v[m] W128^(h m), m = n1 + 8 n2, h = 0 for the even-bin half
+// and 1 for the odd-bin half, through ONE instruction stream (two streams measured 20 % slower: they halve the
+// instruction cache's reach), so the factors are data: [h][n2] = W16^(h n2) rides in the first-level butterflies,
+// [h][8 + 8 k2 + n1] = W64^(n1 k2) W128^(h n1) in the second level's.
+inline void fft_wsplit_host(float2 (&w)[2][72]) {
+    const double tau = 2.0 * 3.14159265358979323846;
+    for (int h = 0; h < 2; h++) {
+        for (int n2 = 0; n2 < 8; n2++) w[h][n2] = make_float2((float)cos(tau * h * n2 / 16.0), (float)(-sin(tau * h * n2 / 16.0)));
+        for (int k2 = 0; k2 < 8; k2++)
+            for (int n1 = 0; n1 < 8; n1++) {
+                const double ang = tau * (double)(n1 * (2 * k2 + h)) / 128.0;
+                w[h][8 + 8 * k2 + n1] = make_float2((float)cos(ang), (float)(-sin(ang)));
+            }
     }
 }
 inline void fft_consts_host(float2 (&kb)[16]) {
@@ -412,6 +423,159 @@ __device__ __forceinline__ void dft_small<64>(c64 (&v)[64], const FftConsts& kc)
     }
 }
 
+// ---- butterflies with the twiddle folded into fused multiply-adds (the 64-point DFT of the large transforms, which are
+// bound by the FP32 pipe):  x = a + W b costs two FFMA2 -- t = b_im (w_im, w_re) + (-a_re, a_im), x = b_re (w_re, w_im) +
+// (-t_re, t_im) -- and y = a - W b = 2 a - x a third, against FMUL2 + FFMA2 + FADD2 + FADD2 for multiply-then-butterfly.
+__device__ __forceinline__ c64 cneg(c64 a) { float x, y; unpack2(a, x, y); return pack2(-x, -y); }
+// W a runtime twiddle (register or uniform register)
+__device__ __forceinline__ void bfly_tw(c64 a, c64 b, c64 w, const FftConsts& kc, c64& x, c64& y) {
+    float ar, ai, br, bi, wx, wy, tx, ty;
+    unpack2(a, ar, ai);
+    unpack2(b, br, bi);
+    unpack2(w, wx, wy);
+    unpack2(fma2(pack2(bi, bi), pack2(wy, wx), pack2(-ar, ai)), tx, ty);
+    x = fma2(pack2(br, br), w, pack2(-tx, ty));
+    y = fma2(a, kc.two, cneg(x));
+}
+// W = SGN * (SW ? swap(base) : base), base one of the constant pairs of FftConsts
+template <int SW, int SGN>
+__device__ __forceinline__ void bfly_base(c64 a, c64 b, c64 base, const FftConsts& kc, c64& x, c64& y) {
+    float ar, ai, br, bi, bx, by, tx, ty;
+    unpack2(a, ar, ai);
+    unpack2(b, br, bi);
+    unpack2(base, bx, by);
+    const float u = SW ? by : bx, v = SW ? bx : by;              // W = SGN (u + i v)
+    const float sbi = SGN > 0 ? bi : -bi, sbr = SGN > 0 ? br : -br;
+    unpack2(fma2(pack2(sbi, sbi), pack2(v, u), pack2(-ar, ai)), tx, ty);
+    x = fma2(pack2(sbr, sbr), pack2(u, v), pack2(-tx, ty));
+    y = fma2(a, kc.two, cneg(x));
+}
+// (a + W64^K b, a - W64^K b), K a compile-time constant
+template <int K>
+__device__ __forceinline__ void bfly_w64(c64 a, c64 b, const FftConsts& kc, c64& x, c64& y) {
+    constexpr int k = K & 63;
+    if constexpr (k % 16 == 0) {
+        constexpr int q = k / 16;
+        if constexpr (q == 0) { x = cadd(a, b); y = csub(a, b); }
+        else if constexpr (q == 1) { x = cadd_mi(a, b); y = cadd_pi(a, b); }
+        else if constexpr (q == 2) { x = csub(a, b); y = cadd(a, b); }
+        else { x = cadd_pi(a, b); y = cadd_mi(a, b); }
+    } else if constexpr ((k & 1) == 0) {              // a power of W32, decoded as in cmul_w32
+        constexpr int h = k / 2, q = h / 8, r = h % 8;
+        if constexpr (r <= 4) {
+            constexpr int i = r - 1;
+            if constexpr (q == 0) bfly_base<0, 1>(a, b, kc.bm[i], kc, x, y);
+            else if constexpr (q == 1) bfly_base<1, -1>(a, b, kc.bp[i], kc, x, y);
+            else if constexpr (q == 2) bfly_base<0, -1>(a, b, kc.bm[i], kc, x, y);
+            else bfly_base<1, 1>(a, b, kc.bp[i], kc, x, y);
+        } else {
+            constexpr int i = 8 - r - 1;
+            if constexpr (q == 0) bfly_base<1, -1>(a, b, kc.bm[i], kc, x, y);
+            else if constexpr (q == 1) bfly_base<0, -1>(a, b, kc.bp[i], kc, x, y);
+            else if constexpr (q == 2) bfly_base<1, 1>(a, b, kc.bm[i], kc, x, y);
+            else bfly_base<0, 1>(a, b, kc.bp[i], kc, x, y);
+        }
+    } else {                                          // an odd power of W64, decoded as in cmul_w64
+        constexpr int q = k / 16, r = k % 16;
+        if constexpr (r < 8) {
+            constexpr int i = (r - 1) / 2;
+            if constexpr (q == 0) bfly_base<0, 1>(a, b, kc.bm64[i], kc, x, y);
+            else if constexpr (q == 1) bfly_base<1, -1>(a, b, kc.bp64[i], kc, x, y);
+            else if constexpr (q == 2) bfly_base<0, -1>(a, b, kc.bm64[i], kc, x, y);
+            else bfly_base<1, 1>(a, b, kc.bp64[i], kc, x, y);
+        } else {
+            constexpr int i = (16 - r - 1) / 2;
+            if constexpr (q == 0) bfly_base<1, -1>(a, b, kc.bm64[i], kc, x, y);
+            else if constexpr (q == 1) bfly_base<0, -1>(a, b, kc.bp64[i], kc, x, y);
+            else if constexpr (q == 2) bfly_base<1, 1>(a, b, kc.bm64[i], kc, x, y);
+            else bfly_base<0, 1>(a, b, kc.bp64[i], kc, x, y);
+        }
+    }
+}
+
+// first layer of the 8-point DFT on inputs that still carry a twiddle each: the pair (t_a w_a, t_b w_b) -> sum, difference.
+// MODE 0: no twiddles.  MODE 1: runtime twiddles w[1..7] (w[0] is not read).  MODE 2: input i carries W64^(KSTEP i).
+template <int MODE, int KSTEP, int IA, int IB>
+__device__ __forceinline__ void dft8_pair(const c64 (&t)[8], const c64* w, const FftConsts& kc, c64& x, c64& y) {
+    if constexpr (MODE == 0) {
+        x = cadd(t[IA], t[IB]);
+        y = csub(t[IA], t[IB]);
+    } else if constexpr (MODE == 1) {
+        const c64 p = (IA == 0) ? t[IA] : cmul(t[IA], w[IA]);
+        bfly_tw(p, t[IB], w[IB], kc, x, y);
+    } else {
+        const c64 p = (IA == 0) ? t[IA] : cmul_w64<KSTEP * IA>(t[IA], kc);
+        bfly_w64<KSTEP * IB>(p, t[IB], kc, x, y);
+    }
+}
+// forward 8-point DFT of (t_i w_i), natural order in and out: 26 packed instructions plain, 36 with seven twiddles
+template <int MODE, int KSTEP>
+__device__ __forceinline__ void dft8_tw(c64 (&t)[8], const c64* w, const FftConsts& kc) {
+    c64 s04, d04, s26, d26, s15, d15, s37, d37;
+    dft8_pair<MODE, KSTEP, 0, 4>(t, w, kc, s04, d04);
+    dft8_pair<MODE, KSTEP, 2, 6>(t, w, kc, s26, d26);
+    dft8_pair<MODE, KSTEP, 1, 5>(t, w, kc, s15, d15);
+    dft8_pair<MODE, KSTEP, 3, 7>(t, w, kc, s37, d37);
+    const c64 e0 = cadd(s04, s26), e2 = csub(s04, s26), e1 = cadd_mi(d04, d26), e3 = cadd_pi(d04, d26);
+    const c64 o0 = cadd(s15, s37), o2 = csub(s15, s37), o1 = cadd_mi(d15, d37), o3 = cadd_pi(d15, d37);
+    t[0] = cadd(e0, o0);
+    t[4] = csub(e0, o0);
+    bfly_w64<8>(e1, o1, kc, t[1], t[5]);            // W8
+    t[2] = cadd_mi(e2, o2);
+    t[6] = cadd_pi(e2, o2);
+    bfly_w64<24>(e3, o3, kc, t[3], t[7]);           // W8^3
+}
+
+// second level of the 64-point DFT: column K2 of a[n1][k2] carries W64^(n1 K2) (TWMODE 0, 1) or the uniform factors
+// wu[(n1 (2 K2 + 1)) & 127] (TWMODE 2: W64^(n1 K2) times the W128^(n1) left over from the split kernel's input twiddle)
+template <int TWMODE, int K2>
+__device__ __forceinline__ void dft64_cols(c64 (&a)[8][8], c64 (&v)[64], const FftConsts& kc, const float2* wu) {
+    if constexpr (K2 < 8) {
+        c64 t[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; n1++) t[n1] = a[n1][K2];
+        if constexpr (TWMODE == 2) {
+            c64 w[8];
+#pragma unroll
+            for (int n1 = 1; n1 < 8; n1++) w[n1] = *reinterpret_cast<const c64*>(&wu[8 + 8 * K2 + n1]);
+            dft8_tw<1, 0>(t, w, kc);
+        } else if constexpr (K2 == 0) {
+            dft8_tw<0, 0>(t, nullptr, kc);
+        } else {
+            dft8_tw<2, K2>(t, nullptr, kc);
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) v[8 * k1 + K2] = t[k1];
+        dft64_cols<TWMODE, K2 + 1>(a, v, kc, wu);
+    }
+}
+// forward 64-point DFT, 64 = 8 x 8 with n = n1 + 8 n2, k = 8 k1 + k2:  W64^(n k) = W8^(n2 k2) W64^(n1 k2) W8^(n1 k1).
+// TWMODE 0: of v.  TWMODE 1: of v[m] z^m, given za[n2] = z^(8 n2) and zb[n1] = z^(n1) (n1, n2 = 1..7; index 0 unused):
+// z^(8 n2) rides in the first level's butterflies, z^(n1) multiplies that level's outputs.  TWMODE 2: of v[m] W128^m, the
+// odd half of a split burst: W128^(n1 + 8 n2) = W128^(n1) W64^(4 n2), the second factor in the first level's butterflies,
+// the first merged into the second level's twiddles (wu = the 128 powers of W128, uniform).
+template <int TWMODE>
+__device__ __forceinline__ void dft64_f(c64 (&v)[64], const FftConsts& kc, const c64* za, const c64* zb, const float2* wu) {
+    c64 a[8][8];
+#pragma unroll
+    for (int n1 = 0; n1 < 8; n1++) {
+        c64 t[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) t[n2] = v[n1 + 8 * n2];
+        if constexpr (TWMODE == 1) dft8_tw<1, 0>(t, za, kc);
+        else if constexpr (TWMODE == 2) {
+            c64 w[8];
+#pragma unroll
+            for (int n2 = 1; n2 < 8; n2++) w[n2] = *reinterpret_cast<const c64*>(&wu[n2]);
+            dft8_tw<1, 0>(t, w, kc);
+        }
+        else dft8_tw<0, 0>(t, nullptr, kc);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) a[n1][k2] = (TWMODE == 1 && n1 > 0) ? cmul(t[k2], zb[n1]) : t[k2];
+    }
+    dft64_cols<TWMODE, 0>(a, v, kc, wu);
+}
+
 template <int SKEW>
 __host__ __device__ constexpr int fft_skew(int i) { return i + i / SKEW; }
 
@@ -471,7 +635,8 @@ struct FftArgs {
     float im_sign;         // +1 forward, -1 inverse (inverse = conj(FFT(conj(x))))
     float scale;           // 1/N forward (fft.c:105-107), 1 inverse (fft.c:122-128)
     float2 kbase[16];      // (cos, sin) and (cos, -sin) of 2 pi r / 32, r = 1..4, then of 2 pi r / 64, r = 1, 3, 5, 7: see FftConsts
-    float2 w128[64];       // exp(-2 pi i r / 128), r = 0..63 (the split 8192-point kernel's input factors)
+    float2 two;            // (2, 2)
+    float2 wsplit[2][72];  // the split 8192-point kernel's stage-0 factors per half, see fft_wsplit_host
 };
 
 // One Stockham stage for the P points a thread owns: radix R, sub-transform length NS already done.
@@ -529,19 +694,13 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
         c64 v[R];
         if (FIRST && SPLIT) {
             // the radix-2 step of the decimation in frequency, as the burst is read: x[n] +- x[n + N], n = j + r STRIDE
-            if (fl == 0) {
+            // x[n] + x[n + N] (even-bin half) or x[n] - x[n + N] (odd-bin half) through one instruction stream: x0 + s x1
+            const float sg = fl ? -1.0f : 1.0f;
+            const c64 sgn = pack2(sg, sg);
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    v[r] = cadd(fd.dst[j + r * STRIDE], fd.dst[j + r * STRIDE + N]);
-                    if (GEN) v[r] = cconj_if(v[r], imsgn);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; r++) {
-                    v[r] = csub(fd.dst[j + r * STRIDE], fd.dst[j + r * STRIDE + N]);
-                    if (GEN) v[r] = cconj_if(v[r], imsgn);
-                    if (r > 0) v[r] = cmul(v[r], *reinterpret_cast<const c64*>(&w128[r]));      // W128^r; w^j is in the next stage's twiddles
-                }
+            for (int r = 0; r < R; r++) {
+                v[r] = fma2(fd.dst[j + r * STRIDE + N], sgn, fd.dst[j + r * STRIDE]);
+                if (GEN) v[r] = cconj_if(v[r], imsgn);               // the odd half's factor w^n = w^j W128^r: W128^r inside the DFT below, w^j in the next stage's twiddles
             }
         }
 #pragma unroll
@@ -562,11 +721,7 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
             if (FIRST && GEN && !SPLIT) v[r] = cconj_if(v[r], imsgn);    // inverse = conj(FFT(conj x))
         }
         if (TW2L) {
-#pragma unroll
-            for (int m = 1; m < R; m++) {
-                if (m / 8 > 0) v[m] = cmul(v[m], tw2[m / 8 - 1]);
-                if (m % 8 > 0) v[m] = cmul(v[m], tw2[7 + m % 8 - 1]);
-            }
+            // applied inside dft64_f<1> below
         } else if (NS > 1 && !PRETW) {
 #pragma unroll
             for (int m = 1; m < R; m++) {
@@ -601,7 +756,20 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
                 }
             }
         }
-        dft_small<R>(v, kc);
+        if constexpr (R == 64) {
+            if constexpr (TW2L) {
+                c64 za[8], zb[8];
+#pragma unroll
+                for (int i = 1; i < 8; i++) { za[i] = tw2[i - 1]; zb[i] = tw2[7 + i - 1]; }
+                dft64_f<1>(v, kc, za, zb, nullptr);
+            } else if constexpr (FIRST && SPLIT) {
+                dft64_f<2>(v, kc, nullptr, nullptr, w128 + fl * 72);      // w128: the half's row of FftArgs::wsplit
+            } else {
+                dft64_f<0>(v, kc, nullptr, nullptr, nullptr);
+            }
+        } else {
+            dft_small<R>(v, kc);
+        }
         if (TWOUT) {
             // output q of butterfly j is input r' = j R RNEXT / N of the next stage's butterfly q: times w^(q r'), table [q - 1][r']
             const c64* two = stw + (j * (R * RNEXT)) / N;
@@ -721,6 +889,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
         kc.bp64[r] = *reinterpret_cast<const c64*>(&a.kbase[8 + r]);
         kc.bm64[r] = *reinterpret_cast<const c64*>(&a.kbase[12 + r]);
     }
+    kc.two = *reinterpret_cast<const c64*>(&a.two);
     constexpr int WPF = (TPF > 32) ? TPF / 32 : 1;      // warps per transform
     const int wib = threadIdx.x >> 5;
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(red_idx + 64) + fl;      // one per transform of the CTA
@@ -761,7 +930,7 @@ __global__ void __launch_bounds__(FftCfg<LOG2N>::THREADS, FftCfg<LOG2N>::MINB) f
             }
         }
         c64 pts[P];
-        fft_stages<SL, 1, true, GEN, SPLIT>(pts, sdat, stw + (SPLIT ? half * (14 * 64) : 0), gin, js, base + half * Sub::N, SPLIT ? half : fl, a.im_sign, kc, fd, a.w128);
+        fft_stages<SL, 1, true, GEN, SPLIT>(pts, sdat, stw + (SPLIT ? half * (14 * 64) : 0), gin, js, base + half * Sub::N, SPLIT ? half : fl, a.im_sign, kc, fd, &a.wsplit[0][0]);
         // bin of pts[i]: a half of a split burst holds every other bin
         auto out_index = [&](int i) { return SPLIT ? 2 * fft_out_index<SL>(js, i) + half : fft_out_index<SL>(js, i); };
 

@@ -1324,7 +1324,8 @@ static int fft_run(qpsk_b200_fft* f, const float* d_in, float* d_out, int nburst
     a.im_sign = inverse ? -1.0f : 1.0f;
     a.scale = inverse ? 1.0f : 1.0f / (float)f->n;           // fft.c:105-107 vs fft.c:130-136
     fft_consts_host(a.kbase);
-    fft_w128_host(a.w128);
+    fft_wsplit_host(a.wsplit);
+    fft_two_host(a.two);
     CU(cudaEventRecord(f->ev[0], s));
     cudaError_t e = launch_fft(f->log2n, a, f->nsm, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "FFT kernel launch failed: %s", cudaGetErrorString(e));

@@ -46,7 +46,8 @@ static void run(int nsm, size_t nbursts_req, const char* label, double hbm_peak)
     FftArgs a;
     a.in = d_in; a.spectrum = nullptr; a.bin = d_bin; a.mag2 = d_mag; a.tw = d_tw; a.nbursts = (int)nb; a.im_sign = 1.0f; a.scale = 1.0f / n;
     fft_consts_host(a.kbase);
-    fft_w128_host(a.w128);
+    fft_wsplit_host(a.wsplit);
+    fft_two_host(a.two);
     CK(cudaFuncSetAttribute(fft_kernel<LOG2N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     CK(cudaFuncSetAttribute(fft_kernel<LOG2N, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
