@@ -269,7 +269,8 @@ int qpsk_b200_tx_create(float fs, float rs, float rrc_alpha, const float *carrie
 int qpsk_b200_tx_destroy(qpsk_b200_tx *tx);
 int qpsk_b200_tx_reset(qpsk_b200_tx *tx);
 /* symbols: uint8 [C][nsym], constellation index per symbol = (tx_bits[2k] << 1) | tx_bits[2k+1] (qpsk.c:270,278-279);
- * pcm: int16 [C][nsym*sps].  nsym must be a multiple of 128/sps.  Device pointers, asynchronous. */
+ * pcm: int16 [C][nsym*sps], 8-byte aligned.  Any nsym >= 1, as tx_frame takes any length (qpsk.c:225-264).  Device pointers,
+ * asynchronous. */
 int qpsk_b200_tx_process_device(qpsk_b200_tx *tx, const uint8_t *d_symbols, int nsym, int16_t *d_pcm, void *cuda_stream);
 int qpsk_b200_tx_process_host(qpsk_b200_tx *tx, const uint8_t *h_symbols, int nsym, int16_t *h_pcm);
 /* new carriers from the next call on: fbb_tx_rect = cmplx(TAU * carrier / FS) again (qpsk.c:320), the up-mix phasor keeps

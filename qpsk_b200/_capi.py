@@ -136,3 +136,4 @@ def _bind_tx(L):
     L.qpsk_b200_tx_reset.argtypes = [C.c_void_p]
     L.qpsk_b200_tx_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.qpsk_b200_tx_process_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.qpsk_b200_tx_end_packet.argtypes = [C.c_void_p]

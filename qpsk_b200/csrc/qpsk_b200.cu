@@ -75,6 +75,7 @@ template <int NTAPS>
 static TapBank<NTAPS> tap_bank(const float* taps) {
     TapBank<NTAPS> tb;
     for (int i = 0; i < NTAPS; i++) tb.t[i] = make_float2(taps[i], taps[i]);
+    tb.one = make_float2(1.0f, 1.0f);
     return tb;
 }
 
@@ -1137,8 +1138,9 @@ static int fir_run(qpsk_b200_fir* f, float* d_samples, int c0, int nc, int nsamp
     if (timed) CU(cudaEventRecord(f->ev[0], s));
     cudaError_t e;
     const bool fast = f->mode == QPSK_B200_MODE_FAST;
-    if (f->ntaps == 127) e = fast ? launch_fir<127, QPSK_MODE_FAST>(f, a, s) : launch_fir<127, QPSK_MODE_EXACT>(f, a, s);
-    else                 e = fast ? launch_fir<256, QPSK_MODE_FAST>(f, a, s) : launch_fir<256, QPSK_MODE_EXACT>(f, a, s);
+    // exact mode of the general filter: the IEEE form (no flush to zero: rrc_fir takes any float input, rrc_fir.c:24-26)
+    if (f->ntaps == 127) e = fast ? launch_fir<127, QPSK_MODE_FAST>(f, a, s) : launch_fir<127, QPSK_MODE_IEEE>(f, a, s);
+    else                 e = fast ? launch_fir<256, QPSK_MODE_FAST>(f, a, s) : launch_fir<256, QPSK_MODE_IEEE>(f, a, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "FIR kernel launch failed: %s", cudaGetErrorString(e));
     if (timed) { CU(cudaEventRecord(f->ev[1], s)); f->timed = true; }
     return QPSK_B200_OK;
@@ -1573,6 +1575,7 @@ struct qpsk_b200_tx {
     float2* d_hist;      // [Cpad][128/sps]
     uint8_t* d_sym_stage;  int16_t* d_pcm_stage;  size_t stage_syms;
     cudaStream_t stream;
+    cudaStream_t last_stream;   // the stream the most recent modulate call ran on (end_packet / reset order themselves after it)
 };
 
 extern "C" int qpsk_b200_tx_destroy(qpsk_b200_tx* tx) {
@@ -1588,6 +1591,7 @@ extern "C" int qpsk_b200_tx_destroy(qpsk_b200_tx* tx) {
 extern "C" int qpsk_b200_tx_reset(qpsk_b200_tx* tx) {
     if (!tx) return fail(QPSK_B200_ERR_ARG, "null transmitter");
     CU(cudaSetDevice(tx->device));
+    CU(cudaDeviceSynchronize());          // the legacy-stream copies below do not order themselves after non-blocking streams
     float c0[2];
     qpsk_host_cis(0.0, 0, c0);                                                  // qpsk.c:316 fbb_tx_phase = cmplx(0)
     float2* ph = new float2[tx->Cpad];
@@ -1689,8 +1693,8 @@ static cudaError_t launch_tx(const TxArgs& a, const float* taps, cudaStream_t s)
 
 static int tx_run(qpsk_b200_tx* tx, const uint8_t* d_symbols, const float2* d_symbols_cf, int nsym, int16_t* d_pcm, void* cuda_stream) {
     if (!tx || (!d_symbols && !d_symbols_cf) || !d_pcm) return fail(QPSK_B200_ERR_ARG, "null argument");
-    const int ts = QPSK_CHUNK / tx->sps;
-    if (nsym < ts || nsym % ts != 0) return fail(QPSK_B200_ERR_ARG, "nsym %d must be a positive multiple of %d", nsym, ts);
+    if (nsym < 1) return fail(QPSK_B200_ERR_ARG, "nsym %d must be positive", nsym);
+    if ((reinterpret_cast<uintptr_t>(d_pcm) & 7) != 0) return fail(QPSK_B200_ERR_ARG, "d_pcm must be 8-byte aligned");
     CU(cudaSetDevice(tx->device));
     cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : tx->stream;
     TxArgs a;
@@ -1698,7 +1702,8 @@ static int tx_run(qpsk_b200_tx* tx, const uint8_t* d_symbols, const float2* d_sy
     a.C = tx->C; a.Cpad = tx->Cpad; a.nsym = nsym; a.packet_samples = tx->packet_samples; a.sample_pos = tx->sample_pos;
     cudaError_t e = tx->sps == 4 ? launch_tx<4>(a, tx->taps, s) : launch_tx<8>(a, tx->taps, s);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "tx kernel launch failed: %s", cudaGetErrorString(e));
-    tx->sample_pos = (tx->sample_pos + nsym * tx->sps) % tx->packet_samples;
+    tx->sample_pos = (int)(((long long)tx->sample_pos + (long long)nsym * tx->sps) % tx->packet_samples);
+    tx->last_stream = s;
     return QPSK_B200_OK;
 }
 
@@ -1756,9 +1761,11 @@ extern "C" int qpsk_b200_tx_end_packet(qpsk_b200_tx* tx) {
     if (!tx) return fail(QPSK_B200_ERR_ARG, "null transmitter");
     CU(cudaSetDevice(tx->device));
     if (tx->sample_pos != 0) {     // not already normalised by a packet boundary inside the last call
-        tx_normalise_kernel<<<(tx->Cpad + 127) / 128, 128, 0, tx->stream>>>(tx->d_phase, tx->Cpad);
+        // on the stream the last modulate call used: the kernel there stores the phasor this one normalises
+        cudaStream_t s = tx->last_stream ? tx->last_stream : tx->stream;
+        tx_normalise_kernel<<<(tx->Cpad + 127) / 128, 128, 0, s>>>(tx->d_phase, tx->Cpad);
         CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(tx->stream));
+        CU(cudaStreamSynchronize(s));
         tx->sample_pos = 0;
     }
     return QPSK_B200_OK;

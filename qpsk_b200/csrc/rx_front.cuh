@@ -14,7 +14,7 @@
 #include "common.cuh"
 #include "rx_costas.cuh"
 
-enum { QPSK_MODE_EXACT = 0, QPSK_MODE_FAST = 1 };
+enum { QPSK_MODE_EXACT = 0, QPSK_MODE_FAST = 1, QPSK_MODE_IEEE = 2 };
 enum { QPSK_UB_ALIAS = 0, QPSK_UB_CLAMP = 1, QPSK_UB_PHASE = 2 };
 
 // Taps duplicated into both halves of a 64-bit constant: the packed-FP32 multiplier operand.  The bank is a
@@ -24,6 +24,7 @@ enum { QPSK_UB_ALIAS = 0, QPSK_UB_CLAMP = 1, QPSK_UB_PHASE = 2 };
 template <int NTAPS>
 struct TapBank {
     float2 t[NTAPS];
+    float2 one;        // (1, 1): the operand that makes an FFMA2 a plain rounded add, see fir_tap<QPSK_MODE_IEEE>
 };
 
 // --------------------------------------------------------------------------------------------
@@ -65,10 +66,17 @@ __global__ void phasor_table_kernel(const float2* __restrict__ prev_table, int p
 // d - r, so walking d upwards accumulates every output oldest-tap-first from +0, exactly the
 // order of rrc_fir.c:22-26.
 // --------------------------------------------------------------------------------------------
+// QPSK_MODE_EXACT: FMUL2.FTZ + FADD2, the receiver's form (its products are never subnormal, see mul2_exact).
+// QPSK_MODE_IEEE : FMUL2 + FFMA2(acc, (1, 1), product) -- acc * 1 + p rounds once, exactly like acc + p, for every input
+//                  including subnormal ones, and a multiply cannot be contracted into the ADDEND of an FMA: the form of
+//                  the general rrc_fir entry points, which must not flush (rrc_fir.c:24-26 does not).  Same two packed
+//                  instructions per tap.  `one` arrives as a kernel argument so that it stays opaque to the optimiser.
+// QPSK_MODE_FAST : FFMA2, fused (not bit-exact).
 template <int MODE>
-__device__ __forceinline__ void fir_tap(u64& acc, const u64 xv, const float2* __restrict__ taps2, const int i) {
+__device__ __forceinline__ void fir_tap(u64& acc, const u64 xv, const float2* __restrict__ taps2, const int i, const u64 one) {
     const u64 cc = *reinterpret_cast<const u64*>(&taps2[i]);
     if (MODE == QPSK_MODE_EXACT) acc = add2(acc, mul2_exact(xv, cc));
+    else if (MODE == QPSK_MODE_IEEE) acc = fma2(acc, one, mul2(xv, cc));
     else acc = fma2(xv, cc, acc);
 }
 
@@ -82,13 +90,14 @@ template <int NTAPS, int R, int MODE>
 __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, const float2* __restrict__ taps2, u64 (&acc)[R]) {
     constexpr int STEADY = NTAPS - R + 1;            // d = R-1 .. NTAPS-1
     constexpr int TRIPS = STEADY / R, REM = STEADY % R;
+    const u64 one = *reinterpret_cast<const u64*>(&taps2[NTAPS]);      // TapBank::one
 #pragma unroll
     for (int r = 0; r < R; r++) acc[r] = 0ull;       // (+0, +0)
 #pragma unroll
     for (int d = 0; d < R - 1; d++) {                // head
         const u64 xv = x[d];
 #pragma unroll
-        for (int r = 0; r <= d; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r);
+        for (int r = 0; r <= d; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r, one);
     }
 #pragma unroll 1
     for (int m = 0; m < TRIPS; m++) {                // steady, rolled
@@ -97,20 +106,20 @@ __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, const float
         for (int e = 0; e < R; e++) {
             const u64 xv = x[d0 + e];
 #pragma unroll
-            for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d0 + e - r);
+            for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d0 + e - r, one);
         }
     }
 #pragma unroll
     for (int d = R - 1 + TRIPS * R; d < R - 1 + TRIPS * R + REM; d++) {   // steady remainder
         const u64 xv = x[d];
 #pragma unroll
-        for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r);
+        for (int r = 0; r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r, one);
     }
 #pragma unroll
     for (int d = NTAPS; d < NTAPS - 1 + R; d++) {    // tail
         const u64 xv = x[d];
 #pragma unroll
-        for (int r = d - (NTAPS - 1); r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r);
+        for (int r = d - (NTAPS - 1); r < R; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r, one);
     }
 }
 

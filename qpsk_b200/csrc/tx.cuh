@@ -60,31 +60,36 @@ __global__ void __launch_bounds__(256, 3) tx_kernel(const __grid_constant__ TxAr
     int pos = a.sample_pos;
     __syncthreads();
 
-    const int ntiles = a.nsym / TS;
+    // any length (qpsk.c:225-264 takes any): the last tile may be partial.  Its missing symbols are zeros that only meet
+    // outputs which are never stored, the phasor stops at the call's last sample, and the history keeps the last TS real symbols.
+    const int ntiles = (a.nsym + TS - 1) / TS;
+    int valid = TS;                                      // real symbols of the current tile
     for (int k = 0; k < ntiles; k++) {
+        valid = (a.nsym - k * TS < TS) ? a.nsym - k * TS : TS;
         // shift own symbol slots and load this tile's symbols
 #pragma unroll
         for (int e = 0; e < SPT; e++) {
             const int i = w * SPT + e;
             srow[i] = srow[TS + i];
-            if (a.symbols_cf != nullptr) srow[TS + i] = reinterpret_cast<const u64*>(a.symbols_cf)[(size_t)chl * a.nsym + (size_t)k * TS + i];
+            if (i >= valid) srow[TS + i] = 0ull;
+            else if (a.symbols_cf != nullptr) srow[TS + i] = reinterpret_cast<const u64*>(a.symbols_cf)[(size_t)chl * a.nsym + (size_t)k * TS + i];
             else srow[TS + i] = point(symrow[(size_t)k * TS + i] & 3u);
         }
         __syncthreads();
 
         // warp 0: the up-mix phasor of every sample of the tile, qpsk.c:248-253 (lane = channel)
         if (w == 0) {
-            for (int t = 0; t < QPSK_CHUNK; t++) {
+            const int nsamp = valid * SPS;
+            for (int t = 0; t < nsamp; t++) {
                 phase = cmul_exact(phase, rect);
                 sm.ph[lane][t] = phase;
-            }
-            pos += QPSK_CHUNK;
-            if (pos >= a.packet_samples) {           // end of a tx_frame call: normalise
-                const double dr = (double)phase.x, di = (double)phase.y;
-                const float mag = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(di, di))));
-                phase.x = __fdiv_rn(phase.x, mag);
-                phase.y = __fdiv_rn(phase.y, mag);
-                pos = 0;
+                if (++pos == a.packet_samples) {     // end of a tx_frame call: normalise (qpsk.c:253)
+                    const double dr = (double)phase.x, di = (double)phase.y;
+                    const float mag = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(di, di))));
+                    phase.x = __fdiv_rn(phase.x, mag);
+                    phase.y = __fdiv_rn(phase.y, mag);
+                    pos = 0;
+                }
             }
         }
 
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(256, 3) tx_kernel(const __grid_constant__ TxAr
             unpack2(acc[r], yr, yi);
             yr = gain_exact(yr);                                       // rrc_fir.c:28
             yi = gain_exact(yi);
-            const float2 p = sm.ph[lane][strip + r];
+            const float2 p = sm.ph[lane][strip + r];                   // (stale beyond a partial tile's end: those outputs are not stored)
             const float re = __fsub_rn(__fmul_rn(yr, p.x), __fmul_rn(yi, p.y));   // crealf(signal[i] * fbb_tx_phase), qpsk.c:250
             sm.out[lane][strip + r] = (short)__float2int_rz(__fmul_rn(re, 16384.0f));   // qpsk.c:260 truncation
         }
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(256, 3) tx_kernel(const __grid_constant__ TxAr
         // coalesced store: each warp writes 4 channel rows, 8 bytes per lane
         for (int rr = w; rr < QPSK_GROUP; rr += 8) {
             const int c = blockIdx.x * QPSK_GROUP + rr;
-            if (c < a.C) {
+            if (c < a.C && lane * 4 < valid * SPS) {                  // valid * SPS is a multiple of 4: whole 8-byte groups
                 const uint2 v = *reinterpret_cast<const uint2*>(&sm.out[rr][lane * 4]);
                 *reinterpret_cast<uint2*>(a.pcm + (size_t)c * a.nsym * SPS + (size_t)k * QPSK_CHUNK + lane * 4) = v;
             }
@@ -133,7 +138,8 @@ __global__ void __launch_bounds__(256, 3) tx_kernel(const __grid_constant__ TxAr
     }
     __syncthreads();
     if (live) {
-        for (int i = w; i < TS; i += 8) reinterpret_cast<u64*>(a.sym_hist)[(size_t)ch * TS + i] = srow[TS + i];
+        // the last TS real symbols: slots [valid, valid + TS) of (previous tile | current tile)
+        for (int i = w; i < TS; i += 8) reinterpret_cast<u64*>(a.sym_hist)[(size_t)ch * TS + i] = srow[valid + i];
         if (w == 0) a.phase_state[ch] = phase;
     }
 }

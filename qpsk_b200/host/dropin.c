@@ -168,8 +168,8 @@ void qpsk_demod(complex float symbol, int bits[2]) {                 /* qpsk.c:7
 static void need_tx(void) {
     if (!g_tx) {
         const float carrier = (float)g_tx_carrier;
-        /* one packet per call: the phasor is renormalised at the end of every tx_frame (qpsk.c:253);
-         * 32 symbols is the smallest unit the kernel accepts, so any multiple of it behaves like one call */
+        /* one packet per call: the phasor is renormalised at the end of every tx_frame (qpsk.c:253), whatever its
+         * length: tx_frame / qpsk_packet_mod end the packet themselves (qpsk_b200_tx_end_packet) */
         MUST(qpsk_b200_tx_create(9600.0f, (float)g_tx_rs, .35f, &carrier, 1, 1 << 20, 0, &g_tx));
     }
 }

@@ -50,6 +50,10 @@ class Transmitter:
                                                       C.c_void_p(stream) if stream else None))
 
 
+    def end_packet(self):
+        """End the current tx_frame call now: the up-mix phasor is renormalised (qpsk.c:253) and the packet position restarts."""
+        capi.check(self.L.qpsk_b200_tx_end_packet(self.h))
+
     def set_carrier(self, carrier_hz):
         """New per-channel carriers from the next call on (phase-continuous): steps of a Doppler ramp."""
         c = np.ascontiguousarray(carrier_hz, np.float32)

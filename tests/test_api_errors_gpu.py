@@ -101,10 +101,11 @@ def test_fir_fft_bits_tx_argument_checks():
     assert L.qpsk_b200_frames_decode_rotated(bp, 32, 1, 1, bp, bp, None, 0) == ERR_ARG
     crc = np.zeros(2, np.uint16)
     assert L.qpsk_b200_bits_crc16(bp, 44, 0, crc.ctypes.data_as(C.c_void_p), 0) == ERR_ARG
-    # transmit: a packet is a whole number of 128-sample tiles
+    # transmit: any positive length is fine (tests/test_tx_gpu.py::test_any_length); zero is not
     tx = qpsk_b200.Transmitter(np.full(3, 1500.0, np.float32))
+    assert tx.modulate(np.zeros((3, 33), np.uint8)).shape == (3, 132)
     with pytest.raises(qpsk_b200.QpskB200Error):
-        tx.modulate(np.zeros((3, 33), np.uint8))
+        tx.modulate(np.zeros((3, 0), np.uint8))
     tx.close()
 
 

@@ -57,6 +57,33 @@ def test_fir_exact_vs_oracle_with_carried_delay_line(oracle_lib, ntaps, rs, ncha
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ntaps,rs", [(127, 2400.0), (256, 1200.0)])
+def test_fir_subnormal_products_bit_exact(oracle_lib, ntaps, rs):
+    """rrc_fir is a general filter (rrc_fir.c:24-26 multiplies and adds whatever it is given, nothing is flushed): inputs so
+    small that tap products, partial sums or the inputs themselves are subnormal must still come out bit for bit -- the
+    general entry points use the non-flushing FMUL2 + FFMA2(acc, 1, p) form, not the receiver's FMUL2.FTZ + FADD2."""
+    import qpsk_b200
+    o = oracle_lib.Oracle()
+    taps = qpsk_b200.rrc_make(ntaps, 9600.0, rs, 0.35)
+    rng = np.random.default_rng(ntaps)
+    nchan, n = 9, 900
+    f = qpsk_b200.Fir(taps, nchan)
+    mem = np.zeros((nchan, ntaps), np.complex64)
+    for scale in (1e-34, 1e-37, 3e-39, 1e-42):          # products subnormal / sums subnormal / inputs subnormal / a few ulps of the smallest
+        x = ((rng.normal(size=(nchan, n)) + 1j * rng.normal(size=(nchan, n))) * scale).astype(np.complex64)
+        x[0, ::7] = 0                                    # signed zeros and exact cancellations ride along
+        x[1, 1::5] = -x[1, 0:-1:5]
+        want = x.copy()
+        for c in range(nchan):
+            o.fir(taps, mem[c], want[c])
+        got = f.filter(x.copy())
+        assert np.any(want != 0) or scale < 1e-41
+        assert bits_equal(got, want), scale
+        assert bits_equal(f.memory, mem), scale
+    f.close()
+
+
+@pytest.mark.gpu
 def test_fir_impulse_and_linearity(oracle_lib):
     import qpsk_b200
     taps = qpsk_b200.rrc_make(127, 9600.0, 2400.0, 0.35)

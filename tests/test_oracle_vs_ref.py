@@ -99,6 +99,20 @@ def test_bit_stages_and_fft_random(oracle_lib):
         assert bits_equal(a.fftn(x, inverse=True), o.fftn(x, inverse=True)), n
 
 
+def test_tx_any_length_against_compiled_reference(oracle_lib):
+    """qpsk_packet_mod / tx_frame (qpsk.c:225-285) accept any length; calls of 1, 7, 33, 255 ... symbols with the filter memory and
+    the phasor carried between them, oracle vs the compiled reference."""
+    for flavour, rs in (("2400", 2400.0), ("1200", 1200.0)):
+        r = _need(oracle_lib, flavour)
+        o = oracle_lib.Oracle(rs=rs)
+        rng = np.random.default_rng(int(rs))
+        r.tx_reset(1531.0)
+        st = o.new_tx(1531.0)
+        for n in (1, 7, 33, 255, 256, 40, 3, 129):
+            bits = rng.integers(0, 2, 2 * n, dtype=np.int32)
+            assert np.array_equal(o.packet_mod(st, bits), r.packet_mod(bits)), (flavour, n)
+
+
 def test_glibc_sincos_restatement_matches_host_libm(oracle_lib):
     """oracle.orc_glibc_{sinf,cosf} restate glibc 2.39's FMA-variant sinf/cosf, which the device NCO
     follows.  Strided sweep over every float in [-7, 7] (the loop phase never leaves [-TAU, TAU]);

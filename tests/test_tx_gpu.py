@@ -40,6 +40,46 @@ def test_pcm_bit_exact_vs_oracle_with_streaming(oracle_lib, rs, nchan, npackets)
     tx.close()
 
 
+@pytest.mark.parametrize("rs", [2400.0, 1200.0])
+def test_any_length(oracle_lib, rs):
+    """tx_frame / qpsk_packet_mod take any length (qpsk.c:225-264), not only whole 128-sample tiles: calls of 1, 7, 33, 255 ...
+    symbols, each its own packet (phasor renormalised at the end of every call, qpsk.c:253), history carried between them."""
+    import qpsk_b200
+    o = oracle_lib.Oracle(rs=rs)
+    nchan, lengths = 5, [1, 7, 33, 255, 256, 40, 3, 129]
+    rng = np.random.default_rng(int(rs) + 1)
+    carriers = (1500.0 + rng.uniform(-75, 75, nchan)).astype(np.float32)
+    bits = [rng.integers(0, 2, (nchan, 2 * n), dtype=np.int32) for n in lengths]
+    tx = qpsk_b200.Transmitter(carriers, rs=rs, packet_symbols=1 << 20)
+    states = [o.new_tx(float(c)) for c in carriers]
+    for n, b in zip(lengths, bits):
+        want = np.stack([o.packet_mod(states[c], b[c]) for c in range(nchan)])
+        got = tx.modulate(qpsk_b200.bits_to_symbols(b))
+        tx.end_packet()
+        assert got.shape == (nchan, n * o.sps)
+        assert np.array_equal(got, want), "length %d" % n
+    tx.close()
+
+
+def test_packet_boundary_inside_a_ragged_call(oracle_lib):
+    """packets of 256 symbols fed in calls that do not divide them: the phasor is renormalised at exactly the packet's last sample"""
+    import qpsk_b200
+    o = oracle_lib.Oracle()
+    rng = np.random.default_rng(9)
+    bits = rng.integers(0, 2, (3, 4, 512), dtype=np.int32)
+    carriers = np.array([1450.0, 1500.0, 1571.5], np.float32)
+    want = np.zeros((3, 4 * 1024), np.int16)
+    for c in range(3):
+        st = o.new_tx(float(carriers[c]))
+        want[c] = np.concatenate([o.packet_mod(st, bits[c, k]) for k in range(4)])
+    tx = qpsk_b200.Transmitter(carriers)
+    syms = qpsk_b200.bits_to_symbols(bits.reshape(3, -1))
+    cuts = [0, 100, 101, 300, 555, 1024]
+    got = np.concatenate([tx.modulate(syms[:, a:b]) for a, b in zip(cuts[:-1], cuts[1:])], axis=1)
+    assert np.array_equal(got, want)
+    tx.close()
+
+
 def test_tx_then_rx_loopback_is_what_the_reference_does(oracle_lib):
     """The reference's experiment (qpsk.c:289-359) on the GPU end to end: modulate at CENTER+50 Hz,
     receive, and compare the decisions with the oracle receiving the oracle's PCM."""
@@ -58,14 +98,15 @@ def test_tx_then_rx_loopback_is_what_the_reference_does(oracle_lib):
     tx.close(); rx.close()
 
 
-def test_tx_rejects_ragged_symbol_counts():
+def test_tx_rejects_empty_calls():
     import ctypes as C
     import qpsk_b200
     from qpsk_b200 import capi
     tx = qpsk_b200.Transmitter([1500.0])
     s = np.zeros((1, 33), np.uint8)
     pcm = np.zeros((1, 33 * 4), np.int16)
-    assert capi.lib().qpsk_b200_tx_process_host(tx.h, s.ctypes.data_as(C.c_void_p), 33, pcm.ctypes.data_as(C.c_void_p)) == -1
+    assert capi.lib().qpsk_b200_tx_process_host(tx.h, s.ctypes.data_as(C.c_void_p), 0, pcm.ctypes.data_as(C.c_void_p)) == -1
+    assert capi.lib().qpsk_b200_tx_process_host(tx.h, s.ctypes.data_as(C.c_void_p), 33, pcm.ctypes.data_as(C.c_void_p)) == 0
     tx.close()
 
 
