@@ -535,13 +535,15 @@ def bench_config4(ctx, pool, want_cpu):
         ms_max = qpsk_b200.shard.max_over_ranks(ms, device=ctx.dev)
         if ctx.rank == 0:
             by = nb * (8 * n + 8)
+            traffic, traffic_src = profiled_traffic("fft_kernel", "r0*_fft%d_v*final.summary.csv" % n)      # captured at 131,072 bursts
             recs.append({"config": "configs[4]", "workload": "FFT + |X|^2 argmax, n = %d, %d bursts per GPU x %d GPU(s) (tone at a random bin + AWGN), complex float in HBM"
                                                             % (n, nb, ctx.world),
                          "n": n, "ms": ms_max, "iters": iters, "value": tot[0] * n / ms_max / 1e3, "unit": "Msamples/s", "bursts_per_s": tot[0] / (ms_max * 1e-3),
                          "bursts": int(tot[0]), "argmax_equals_tone": int(tot[1]), "argmax_checksum": int(tot[2]),
                          "roofline": {"bound": "hbm", "kernel": "fft_kernel<%d,estimator>" % int(np.log2(n)), "achieved": by / (km * 1e-3) / 1e9, "peak": ctx.hbm_peak,
                                       "unit": "GB/s", "frac": by / (km * 1e-3) / 1e9 / ctx.hbm_peak, "kernel_ms": km, "bytes_per_burst": 8 * n + 8, "peak_kind": ctx.hbm_kind,
-                                      "traffic": None, "gflops": 5.0 * n * np.log2(n) * nb / (km * 1e-3) / 1e9},
+                                      "traffic": traffic * (nb / 131072.0) if traffic else None, "traffic_source": traffic_src,
+                                      "gflops": 5.0 * n * np.log2(n) * nb / (km * 1e-3) / 1e9},
                          "l2": "%.2f GiB of bursts per GPU exceeds L2" % (nb * n * 8 / 2 ** 30), "clocks": clocks})
             if want_cpu:
                 from oracle import RefAlg
@@ -553,6 +555,30 @@ def bench_config4(ctx, pool, want_cpu):
         f.close()
         del x, tone, tone_all
     return recs
+
+
+def bench_stream(ctx):
+    """SURVEY 8(f) row 3, streaming ingest: the continuous receiver over one raw s16le file per channel (the reference's
+    on-disk format and read loop, qpsk.h:14, qpsk.c:339-354), 1,024 channels x 1,000 frames from the page cache."""
+    import tempfile
+    torch, qpsk_b200 = ctx.torch, ctx.qpsk_b200
+    Cn, F = 1024, 1000
+    pcm = synth_pcm_gpu(torch, qpsk_b200, Cn, F * FRAME, ctx.dev, ctx.local, seed=23).cpu().numpy()
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for c in range(Cn):
+            pth = os.path.join(d, "ch%04d.raw" % c)
+            pcm[c].astype("<i2").tofile(pth)
+            paths.append(pth)
+        stats = {}
+        qpsk_b200.receive_files(paths, frames_per_call=250, device=ctx.local, keep=False, stats=stats)      # warm-up: page cache, contexts
+        stats = {}
+        qpsk_b200.receive_files(paths, frames_per_call=250, device=ctx.local, keep=False, stats=stats)
+    return {"config": "8(f)-3 streaming ingest", "workload": "qpsk_b200_stream_run: 1,024 raw s16le files (one per channel) x 1,000 frames, batches of 250 frames read by host "
+                                                             "threads while the GPU works on the previous batch (submit_host / wait), dibits delivered to a sink",
+            "value": stats["samples_per_s"] / 1e6, "unit": "Msamples/s", "seconds": stats["seconds"], "read_seconds": stats["read_seconds"],
+            "wait_seconds": stats["wait_seconds"], "reader_threads": stats["readers"], "frames": stats["frames"],
+            "note": "wall clock of the whole run, files in the page cache; read_seconds / wait_seconds are the host's time in fread and in qpsk_b200_rx_wait"}
 
 
 def bench_config0(ctx):
@@ -791,6 +817,7 @@ def main():
                 configs.append(bench_config0(ctx))
                 configs.append(bench_config1(ctx, pool, want_cpu))
                 configs.extend(bench_config3(ctx, pool, want_cpu))
+                configs.append(bench_stream(ctx))
             configs.extend(bench_config4(ctx, pool, want_cpu))
         except Exception as ex:      # the headline stands on its own
             configs.append({"error": "%s: %s" % (type(ex).__name__, ex)})

@@ -49,8 +49,11 @@ enum { QPSK_B200_MODE_EXACT = 0,   /* reference arithmetic, bit-exact decisions 
        QPSK_B200_MODE_FAST = 1 };  /* fused multiply-add FIR (<= 1e-5 relative), not bit-exact */
 enum { QPSK_B200_UB_ALIAS = 0,     /* reproduce the Makefile-build out-of-frame read of qpsk.c:190 */
        QPSK_B200_UB_CLAMP = 1,     /* fenced: out-of-frame reads return the last sample of the frame */
-       QPSK_B200_UB_PHASE = 2 };   /* extension, not the reference: the timing index only picks the sampling phase
+       QPSK_B200_UB_PHASE = 2,     /* extension, not the reference: the timing index only picks the sampling phase
                                       (sample i*CYCLES + index % CYCLES), so no symbol is ever taken from outside the frame */
+       QPSK_B200_UB_TAU = 3 };     /* extension ("sample at tau"): the histogram index is replaced by round(tau) mod CYCLES, tau the
+                                      square-law timing estimate of the frame (OUT_TIMING_TAU): the sample nearest to the eye's
+                                      maximum, stable from frame to frame.  OUT_INDEX then reports that phase */
 
 enum {                              /* cfg.flags */
     QPSK_B200_KEEP_FIR = 1,         /* keep the matched-filter output (16 B/sample!) for parity checks */
@@ -71,6 +74,10 @@ enum {                              /* cfg.flags */
                                        reference's amplitude histogram; OUT_TIMING_SUM / OUT_TIMING_TAU.  The decisions do not use it */
     QPSK_B200_RESOLVE_ROTATION = 16,/* with DECODE_FRAMES: a frame whose CRC fails is retried with its dibits turned back
                                        by 90, 180 and 270 degrees (the loop's phase ambiguity); first match wins */
+    QPSK_B200_PREROTATE_OFFSET = 512, /* extension: in the first call after create / reset the FFT frequency estimator (4th power of the
+                                       call's first symbols -> FFT -> argmax, see ESTIMATE_OFFSET, which this flag implies) runs BEFORE the
+                                       Costas loop and seeds every channel's d_freq with its estimate, set_frequency(TAU * offset_hz / RS):
+                                       the loop starts locked instead of pulling in.  Later calls are unchanged */
     QPSK_B200_NO_CHUNK = 256        /* never cut a call into frame chunks (with few channels a long call is processed as
                                        chunks of frames so that the Costas loop of one chunk runs under the front end of
                                        the next; results are identical either way) */

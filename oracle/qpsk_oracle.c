@@ -230,6 +230,11 @@ void orc_rx_frame(const orc_profile *p, orc_rx_state *s, const int16_t *pcm, con
         const int h = hist_i[k] + hist_q[k];
         if (h > hmax) { hmax = h; index = k; }
     }
+    if (p->ub_mode == ORC_UB_TAU) {                              /* extension: the sample nearest to the eye's maximum */
+        orc_cf S;
+        orc_timing_sum(frame, N, sps, &S);
+        index = orc_tau_index(S, sps);
+    }
     if (t && t->index) *t->index = index;
 
     /* 4. decimate with a one-frame delay, qpsk.c:186-191.  For sps == 4 and index >= 4 the
@@ -343,6 +348,21 @@ static void timing_half(const float *y, int stride, int n, int sps, float *re_ou
         }
     }
     *re_out = re; *im_out = im;
+}
+
+/* round(tau) mod sps, tau = -arg(S) sps / (2 pi), as the sector of S: comparisons and (at 8 samples per symbol) one rounded
+ * multiply, in the order of tau_index() in rx_front.cuh */
+int orc_tau_index(orc_cf S, int sps) {
+    const float ax = fabsf(S.re), ay = fabsf(S.im);
+    if (sps == 4) {
+        if (ax >= ay) return S.re >= 0.0f ? 0 : 2;
+        return S.im < 0.0f ? 1 : 3;
+    }
+    const float T = 0.41421356237309503f;
+    if (ay <= T * ax) return S.re >= 0.0f ? 0 : 4;
+    if (ax <= T * ay) return S.im < 0.0f ? 2 : 6;
+    if (S.im < 0.0f) return S.re > 0.0f ? 1 : 3;
+    return S.re > 0.0f ? 7 : 5;
 }
 
 void orc_timing_sum(const orc_cf *frame, int n, int sps, orc_cf *out) {

@@ -35,7 +35,8 @@ typedef struct { double re, im; } orc_cd;
 
 enum { ORC_UB_ALIAS = 0, /* Makefile (-O0) build: input_frame[512+k] aliases decimated_frame[k] */
        ORC_UB_CLAMP = 1, /* fenced variant: out-of-frame reads return input_frame[FRAME_SIZE-1] */
-       ORC_UB_PHASE = 2  /* extension: sample i*CYCLES + index % CYCLES, never out of frame */ };
+       ORC_UB_PHASE = 2, /* extension: sample i*CYCLES + index % CYCLES, never out of frame */
+       ORC_UB_TAU = 3    /* extension: index = round(tau) mod CYCLES from the square-law timing sum (orc_tau_index) */ };
 
 /* ---- RRC FIR: rrc_fir.c:17-76 -------------------------------------------------------- */
 void orc_rrc_make(float *taps, int ntaps, float fs, float rs, float alpha);
@@ -102,6 +103,7 @@ void orc_qpsk_demod(const orc_profile *p, orc_cf sym, int bits[2]);
 void orc_awgn(int16_t *pcm, long long nsamples, float sigma, uint64_t seed, long long first_sample, int channel);
 /* extension, parity unpinned: square-law timing statistic of one filtered frame (see the .c file) */
 void orc_timing_sum(const orc_cf *frame, int n, int sps, orc_cf *out);
+int  orc_tau_index(orc_cf S, int sps);
 void orc_profile_slice_diagonal(orc_profile *p, int on);
 
 /* ---- transmit: qpsk.c:58-63,225-285 --------------------------------------------------- */

@@ -28,8 +28,8 @@ class StreamStats(C.Structure):
 STREAM_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_uint8))
 
 MODE_EXACT, MODE_FAST = 0, 1
-UB_ALIAS, UB_CLAMP, UB_PHASE = 0, 1, 2
-KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL, ESTIMATE_OFFSET, ESTIMATE_TIMING, NO_CHUNK = 1, 2, 4, 8, 16, 32, 64, 128, 256
+UB_ALIAS, UB_CLAMP, UB_PHASE, UB_TAU = 0, 1, 2, 3
+KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL, ESTIMATE_OFFSET, ESTIMATE_TIMING, NO_CHUNK, PREROTATE_OFFSET = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK, OUT_ROTATION, OUT_OFFSET_BIN, OUT_OFFSET_HZ, OUT_TIMING_SUM, OUT_TIMING_TAU = range(14)
 
 _lib = None

@@ -126,6 +126,7 @@ struct qpsk_b200_rx {
     int inflight;                           // submitted host calls not yet waited for (at most 2)
     bool needs_reset;                       // a host call failed half way
     bool no_chunk;                          // QPSK_B200_NO_CHUNK
+    bool prerotate, loop_seeded;            // QPSK_B200_PREROTATE_OFFSET; the first call after a reset has seeded the loop
     cudaStream_t s_loop;                    // the loop of frame chunk k runs here, under the front end of chunk k+1
     cudaEvent_t ev_front;
     int nsm, sm_clock_khz;                  // launch policy inputs, read from the device
@@ -212,7 +213,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     const int sps = (int)((double)cfg->fs / (double)cfg->rs);   // CYCLES, qpsk.h:21
     if (sps != 4 && sps != 8) return fail(QPSK_B200_ERR_ARG, "samples/symbol %d unsupported (4 = 2400 baud, 8 = 1200 baud)", sps);
     if (cfg->mode != QPSK_B200_MODE_EXACT && cfg->mode != QPSK_B200_MODE_FAST) return fail(QPSK_B200_ERR_ARG, "bad mode");
-    if (cfg->ub_mode < QPSK_B200_UB_ALIAS || cfg->ub_mode > QPSK_B200_UB_PHASE) return fail(QPSK_B200_ERR_ARG, "bad ub_mode %d", cfg->ub_mode);
+    if (cfg->ub_mode < QPSK_B200_UB_ALIAS || cfg->ub_mode > QPSK_B200_UB_TAU) return fail(QPSK_B200_ERR_ARG, "bad ub_mode %d", cfg->ub_mode);
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(QPSK_B200_ERR_CUDA, "CUDA device %d not present (%d devices)", cfg->device, ndev);
@@ -288,7 +289,8 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         alloc((void**)&rx->d_counters, 2 * sizeof(unsigned long long));
     }
     if (cfg->flags & QPSK_B200_ESTIMATE_TIMING) alloc((void**)&rx->d_timing_t, F * Cp * sizeof(float2));
-    if (cfg->flags & QPSK_B200_ESTIMATE_OFFSET) {
+    rx->prerotate = (cfg->flags & QPSK_B200_PREROTATE_OFFSET) != 0;
+    if (cfg->flags & (QPSK_B200_ESTIMATE_OFFSET | QPSK_B200_PREROTATE_OFFSET)) {
         rx->est_on = true;
         alloc((void**)&rx->d_est_bursts, (size_t)nchan * 1024 * sizeof(float2));
         alloc((void**)&rx->d_est_bins, (size_t)nchan * sizeof(int));
@@ -329,6 +331,7 @@ extern "C" int qpsk_b200_rx_reset(qpsk_b200_rx* rx) {
     CU(cudaStreamSynchronize(s));
     rx->slot_base = 0;
     rx->lastF = 0;
+    rx->loop_seeded = false;
     rx->inflight = 0;
     rx->needs_reset = false;
     return QPSK_B200_OK;
@@ -557,6 +560,29 @@ static int rx_launch_estimator(qpsk_b200_rx* rx, int c0, int c1, int F, int firs
     return 0;
 }
 
+// PREROTATE_OFFSET: d_freq of every channel from the estimator's bin, as set_frequency(TAU * offset_hz / RS) would
+// (costas_loop.c:117-125 clamps to [min_freq, max_freq]); offset_hz = signed bin * rs / (4 n), rounded to float as OUT_OFFSET_HZ is
+__global__ void seed_loop_freq_kernel(float2* __restrict__ loop_state, const int* __restrict__ bins, int c0, int c1, int n, float rs,
+                                      float min_freq, float max_freq) {
+    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    const int b = bins[c], sb = b >= n / 2 ? b - n : b;
+    const float hz = __double2float_rn(__ddiv_rn(__dmul_rn((double)sb, (double)rs), (double)(4 * n)));
+    float f = __double2float_rn(__ddiv_rn(__dmul_rn(6.283185307179586476925286766559, (double)hz), (double)rs));
+    f = fminf(fmaxf(f, min_freq), max_freq);
+    loop_state[c].y = f;
+}
+
+static int rx_seed_loop(qpsk_b200_rx* rx, int c0, int c1, int F, int first_slot, cudaStream_t s) {
+    int rc = rx_launch_estimator(rx, c0, c1, F, first_slot, s);
+    if (rc) return rc;
+    seed_loop_freq_kernel<<<(c1 - c0 + 127) / 128, 128, 0, s>>>(rx->d_loop_state, rx->d_est_bins, c0, c1, rx->est_call_n, rx->cfg.rs,
+                                                                  rx->loop.min_freq, rx->loop.max_freq);
+    CU(cudaGetLastError());
+    rx->launches += 1;
+    return 0;
+}
+
 // Frame chunks of a call.  With few channels the loop cannot ride along in the front end (a CTA would have to own whole
 // streams and there are too few CTAs for that), and as one kernel after the front end it is a pure latency chain:
 // 1,024 streams x 16,384 symbols x ~540 cycles = 4.7 ms behind a 2.3 ms front end.  Cutting the call into frame chunks
@@ -564,6 +590,7 @@ static int rx_launch_estimator(qpsk_b200_rx* rx, int c0, int c1, int F, int firs
 // chunk k+1 in and chunk k-1 out meanwhile.  State carries between chunks exactly as between calls.
 static int rx_plan_chunks(const qpsk_b200_rx* rx, int nc, int F) {
     if (rx->d_fir_dbg || rx->d_costas_dbg || rx->no_chunk) return F;         // debug taps are indexed by the call's frames
+    if (rx->prerotate && !rx->loop_seeded) return F;                          // the seeding call: front end, estimator, then the loop
     const int ngroups = (nc + QPSK_GROUP - 1) / QPSK_GROUP;
     if (F < 32) return F;
     if (rx_frame_blocks(rx, ngroups, nc, F, false) == 1) return F;            // the fused kernel is the better plan
@@ -578,6 +605,10 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
     const int fc = rx_plan_chunks(rx, rx->C, F);
     const bool chunked = fc < F;
     const int first_slot = (rx->slot_base + 1) % rx->nslots;
+    // PREROTATE_OFFSET, first call after a reset: the loop runs as its own kernel, after the estimator has seeded it
+    const bool seeding = rx->prerotate && !rx->loop_seeded;
+    const bool saved_no_fuse = rx->no_fuse;
+    if (seeding) rx->no_fuse = true;
     bool loop_stream_used = false;
     int k = 0;
     rx->timed_loop = false;
@@ -585,10 +616,11 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
         RxJob j;
         j.d_pcm = d_pcm + (size_t)f0 * rx->N; j.pcm_row = pcm_row; j.c0 = 0; j.nc = rx->C; j.F = (F - f0 < fc) ? F - f0 : fc; j.f_off = f0;
         int rc = rx_begin_chunk(rx, j.F, s);
-        if (rc) return rc;
+        if (rc) { rx->no_fuse = saved_no_fuse; return rc; }
         bool fused = false;
         rc = rx_launch_front(rx, j, chunked, s, &fused, k);
-        if (rc) return rc;
+        if (!rc && seeding) rc = rx_seed_loop(rx, 0, rx->C, F, first_slot, s);
+        if (rc) { rx->no_fuse = saved_no_fuse; return rc; }
         cudaStream_t sl = s;
         if (chunked && !fused) {
             sl = rx->s_loop;
@@ -606,7 +638,8 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
         CU(cudaEventRecord(rx->ev_front, rx->s_loop));
         CU(cudaStreamWaitEvent(s, rx->ev_front, 0));
     }
-    if (rx->est_on) {
+    if (seeding) { rx->no_fuse = saved_no_fuse; rx->loop_seeded = true; }
+    if (rx->est_on && !seeding) {
         int rc = rx_launch_estimator(rx, 0, rx->C, F, first_slot, s);
         if (rc) return rc;
     }
@@ -836,6 +869,7 @@ static int rx_host_abort(qpsk_b200_rx* rx, int rc) {
     cudaStreamSynchronize(rx->s_loop);
     cudaStreamSynchronize(rx->s_out);
     rx->inflight = 0;
+    rx->no_fuse = (rx->cfg.flags & QPSK_B200_NO_FUSE) != 0;      // a seeding call (PREROTATE_OFFSET) may have been cut short
     rx->needs_reset = true;      // some jobs of the call ran, others did not: channel state is inconsistent
     return rc;
 }
@@ -875,6 +909,9 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
     }
     cudaStream_t sc = rx->stream;
     const int first_slot = (rx->slot_base + 1) % rx->nslots;
+    const bool seeding = rx->prerotate && !rx->loop_seeded && !copy_only;      // see rx_run_call
+    const bool saved_no_fuse = rx->no_fuse;
+    if (seeding) rx->no_fuse = true;
     bool loop_stream_used = false;
     for (int f0 = 0; f0 < F; f0 += fc) {
         const int Fj = (F - f0 < fc) ? F - f0 : fc;
@@ -900,7 +937,8 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
             if (!copy_only) {
                 bool fused = false;
                 rc = rx_launch_front(rx, j, chunked, sc, &fused);
-                if (rc) return rx_host_abort(rx, rc);
+                if (!rc && seeding) rc = rx_seed_loop(rx, c0, (c0 + nc < C) ? c0 + nc : C, F, first_slot, sc);
+                if (rc) { rx->no_fuse = saved_no_fuse; return rx_host_abort(rx, rc); }
                 CU(cudaEventRecord(rx->ev_cmp[b], sc));         // the PCM staging buffer is free again
                 if (chunked && !fused) {
                     sr = rx->s_loop;
@@ -937,7 +975,8 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
         CU(cudaEventRecord(rx->ev_front, rx->s_loop));
         CU(cudaStreamWaitEvent(sc, rx->ev_front, 0));
     }
-    if (rx->est_on && !copy_only) {
+    if (seeding) { rx->no_fuse = saved_no_fuse; rx->loop_seeded = true; }
+    if (rx->est_on && !copy_only && !seeding) {
         rc = rx_launch_estimator(rx, 0, C, F, first_slot, sc);
         if (rc) return rx_host_abort(rx, rc);
     }

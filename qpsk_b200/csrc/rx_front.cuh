@@ -15,7 +15,7 @@
 #include "rx_costas.cuh"
 
 enum { QPSK_MODE_EXACT = 0, QPSK_MODE_FAST = 1, QPSK_MODE_IEEE = 2 };
-enum { QPSK_UB_ALIAS = 0, QPSK_UB_CLAMP = 1, QPSK_UB_PHASE = 2 };
+enum { QPSK_UB_ALIAS = 0, QPSK_UB_CLAMP = 1, QPSK_UB_PHASE = 2, QPSK_UB_TAU = 3 };
 
 // Taps duplicated into both halves of a 64-bit constant: the packed-FP32 multiplier operand.  The bank is a
 // __grid_constant__ kernel parameter, i.e. it lives in the launch's own slice of the constant bank: every
@@ -205,6 +205,24 @@ __device__ __forceinline__ void timing_accumulate(const int j, const float p, fl
     }
 }
 
+// Extension (QPSK_UB_TAU): the sampling phase as the sample nearest to the eye's maximum, round(tau) mod SPS with
+// tau = -arg(S) SPS / (2 pi): the sector of S, found with comparisons only (one rounded multiply at 8 samples per symbol), so
+// the oracle decides identically (orc_tau_index).
+template <int SPS>
+__device__ __forceinline__ int tau_index(const float re, const float im) {
+    const float ax = fabsf(re), ay = fabsf(im);
+    if (SPS == 4) {
+        if (ax >= ay) return re >= 0.0f ? 0 : 2;
+        return im < 0.0f ? 1 : 3;
+    } else {
+        const float T = 0.41421356237309503f;            // tan(pi / 8)
+        if (ay <= __fmul_rn(T, ax)) return re >= 0.0f ? 0 : 4;
+        if (ax <= __fmul_rn(T, ay)) return im < 0.0f ? 2 : 6;
+        if (im < 0.0f) return re > 0.0f ? 1 : 3;
+        return re > 0.0f ? 7 : 5;
+    }
+}
+
 // named barriers (id 0 is __syncthreads)
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -331,7 +349,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
             u64 hist = 0ull;
             // extension (ESTIMATE_TIMING): this component's half of S = sum_n y_n^2 e^{-2 pi i n / SPS}, the symbol-rate line
             // of the squared matched-filter output (Oerder & Meyr); its argument is the sampling phase of the eye
-            const bool est = a.timing_t != nullptr;
+            const bool est = a.timing_t != nullptr || a.ub_mode == QPSK_UB_TAU;
             float sre = 0.0f, sim = 0.0f;
             for (int t = 0; t < tiles_per_frame; t++) {
                 bar_sync(BAR_FULL, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
@@ -380,11 +398,13 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
                     if (h > hmax) { hmax = h; index = kk; }
                 }
             }
-            if (comp == 0 && live) a.index_t[(size_t)f * a.Cpad + ch] = index;
-            if (est && comp == 0 && live) {
+            if (est) {
                 const float2 ti = sm.tsum[0][lane], tq = sm.tsum[1][lane];
-                a.timing_t[(size_t)f * a.Cpad + ch] = make_float2(__fadd_rn(ti.x, tq.x), __fadd_rn(ti.y, tq.y));
+                const float2 S = make_float2(__fadd_rn(ti.x, tq.x), __fadd_rn(ti.y, tq.y));
+                if (a.timing_t != nullptr && comp == 0 && live) a.timing_t[(size_t)f * a.Cpad + ch] = S;
+                if (a.ub_mode == QPSK_UB_TAU) index = tau_index<SPS>(S.x, S.y);       // both warps of the pair decide alike
             }
+            if (comp == 0 && live) a.index_t[(size_t)f * a.Cpad + ch] = index;
             if (a.fir_dbg != nullptr && live) {                    // parity tap: the whole filtered frame
                 float2* dst = a.fir_dbg + (size_t)ch * ((size_t)a.F * N) + (size_t)f * N;
                 for (int i = comp; i < N; i += 2) dst[i] = make_float2(__ldcg(scr_at(i, 0)), __ldcg(scr_at(i, 1)));
