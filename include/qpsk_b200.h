@@ -78,6 +78,10 @@ enum {                              /* cfg.flags */
                                        call's first symbols -> FFT -> argmax, see ESTIMATE_OFFSET, which this flag implies) runs BEFORE the
                                        Costas loop and seeds every channel's d_freq with its estimate, set_frequency(TAU * offset_hz / RS):
                                        the loop starts locked instead of pulling in.  Later calls are unchanged */
+    QPSK_B200_TRANSIENT_SYMBOLS = 1024, /* the decimated symbols are a hand-off between the timing stage and the loop, not an output:
+                                       when the loop rides along in the front-end kernel, a ring slot is dropped from L2 without write-back
+                                       (discard.global.L2) as soon as the loop has consumed it, which halves the kernel's HBM write traffic.
+                                       QPSK_B200_OUT_DEC is then unavailable; every other output is unchanged */
     QPSK_B200_NO_CHUNK = 256        /* never cut a call into frame chunks (with few channels a long call is processed as
                                        chunks of frames so that the Costas loop of one chunk runs under the front end of
                                        the next; results are identical either way) */

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqpsk_b200.so")
+LIB_PATH = os.environ.get("QPSK_B200_LIB") or os.path.join(HERE, "libqpsk_b200.so")      # the override is for A/B builds of the same library
 
 
 class QpskB200Error(RuntimeError):
@@ -29,7 +29,7 @@ STREAM_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(
 
 MODE_EXACT, MODE_FAST = 0, 1
 UB_ALIAS, UB_CLAMP, UB_PHASE, UB_TAU = 0, 1, 2, 3
-KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL, ESTIMATE_OFFSET, ESTIMATE_TIMING, NO_CHUNK, PREROTATE_OFFSET = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL, ESTIMATE_OFFSET, ESTIMATE_TIMING, NO_CHUNK, PREROTATE_OFFSET, TRANSIENT_SYMBOLS = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
 OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK, OUT_ROTATION, OUT_OFFSET_BIN, OUT_OFFSET_HZ, OUT_TIMING_SUM, OUT_TIMING_TAU = range(14)
 
 _lib = None

@@ -130,8 +130,10 @@ struct qpsk_b200_rx {
     cudaStream_t s_loop;                    // the loop of frame chunk k runs here, under the front end of chunk k+1
     cudaEvent_t ev_front;
     int nsm, sm_clock_khz;                  // launch policy inputs, read from the device
-    float* d_front_scratch; // front-end per-CTA frame scratch (lazy, grow-only)
+    size_t l2_persist_bytes, l2_window_bytes;   // persisting-L2 carve-out set aside for the frame scratch, largest access-policy window
+    float* d_front_scratch; // front-end frame scratch: nsm * QPSK_SCRATCH_SLOTS shared slots, then one private region per CTA (grow-only)
     size_t front_scratch_bytes;
+    int* d_scratch_slots;   // [nsm * QPSK_SCRATCH_SLOTS] claim flags of the shared slots
     qpsk_b200_fft* est_fft; int est_fft_n;   // estimator extension (lazy)
     void* d_scratch;        // transposed download staging (lazy)
     size_t scratch_bytes;
@@ -168,7 +170,8 @@ static int rx_free(qpsk_b200_rx* rx) {
     void* ptrs[] = { rx->d_pcm_tail, rx->d_phasor2[0], rx->d_phasor2[1], rx->d_ph_state2, rx->d_dec_ring, rx->d_index_t,
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
                      rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, rx->d_est_bursts, rx->d_est_bins, rx->d_est_mag, rx->d_timing_t,
-                     rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch };
+                     rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch,
+                     rx->d_scratch_slots };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev_fr) if (e) cudaEventDestroy(e);
     for (auto& e : rx->ev_lp) if (e) cudaEventDestroy(e);
@@ -194,14 +197,32 @@ static int rx_free(qpsk_b200_rx* rx) {
 extern "C" int qpsk_b200_rx_destroy(qpsk_b200_rx* rx) { return rx_free(rx); }
 
 template <int NTAPS, int SPS, int MODE>
-static cudaError_t launch_front(const RxFrontArgs& a, const float* taps, int grid, cudaStream_t s) {
+static cudaError_t launch_front(const RxFrontArgs& a, const float* taps, int grid, cudaStream_t s, size_t persist_bytes, size_t persist_window) {
     const size_t smem = sizeof(RxFrontSmem<SPS>);
     cudaError_t e = cudaFuncSetAttribute(rx_front_kernel<NTAPS, SPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(rx_front_kernel<NTAPS, SPS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
-    rx_front_kernel<NTAPS, SPS, MODE><<<grid, QPSK_FRONT_THREADS, smem, s>>>(a, tap_bank<NTAPS>(taps));
-    return cudaGetLastError();
+    // The per-CTA frame scratch is rewritten every frame and re-read within the frame: its lines are marked persisting in L2
+    // for this launch (an access-policy window as a launch attribute: nothing is changed on the caller's stream), so that
+    // the PCM streaming through does not send them on a round trip to HBM.
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(QPSK_FRONT_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    int nattr = 0;
+    if (persist_bytes > 0 && a.scratch != nullptr) {
+        const size_t live = (size_t)a.scratch_nslots * 512 * 2 * QPSK_GROUP * sizeof(float);      // the shared slots, not the fallback regions
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = a.scratch;
+        attr[0].val.accessPolicyWindow.num_bytes = live < persist_window ? live : persist_window;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        nattr = 1;
+    }
+    cfg.attrs = attr; cfg.numAttrs = nattr;
+    return cudaLaunchKernelEx(&cfg, rx_front_kernel<NTAPS, SPS, MODE>, a, tap_bank<NTAPS>(taps));
 }
 
 extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, int max_frames, qpsk_b200_rx** out) {
@@ -232,6 +253,20 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     rx->sm_clock_khz = 0;
     cudaDeviceGetAttribute(&rx->sm_clock_khz, cudaDevAttrClockRate, cfg->device);      // the device's own boost clock
     if (rx->sm_clock_khz <= 0) rx->sm_clock_khz = 1965000;
+    {
+        // room in L2 for the resident CTAs' frame scratch (2 per SM x 128 KB), if the device offers a persisting carve-out
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg->device);
+        size_t want = (size_t)2 * rx->nsm * 512 * 2 * QPSK_GROUP * sizeof(float);
+        if ((size_t)max_persist < want) want = (size_t)max_persist;
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            rx->l2_persist_bytes = want;
+            rx->l2_window_bytes = (size_t)max_window;
+        } else {
+            cudaGetLastError();
+        }
+    }
     rx->id = g_next_id++;
     rx->C = nchan;
     rx->Cpad = (nchan + QPSK_GROUP - 1) / QPSK_GROUP * QPSK_GROUP;
@@ -271,9 +306,10 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         long long ctas = (long long)(rx->Cpad / QPSK_GROUP) * max_frames;
         const long long cap = (long long)(rx->Cpad / QPSK_GROUP) > 16LL * rx->nsm ? (long long)(rx->Cpad / QPSK_GROUP) : 16LL * rx->nsm;
         if (ctas > cap) ctas = cap;
-        rx->front_scratch_bytes = (size_t)ctas * 512 * 2 * QPSK_GROUP * sizeof(float);
+        rx->front_scratch_bytes = (size_t)(ctas + (long long)rx->nsm * QPSK_SCRATCH_SLOTS) * 512 * 2 * QPSK_GROUP * sizeof(float);
         e = cudaMalloc((void**)&rx->d_front_scratch, rx->front_scratch_bytes);
         if (e != cudaSuccess) rx->front_scratch_bytes = 0;
+        if (e == cudaSuccess) e = cudaMalloc((void**)&rx->d_scratch_slots, (size_t)rx->nsm * QPSK_SCRATCH_SLOTS * sizeof(int));
     }
     alloc((void**)&rx->d_dec_ring, (F + 1) * S * Cp * sizeof(float2));
     alloc((void**)&rx->d_index_t, F * Cp * sizeof(int));
@@ -328,6 +364,7 @@ extern "C" int qpsk_b200_rx_reset(qpsk_b200_rx* rx) {
     // d_phase = d_freq = 0 (costas_loop.c:32-33)
     CU(cudaMemsetAsync(rx->d_loop_state, 0, Cp * sizeof(float2), s));
     if (rx->d_counters) CU(cudaMemsetAsync(rx->d_counters, 0, 2 * sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(rx->d_scratch_slots, 0, (size_t)rx->nsm * QPSK_SCRATCH_SLOTS * sizeof(int), s));      // every slot free
     CU(cudaStreamSynchronize(s));
     rx->slot_base = 0;
     rx->lastF = 0;
@@ -457,7 +494,7 @@ static int rx_ensure_front_scratch(qpsk_b200_rx* rx, int grid) {
     // per-CTA frame scratch (512 samples x 2 components x 32 lanes of float); rewritten every frame, so it lives in L2.
     // Sized once for the largest grid any call can ask for (every channel group x every frame), so no allocation ever
     // happens in the middle of a stream-ordered call.
-    const size_t need = (size_t)grid * 512 * 2 * QPSK_GROUP * sizeof(float);
+    const size_t need = (size_t)(grid + rx->nsm * QPSK_SCRATCH_SLOTS) * 512 * 2 * QPSK_GROUP * sizeof(float);
     if (rx->front_scratch_bytes >= need) return 0;
     CU(cudaDeviceSynchronize());
     if (rx->d_front_scratch) { cudaFree(rx->d_front_scratch); rx->d_front_scratch = nullptr; rx->front_scratch_bytes = 0; }
@@ -476,6 +513,11 @@ static CostasArgs rx_costas_args(const qpsk_b200_rx* rx, const RxJob& j) {
     ca.C = rx->C; ca.Cpad = rx->Cpad; ca.F = j.F; ca.nsym = rx->nsym; ca.sps = rx->sps; ca.N = rx->N;
     ca.c0 = j.c0; ca.c1 = (j.c0 + j.nc < rx->C) ? j.c0 + j.nc : rx->C;
     ca.slot_base = rx->slot_base; ca.nslots = rx->nslots; ca.ub_mode = rx->cfg.ub_mode;
+    // TRANSIENT_SYMBOLS: the estimator reads the call's first symbols after the kernel, those slots stay
+    ca.discard_from = -1;
+    if (rx->cfg.flags & QPSK_B200_TRANSIENT_SYMBOLS)
+        ca.discard_from = rx->est_on ? (est_burst_length(rx, j.F + j.f_off) + rx->nsym - 1) / rx->nsym + 1 - j.f_off : 1;
+    if (ca.discard_from >= 0 && ca.discard_from < 1) ca.discard_from = 1;
     ca.alpha = rx->loop.alpha; ca.beta = rx->loop.beta; ca.max_freq = rx->loop.max_freq; ca.min_freq = rx->loop.min_freq;
     ca.rot45 = rx->rot45;
     return ca;
@@ -499,14 +541,17 @@ static int rx_launch_front(qpsk_b200_rx* rx, const RxJob& j, bool loop_overlappe
     int rc = rx_ensure_front_scratch(rx, grid);      // a no-op after creation (sized for Cpad/32 x maxF CTAs)
     if (rc) return rc;
     fa.scratch = rx->d_front_scratch;
+    fa.scratch_slots = rx->d_scratch_slots;
+    fa.scratch_nslots = rx->nsm * QPSK_SCRATCH_SLOTS;
     const bool fused = (fblocks == 1) && !rx->no_fuse;
     fa.fuse_costas = fused ? 1 : 0;
     fa.costas = rx_costas_args(rx, j);
     cudaError_t e;
     const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
     if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_fr[2 * timed_chunk], s));
-    if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, rx->taps, grid, s) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, rx->taps, grid, s);
-    else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, rx->taps, grid, s) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, rx->taps, grid, s);
+    const size_t pb = rx->l2_persist_bytes, pw = rx->l2_window_bytes;
+    if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, rx->taps, grid, s, pb, pw) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, rx->taps, grid, s, pb, pw);
+    else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, rx->taps, grid, s, pb, pw) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, rx->taps, grid, s, pb, pw);
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
     if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_fr[2 * timed_chunk + 1], s));
     // carry the last 128 PCM samples of every channel (the next chunk's filter history)
@@ -814,6 +859,7 @@ extern "C" int qpsk_b200_rx_read(qpsk_b200_rx* rx, int what, void* h_dst, size_t
             CU(cudaMemcpy(h_dst, rx->d_fir_dbg, need, cudaMemcpyDeviceToHost));
             return 0;
         case QPSK_B200_OUT_DEC: {
+            if (rx->cfg.flags & QPSK_B200_TRANSIENT_SYMBOLS) return fail(QPSK_B200_ERR_STATE, "the decimated symbols were not kept (QPSK_B200_TRANSIENT_SYMBOLS)");
             // frames of the last call live in ring slots (slot_base_before + 1 + f); slot_base already advanced by F
             const int base_before = ((rx->slot_base - F) % rx->nslots + rx->nslots) % rx->nslots;
             int rc = ensure_scratch(rx, need + (size_t)F * S * rx->Cpad * sizeof(float2));

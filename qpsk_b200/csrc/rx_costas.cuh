@@ -19,6 +19,8 @@ struct CostasArgs {
     int C, Cpad, F, nsym, sps, N;
     int c0, c1;              // channels [c0, c1) are processed by the standalone kernel launch
     int slot_base, nslots, ub_mode;
+    int discard_from;        // QPSK_B200_TRANSIENT_SYMBOLS: ring slots consumed by frame 0 and by frames >= discard_from are dropped from L2
+                             // without write-back once the loop has read them (-1: every slot is kept, OUT_DEC stays readable)
     float alpha, beta, max_freq, min_freq;
     float2 rot45;            // cmplx(ROTATE45) from the host libm, qpsk.c:75
 };
@@ -106,6 +108,18 @@ __device__ __forceinline__ void costas_run_frame(const CostasArgs& a, const Cost
         }
     }
     a.track_t[(size_t)f * a.Cpad + c] = make_float2(phase, freq);
+}
+
+// The ring slot frame f has just consumed is dead (nobody reads it again: the next reader of that slot is a later call's frame
+// after it has been rewritten): drop its lines from L2 instead of letting them be written back to HBM.  One warp = the 32
+// channels of a group = two 128-byte lines per symbol.
+__device__ __forceinline__ void costas_discard_slot(const CostasArgs& a, int f, int group_first_channel, int lane) {
+    if (a.discard_from < 0 || !(f == 0 || f >= a.discard_from)) return;
+    const char* base = reinterpret_cast<const char*>(a.dec_ring + (size_t)((a.slot_base + f) % a.nslots) * ((size_t)a.nsym * a.Cpad) + group_first_channel);
+    for (int i = lane; i < 2 * a.nsym; i += 32) {
+        const char* q = base + (size_t)(i >> 1) * a.Cpad * sizeof(float2) + (size_t)(i & 1) * 128;
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(q) : "memory");
+    }
 }
 
 __device__ __forceinline__ CostasParams costas_params(const CostasArgs& a) {

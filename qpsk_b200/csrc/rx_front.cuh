@@ -132,7 +132,11 @@ struct RxFrontArgs {
     int*    index_t;           // [F][Cpad] timing index per frame
     float2* fir_dbg;           // optional [C][F*N] matched-filter output (parity taps), may be null
     float2* timing_t;          // optional [F][Cpad] spectral-line timing statistic per frame (extension), may be null
-    float*  scratch;           // [grid][512][2][32] the current frame's filter output per CTA (L2-resident: rewritten every frame)
+    float*  scratch;           // [nsm * QPSK_SCRATCH_SLOTS + grid][512][2][32] the current frame's filter output per CTA: a CTA claims one of
+                               // its SM's slots (the first nsm * SLOTS regions: rewritten every frame by whoever is resident, so they
+                               // live in L2 and never travel to HBM) and falls back to the region of its block index if none is free
+    int*    scratch_slots;     // [nsm * QPSK_SCRATCH_SLOTS] 0 = free (claimed with atomicCAS by the CTA's timing warps, released when they finish)
+    int     scratch_nslots;    // nsm * QPSK_SCRATCH_SLOTS
     int C, Cpad, F, N;
     int chan_base, chan_count; // this launch covers channels [chan_base, chan_base + chan_count); pcm is indexed from chan_base
     int frames_per_block;      // frames handled by one CTA
@@ -154,10 +158,47 @@ struct RxFrontSmem {
     float2 tsum[2][QPSK_GROUP];   // per-component halves of the timing statistic (extension)
     int index[QPSK_GROUP];
     volatile int frames_decimated; // frames whose symbols are in the ring (producer: timing warps, consumer: Costas warp)
+    int scr_slot;                  // the scratch slot this CTA claimed, -1 = private fallback region
 };
 // 110 KB: two CTAs per SM.  While one CTA sits at a barrier or in its fill phase the other one keeps the FP32
 // pipe busy, and two Costas warps per SM run concurrently, so the loop's latency no longer paces the filter.
 
+#ifndef QPSK_L2_PCM_HINT
+#define QPSK_L2_PCM_HINT 1
+#endif
+#ifndef QPSK_L2_STORE_HINT
+#define QPSK_L2_STORE_HINT 1
+#endif
+#ifndef QPSK_SCRATCH_SLOT_CLAIM
+#define QPSK_SCRATCH_SLOT_CLAIM 1
+#endif
+// PCM is read exactly once: it enters L2 with the evict-first priority, so that streaming 4 GiB of it through does not push
+// out the frame scratch and the symbol ring, which are re-read within a frame's time
+__device__ __forceinline__ u64 l2_evict_first_policy() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// ... and the two buffers that ARE re-read within a frame's time, the frame scratch and the symbol ring, are stored with the
+// evict-last priority
+__device__ __forceinline__ u64 l2_evict_last_policy() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void st_keep_f4(float4* dst, const float4 v, u64 policy) {
+    if (!QPSK_L2_STORE_HINT) { *dst = v; return; }
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void st_keep_f2(float2* dst, const float2 v, u64 policy) {
+    if (!QPSK_L2_STORE_HINT) { *dst = v; return; }
+    asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(dst), "f"(v.x), "f"(v.y), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async16_stream(void* smem_dst, const void* gmem_src, u64 policy) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (!QPSK_L2_PCM_HINT) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory"); return; }
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -235,6 +276,7 @@ enum { BAR_ROWS = 1,      // FIR warps: sample rows of the tile are in shared me
 #define QPSK_FIR_THREADS 256
 #define QPSK_AUX_THREADS 64
 #define QPSK_FRONT_THREADS 352   // 8 FIR warps + 2 timing/decimation warps + 1 Costas warp
+#define QPSK_SCRATCH_SLOTS 2     // resident CTAs per SM (__launch_bounds__ below)
 
 // Warp-specialised front end, two CTAs per SM.  Warps 0-7 mix and filter (the FP32-pipe-bound part) and hand
 // each tile's raw sums to warps 8-9 through a single-tile shared-memory buffer (named barriers BAR_FULL /
@@ -289,10 +331,11 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
         short* stage = &sm.pcm[lane][strip];
         const size_t s0 = (size_t)f0 * N;
         const int ntiles = nframes * tiles_per_frame;
+        const u64 pcm_policy = l2_evict_first_policy();
         {
             const int16_t* src = pcm_row + s0 + strip;
-            cp_async16(stage, src);
-            cp_async16(stage + 8, src + 8);
+            cp_async16_stream(stage, src, pcm_policy);
+            cp_async16_stream(stage + 8, src + 8, pcm_policy);
             if (threadIdx.x < QPSK_CHUNK) cp_async8(&sm.ph[0][threadIdx.x], &a.phasor[QPSK_CHUNK + s0 + threadIdx.x]);
         }
         cp_async_wait_all();
@@ -312,8 +355,8 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
 
             if (k + 1 < ntiles) {
                 const int16_t* src = pcm_row + tbase + QPSK_CHUNK + strip;
-                cp_async16(stage, src);
-                cp_async16(stage + 8, src + 8);
+                cp_async16_stream(stage, src, pcm_policy);
+                cp_async16_stream(stage + 8, src + 8, pcm_policy);
                 if (threadIdx.x < QPSK_CHUNK) cp_async8(&sm.ph[(k + 1) & 1][threadIdx.x], &a.phasor[QPSK_CHUNK + tbase + QPSK_CHUNK + threadIdx.x]);
             }
 
@@ -338,7 +381,23 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
         const int nsym = N / SPS;
         // this CTA's frame scratch: [symbol][component][lane][SPS] floats, so that a symbol's SPS samples of one lane are one
         // (or two) 128-bit stores and a warp writes whole 512-byte runs
-        float* scr = a.scratch + (size_t)blockIdx.x * (512 * 2 * QPSK_GROUP);
+        if (threadIdx.x == 8 * 32) {
+            int slot = -1;
+            if (QPSK_SCRATCH_SLOT_CLAIM && a.scratch_slots != nullptr) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                if ((int)smid * QPSK_SCRATCH_SLOTS + QPSK_SCRATCH_SLOTS <= a.scratch_nslots) {
+                    for (int tries = 0; tries < 4 && slot < 0; tries++)
+                        for (int i = 0; i < QPSK_SCRATCH_SLOTS; i++)
+                            if (atomicCAS(&a.scratch_slots[smid * QPSK_SCRATCH_SLOTS + i], 0, 1) == 0) { slot = (int)smid * QPSK_SCRATCH_SLOTS + i; break; }
+                }
+            }
+            sm.scr_slot = slot;
+        }
+        bar_sync(BAR_AUX, QPSK_AUX_THREADS);
+        const int scr_slot = sm.scr_slot;
+        const u64 keep_policy = l2_evict_last_policy();
+        float* scr = a.scratch + (size_t)(scr_slot >= 0 ? scr_slot : a.scratch_nslots + (int)blockIdx.x) * (512 * 2 * QPSK_GROUP);
         auto scr_at = [&](int n, int c) -> const float* {         // sample n of the frame, component c, this lane
             return scr + ((size_t)((n / SPS) * 2 + c) * QPSK_GROUP + lane) * SPS + (n % SPS);
         };
@@ -368,7 +427,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
                     {                                                          // kept for the decimation
                         float4* dst = reinterpret_cast<float4*>(scr + ((size_t)((t * TILE_SYMS + s) * 2 + comp) * QPSK_GROUP + lane) * SPS);
 #pragma unroll
-                        for (int q = 0; q < SPS / 4; q++) dst[q] = make_float4(ys[4 * q], ys[4 * q + 1], ys[4 * q + 2], ys[4 * q + 3]);
+                        for (int q = 0; q < SPS / 4; q++) st_keep_f4(dst + q, make_float4(ys[4 * q], ys[4 * q + 1], ys[4 * q + 2], ys[4 * q + 3]), keep_policy);
                     }
                     av = __fmul_rn(av, 1.0f / SPS);              // av /= CYCLES, exact for a power of two
                     mx = fmaxf(mx, av);                            // qpsk.c:140-146 (strict > or >= give the same maximum)
@@ -429,7 +488,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
                     }
 #pragma unroll
                     for (int b = 0; b < BATCH; b++)
-                        if (live) dst[(size_t)(i0 + 2 * b) * a.Cpad] = v[b];
+                        if (live) st_keep_f2(dst + (size_t)(i0 + 2 * b) * a.Cpad, v[b], keep_policy);
                 }
             }
             if (a.fuse_costas) {
@@ -439,6 +498,12 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
             } else {
                 bar_sync(BAR_AUX, QPSK_AUX_THREADS);               // sm.hist is rewritten next frame
             }
+        }
+        // both timing warps are done with the scratch: the slot goes back to the SM
+        bar_sync(BAR_AUX, QPSK_AUX_THREADS);
+        if (threadIdx.x == 8 * 32 && scr_slot >= 0) {
+            __threadfence();
+            atomicExch(&a.scratch_slots[scr_slot], 0);
         }
     } else {
         // ================================== Costas warp ==================================
@@ -452,6 +517,8 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
             while (sm.frames_decimated < fr + 1) __nanosleep(200);
             __threadfence();
             costas_run_frame<true, 1>(a.costas, p, f0 + fr, ch, phase, freq);
+            __syncwarp(__activemask());                            // every lane has read the slot
+            costas_discard_slot(a.costas, f0 + fr, ch - lane, lane);
         }
         a.costas.loop_state[ch] = make_float2(phase, freq);
     }

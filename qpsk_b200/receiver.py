@@ -14,7 +14,7 @@ from . import _capi as capi
 class Receiver:
     def __init__(self, nchan, max_frames, rs=2400.0, mode=capi.MODE_EXACT, ub_mode=capi.UB_ALIAS,
                  keep_fir=False, keep_symbols=False, decode_frames=False, no_fuse=False, resolve_rotation=False, slice_diagonal=False, estimate_offset=False, estimate_timing=False, device=0, loop_bw=None, center=1500.0,
-                 no_chunk=False, prerotate_offset=False):
+                 no_chunk=False, prerotate_offset=False, transient_symbols=False):
         self.L = capi.lib()
         cfg = capi.RxConfig()
         self.L.qpsk_b200_rx_default_config(C.byref(cfg))
@@ -26,7 +26,8 @@ class Receiver:
                      | (capi.DECODE_FRAMES if decode_frames else 0) | (capi.NO_FUSE if no_fuse else 0)
                      | (capi.RESOLVE_ROTATION if resolve_rotation else 0) | (capi.SLICE_DIAGONAL if slice_diagonal else 0)
                      | (capi.ESTIMATE_OFFSET if estimate_offset else 0) | (capi.ESTIMATE_TIMING if estimate_timing else 0)
-                     | (capi.NO_CHUNK if no_chunk else 0) | (capi.PREROTATE_OFFSET if prerotate_offset else 0))
+                     | (capi.NO_CHUNK if no_chunk else 0) | (capi.PREROTATE_OFFSET if prerotate_offset else 0)
+                     | (capi.TRANSIENT_SYMBOLS if transient_symbols else 0))
         cfg.device = device
         if loop_bw is not None:
             cfg.loop_bw = loop_bw

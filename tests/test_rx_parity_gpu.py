@@ -256,3 +256,39 @@ def test_long_stream_many_calls_random_frame_counts(oracle_lib):
     assert np.array_equal(track[..., 0], want["phase"]) and np.array_equal(track[..., 1], want["freq"])
     assert np.array_equal(np.concatenate(idxs, axis=1), want["index"])
     rx.close()
+
+
+@pytest.mark.gpu
+def test_transient_symbols_change_no_decision(oracle_lib):
+    """QPSK_B200_TRANSIENT_SYMBOLS drops the ring slots of the decimated symbols from L2 once the fused loop has consumed them
+    (discard.global.L2): every decision, index and loop track is unchanged, over several calls (the last slot of a call is the
+    first the next call reads) and with the in-call estimator keeping its frames; only OUT_DEC is gone."""
+    import qpsk_b200
+    from qpsk_b200 import capi
+    o = oracle_lib.Oracle()
+    C, F = 296 * 32 - 5, 24                            # one wave of fused CTAs (the loop rides along: that is where slots are discarded), ragged last group
+    rng = np.random.default_rng(21)
+    tx = qpsk_b200.Transmitter((1500.0 + rng.uniform(-75, 75, C)).astype(np.float32))
+    pcm = tx.modulate(rng.integers(0, 4, (C, F * 128), dtype=np.uint8))
+    tx.close()
+    pcm = np.clip(pcm + rng.normal(0.0, 900.0, pcm.shape), -32768, 32767).astype(np.int16)
+    out = {}
+    for name, kw in (("default", {}), ("transient", {"transient_symbols": True}), ("transient_est", {"transient_symbols": True, "estimate_offset": True})):
+        rx = qpsk_b200.Receiver(C, 10, decode_frames=True, **kw)
+        dib, idx, trk = [], [], []
+        for f0, f1 in ((0, 10), (10, 13), (13, 23), (23, 24)):
+            rx.rx_frames(pcm[:, f0 * 512:f1 * 512])
+            dib.append(rx.dibits()); idx.append(rx.read(capi.OUT_INDEX)); trk.append(rx.read(capi.OUT_TRACK))
+        if name != "default":
+            with pytest.raises(qpsk_b200.QpskB200Error):
+                rx.read(capi.OUT_DEC)
+        if name == "transient_est":
+            out["hz"] = rx.read(capi.OUT_OFFSET_HZ)
+        out[name] = (np.concatenate(dib, axis=1), np.concatenate(idx, axis=1), np.concatenate(trk, axis=1))
+        rx.close()
+    for name in ("transient", "transient_est"):
+        for a, b in zip(out["default"], out[name]):
+            assert np.array_equal(a, b), name
+    pick = [0, 31, 32, 4799, C - 1]
+    want = o.rx_run(pcm[pick], want=("dibit", "index"))
+    assert np.array_equal(out["transient"][0][pick], want["dibit"]) and np.array_equal(out["transient"][1][pick], want["index"])
