@@ -771,6 +771,29 @@ def main():
     samples_per_step = NCHAN * nsamp
     value = world * samples_per_step / (ms_per_step * 1e-3) / 1e6
 
+    # ---- strong scaling of ONE 65,536-channel set (SURVEY 8(d) C3 asks for both): every rank takes its contiguous block of the
+    # channel set (qpsk_b200.shard.partition) out of the PCM it already holds; reported next to the weak-scaling headline
+    strong = None
+    if world > 1 and not args.strong and NCHAN % world == 0:
+        sc = NCHAN // world
+        rxs = qpsk_b200.Receiver(sc, NFRAMES, rs=2400.0, mode=mode, device=local, decode_frames=True, estimate_offset=True, transient_symbols=TRANSIENT)
+        sub = pcm[:sc]                                   # rows are independent channels: any block is as good as the rank's own
+        for _ in range(W):
+            rxs.process_device(sub.data_ptr(), NFRAMES, stream)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            rxs.process_device(sub.data_ptr(), NFRAMES, stream)
+        s1.record()
+        barrier()
+        sms = qpsk_b200.shard.max_over_ranks(s0.elapsed_time(s1), device=dev) / args.steps
+        strong = {"channels_total": NCHAN, "channels_per_gpu": sc, "ms_per_step": sms, "value": NCHAN * nsamp / (sms * 1e-3) / 1e6, "unit": "Msamples/s",
+                  "speedup_vs_one_gpu_weak_step": ms_per_step / sms, "ideal": world,
+                  "note": "one set of 65,536 channels split over the ranks; fewer channels per GPU are fewer waves of the fused kernel "
+                          "(16,384 channels = 1.73 waves of 2 CTAs x 148 SMs), so the split is not even"}
+        rxs.close()
+
     # ---- statistics gather (the only collective): symbols decided + mean |freq| per GPU
     track = rx.read(capi.OUT_TRACK)
     nfr, npass = rx.crc_counters()
@@ -863,6 +886,8 @@ def main():
             "stats": {"symbols": stats[0], "frames_crc_checked": stats[1], "frames_crc_ok": stats[2], "channels_locked": stats[3],
                       "note": "random payload: CRC passes are chance (2^-16); counters show K4 ran over every frame"},
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
         if e2e is not None:
             e2e["ranks"] = topos
             line["e2e"] = e2e

@@ -236,6 +236,9 @@ int qpsk_b200_fft_argmax_host(qpsk_b200_fft *f, const float *h_in, int nbursts, 
 int qpsk_b200_fft_transform_device(qpsk_b200_fft *f, const float *d_in, float *d_out, int nbursts, int inverse, void *cuda_stream);
 int qpsk_b200_fft_transform_host(qpsk_b200_fft *f, const float *h_in, float *h_out, int nbursts, int inverse);
 int qpsk_b200_fft_last_kernel_ms(qpsk_b200_fft *f, float *ms);
+/* one transform longer than a CTA holds, n a power of two in 16384 .. 2^26 (the reference's fftn / ifftn take any power of
+ * two, fft.c:110-136): four-step decomposition over the batched kernel; h_out may equal h_in */
+int qpsk_b200_fft_big_host(const float *h_in, float *h_out, int n, int inverse, int device);
 
 /* ------------------------------------------------------------------------------------------
  * Bit stages  (algorithms/bit-scramble.h:29-30, interleave.h:13, crc16.h:10), batched over frames.

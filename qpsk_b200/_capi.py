@@ -112,6 +112,7 @@ def _bind_fft(L):
     L.qpsk_b200_fft_transform_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.qpsk_b200_fft_transform_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.qpsk_b200_fft_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.qpsk_b200_fft_big_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
 
 
 def _bind_bits(L):

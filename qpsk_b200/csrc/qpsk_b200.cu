@@ -68,6 +68,10 @@ struct qpsk_b200_fft;
 static const double kTau = 2.0 * 3.14159265358979323846;
 
 static long long g_next_id = 0;
+struct DevBuf {      // scoped device allocation for the one-shot entry points
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
 #define QPSK_MAX_CHUNKS 16      // frame chunks per call (rx_plan_chunks)
 
 // the taps of a context as the kernels take them: a __grid_constant__ parameter (see TapBank, rx_front.cuh)
@@ -1481,6 +1485,70 @@ extern "C" int qpsk_b200_fft_transform_host(qpsk_b200_fft* f, const float* h_in,
     return QPSK_B200_OK;
 }
 
+// ---- transforms longer than one CTA can hold (n > 8192): the four-step decomposition n = N1 N2 over the batched kernel --
+// N2 transforms of length N1 down the columns (after a transpose), the twiddles w_n^(i2 k1) (evaluated in double) applied
+// while transposing back, N1 transforms of length N2, a last transpose into natural order.  Forward is scaled by
+// 1/N1 * 1/N2 = 1/n and the inverse is unscaled, as in the reference (fft.c:105-107, 122-128), which takes any power of two.
+__global__ void fft_transpose_twiddle_kernel(const float2* __restrict__ src, float2* __restrict__ dst, int rows, int cols, long long n, int tw_sign) {
+    __shared__ float2 tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            float2 v = src[(size_t)r * cols + c];
+            if (tw_sign != 0) {                                   // times exp(-+ 2 pi i r c / n)
+                const long long e = ((long long)r * c) % n;
+                double sn, cs;
+                sincospi(2.0 * (double)e / (double)n, &sn, &cs);
+                const double wr = cs, wi = tw_sign > 0 ? -sn : sn;
+                v = make_float2((float)((double)v.x * wr - (double)v.y * wi), (float)((double)v.x * wi + (double)v.y * wr));
+            }
+            tile[j][threadIdx.x] = v;
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][j];
+    }
+}
+
+extern "C" int qpsk_b200_fft_big_host(const float* h_in, float* h_out, int n, int inverse, int device) {
+    if (!h_in || !h_out) return fail(QPSK_B200_ERR_ARG, "null argument");
+    int lg = 0;
+    while ((1LL << lg) < n) lg++;
+    if (n <= 8192 || (1LL << lg) != n || lg > 26) return fail(QPSK_B200_ERR_ARG, "long fft length %d unsupported: powers of two 16384..2^26", n);
+    int rc = check_device(device);
+    if (rc) return rc;
+    const int n1 = 1 << ((lg + 1) / 2), n2 = n / n1;
+    qpsk_b200_fft *f1 = nullptr, *f2 = nullptr;
+    DevBuf a, b;
+    cudaStream_t s = nullptr;
+    auto done = [&](int code) { if (f1) qpsk_b200_fft_destroy(f1); if (f2) qpsk_b200_fft_destroy(f2); if (s) cudaStreamDestroy(s); return code; };
+    if ((rc = qpsk_b200_fft_create(n1, device, &f1)) != 0) return done(rc);
+    if ((rc = qpsk_b200_fft_create(n2, device, &f2)) != 0) return done(rc);
+    if (cudaMalloc(&a.p, (size_t)n * sizeof(float2)) != cudaSuccess || cudaMalloc(&b.p, (size_t)n * sizeof(float2)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess)
+        return done(fail(QPSK_B200_ERR_CUDA, "allocating the long transform failed: %s", cudaGetErrorString(cudaGetLastError())));
+    float2 *A = (float2*)a.p, *B = (float2*)b.p;
+    const dim3 blk(32, 8);
+    cudaError_t e = cudaMemcpyAsync(A, h_in, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, s);
+    // x[i1 N2 + i2] as [N1][N2] -> [N2][N1]
+    if (e == cudaSuccess) { fft_transpose_twiddle_kernel<<<dim3((n2 + 31) / 32, (n1 + 31) / 32), blk, 0, s>>>(A, B, n1, n2, n, 0); e = cudaGetLastError(); }
+    if (e != cudaSuccess) return done(fail(QPSK_B200_ERR_CUDA, "long transform failed: %s", cudaGetErrorString(e)));
+    if ((rc = qpsk_b200_fft_transform_device(f1, (const float*)B, (float*)B, n2, inverse, s)) != 0) return done(rc);
+    // Y[i2][k1] w^(i2 k1) -> [N1][N2]
+    fft_transpose_twiddle_kernel<<<dim3((n1 + 31) / 32, (n2 + 31) / 32), blk, 0, s>>>(B, A, n2, n1, n, inverse ? -1 : 1);
+    if ((e = cudaGetLastError()) != cudaSuccess) return done(fail(QPSK_B200_ERR_CUDA, "long transform failed: %s", cudaGetErrorString(e)));
+    if ((rc = qpsk_b200_fft_transform_device(f2, (const float*)A, (float*)A, n1, inverse, s)) != 0) return done(rc);
+    // Z[k1][k2] -> X[k1 + N1 k2] = [N2][N1]
+    fft_transpose_twiddle_kernel<<<dim3((n2 + 31) / 32, (n1 + 31) / 32), blk, 0, s>>>(A, B, n1, n2, n, 0);
+    if ((e = cudaGetLastError()) == cudaSuccess) e = cudaMemcpyAsync(h_out, B, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return done(fail(QPSK_B200_ERR_CUDA, "long transform failed: %s", cudaGetErrorString(e)));
+    return done(QPSK_B200_OK);
+}
+
 extern "C" int qpsk_b200_fft_last_kernel_ms(qpsk_b200_fft* f, float* ms) {
     if (!f || !ms || !f->timed) return fail(QPSK_B200_ERR_STATE, "no transform yet");
     CU(cudaEventSynchronize(f->ev[1]));
@@ -1503,10 +1571,6 @@ extern "C" int qpsk_b200_rx_crc_counters(qpsk_b200_rx* rx, unsigned long long* f
     return QPSK_B200_OK;
 }
 
-struct DevBuf {      // scoped device allocation for the one-shot entry points
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-};
 
 extern "C" int qpsk_b200_bits_crc16(const uint8_t* h_data, int nbytes, int nframes, uint16_t* h_crc, int device) {
     if (!h_crc || nframes < 1 || nbytes < 0 || (nbytes > 0 && !h_data)) return fail(QPSK_B200_ERR_ARG, "bad argument");

@@ -203,6 +203,16 @@ static int g_fft_n = 0;
 
 static void fft_any(complex double *in, complex double *out, int n, int inverse) {
     if (n == 1) { out[0] = in[0]; return; }
+    if (n > 8192) {                                        /* the reference takes any power of two: four-step path */
+        float *big = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+        if (!big) die("malloc", -1);
+        for (int i = 0; i < n; i++) { big[2 * i] = (float)creal(in[i]); big[2 * i + 1] = (float)cimag(in[i]); }
+        const int brc = qpsk_b200_fft_big_host(big, big, n, inverse, 0);
+        if (brc) { free(big); die("qpsk_b200_fft_big_host", brc); }
+        for (int i = 0; i < n; i++) out[i] = (double)big[2 * i] + (double)big[2 * i + 1] * I;
+        free(big);
+        return;
+    }
     if (n != g_fft_n) {
         if (g_fft) { qpsk_b200_fft_destroy(g_fft); g_fft = NULL; }
         MUST(qpsk_b200_fft_create(n, 0, &g_fft));

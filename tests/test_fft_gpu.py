@@ -79,6 +79,26 @@ def test_argmax_first_strict_maximum_on_ties():
     f.close()
 
 
+@pytest.mark.parametrize("n", [16384, 65536, 1 << 19])
+def test_long_transforms_four_step(oracle_lib, n):
+    """fftn / ifftn of the reference take any power of two (fft.c:110-136); beyond 8192 points the library runs a four-step
+    decomposition over the batched kernel (qpsk_b200_fft_big_host, what the drop-in's fftn calls): <= 1e-5 against the oracle."""
+    import ctypes as C
+    from qpsk_b200 import capi
+    o = oracle_lib.Oracle()
+    rng = np.random.default_rng(n)
+    x = (rng.normal(size=n) + 1j * rng.normal(size=n)).astype(np.complex64)
+    x[n // 3] += 40.0
+    L = capi.lib()
+    for inverse in (0, 1):
+        got = np.empty_like(x)
+        capi.check(L.qpsk_b200_fft_big_host(x.ctypes.data_as(C.c_void_p), got.ctypes.data_as(C.c_void_p), n, inverse, 0))
+        want = o.fftn(x.astype(np.complex128), inverse=bool(inverse))
+        assert np.max(np.abs(got - want)) / np.max(np.abs(want)) <= 1e-5, (n, inverse)
+    assert L.qpsk_b200_fft_big_host(x.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), 8192, 0, 0) == -1
+    assert L.qpsk_b200_fft_big_host(x.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), 20000, 0, 0) == -1
+
+
 def test_fft_rejects_bad_length():
     import ctypes as C
     from qpsk_b200 import capi
