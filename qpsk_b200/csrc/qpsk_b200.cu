@@ -1409,6 +1409,8 @@ static cudaError_t launch_fft(int log2n, const FftArgs& a, int nsm, cudaStream_t
 }
 
 static int fft_run(qpsk_b200_fft* f, const float* d_in, float* d_out, int nbursts, int inverse, int32_t* d_bin, float* d_mag2, cudaStream_t s) {
+    // n >= 2048: the bursts travel by bulk copy (cp.async.bulk), which wants 16-byte aligned sources
+    if (f->n >= 2048 && (reinterpret_cast<uintptr_t>(d_in) & 15) != 0) return fail(QPSK_B200_ERR_ARG, "fft input must be 16-byte aligned for n >= 2048");
     FftArgs a;
     a.in = reinterpret_cast<const float2*>(d_in); a.spectrum = reinterpret_cast<float2*>(d_out);
     a.bin = d_bin; a.mag2 = d_mag2; a.tw = f->d_tw; a.nbursts = nbursts;
