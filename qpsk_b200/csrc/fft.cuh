@@ -149,6 +149,9 @@ inline void qpsk_fft_make_twiddles(int n, float2* tw) {
 #ifndef QPSK_FFT_L2_AHEAD
 #define QPSK_FFT_L2_AHEAD 1
 #endif
+#ifndef QPSK_FFT_FMA_SMALL
+#define QPSK_FFT_FMA_SMALL 1     // radix-32 / radix-16 stages in the FMA form too (dft32_f / dft16_f)
+#endif
 #ifndef QPSK_FFT_TW_SMEM_MAX
 #define QPSK_FFT_TW_SMEM_MAX 4096
 #endif
@@ -495,13 +498,14 @@ __device__ __forceinline__ void bfly_w64(c64 a, c64 b, const FftConsts& kc, c64&
 
 // first layer of the 8-point DFT on inputs that still carry a twiddle each: the pair (t_a w_a, t_b w_b) -> sum, difference.
 // MODE 0: no twiddles.  MODE 1: runtime twiddles w[1..7] (w[0] is not read).  MODE 2: input i carries W64^(KSTEP i).
+// MODE 3: runtime twiddles w[0..7], input 0 included.
 template <int MODE, int KSTEP, int IA, int IB>
 __device__ __forceinline__ void dft8_pair(const c64 (&t)[8], const c64* w, const FftConsts& kc, c64& x, c64& y) {
     if constexpr (MODE == 0) {
         x = cadd(t[IA], t[IB]);
         y = csub(t[IA], t[IB]);
-    } else if constexpr (MODE == 1) {
-        const c64 p = (IA == 0) ? t[IA] : cmul(t[IA], w[IA]);
+    } else if constexpr (MODE == 1 || MODE == 3) {
+        const c64 p = (IA == 0 && MODE == 1) ? t[IA] : cmul(t[IA], w[IA]);
         bfly_tw(p, t[IB], w[IB], kc, x, y);
     } else {
         const c64 p = (IA == 0) ? t[IA] : cmul_w64<KSTEP * IA>(t[IA], kc);
@@ -574,6 +578,63 @@ __device__ __forceinline__ void dft64_f(c64 (&v)[64], const FftConsts& kc, const
         for (int k2 = 0; k2 < 8; k2++) a[n1][k2] = (TWMODE == 1 && n1 > 0) ? cmul(t[k2], zb[n1]) : t[k2];
     }
     dft64_cols<TWMODE, 0>(a, v, kc, wu);
+}
+
+// 32 = 4 x 8 with n = n1 + 4 n2, k = 8 k1 + k2:  W32^(n k) = W8^(n2 k2) W32^(n1 k2) W4^(n1 k1); the same FMA-form butterflies.
+// TW: input m carries the runtime twiddle w[m] (m = 1..31), folded into the first level.
+template <int K2>
+__device__ __forceinline__ void dft32_cols(c64 (&a)[4][8], c64 (&v)[32], const FftConsts& kc) {
+    if constexpr (K2 < 8) {
+        c64 s02, d02, s13, d13;
+        bfly_w64<4 * K2>(a[0][K2], a[2][K2], kc, s02, d02);            // W32^(2 K2)
+        const c64 p = cmul_w64<2 * K2>(a[1][K2], kc);                    // W32^(K2)
+        bfly_w64<6 * K2>(p, a[3][K2], kc, s13, d13);                    // W32^(3 K2)
+        v[K2] = cadd(s02, s13);
+        v[16 + K2] = csub(s02, s13);
+        v[8 + K2] = cadd_mi(d02, d13);
+        v[24 + K2] = cadd_pi(d02, d13);
+        dft32_cols<K2 + 1>(a, v, kc);
+    }
+}
+template <bool TW>
+__device__ __forceinline__ void dft32_f(c64 (&v)[32], const c64* w, const FftConsts& kc) {
+    c64 a[4][8];
+#pragma unroll
+    for (int n1 = 0; n1 < 4; n1++) {
+        c64 t[8], wt[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) { t[n2] = v[n1 + 4 * n2]; wt[n2] = TW ? w[n1 + 4 * n2] : 0ull; }
+        if constexpr (!TW) dft8_tw<0, 0>(t, nullptr, kc);
+        else if (n1 == 0) dft8_tw<1, 0>(t, wt, kc);
+        else dft8_tw<3, 0>(t, wt, kc);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) a[n1][k2] = t[k2];
+    }
+    dft32_cols<0>(a, v, kc);
+}
+// 16 = 2 x 8 with n = n1 + 2 n2, k = 8 k1 + k2:  W16^(n k) = W8^(n2 k2) W16^(n1 k2) W2^(n1 k1)
+template <int K2>
+__device__ __forceinline__ void dft16_cols(c64 (&a)[2][8], c64 (&v)[16], const FftConsts& kc) {
+    if constexpr (K2 < 8) {
+        bfly_w64<4 * K2>(a[0][K2], a[1][K2], kc, v[K2], v[8 + K2]);     // W16^(K2)
+        dft16_cols<K2 + 1>(a, v, kc);
+    }
+}
+template <bool TW>
+__device__ __forceinline__ void dft16_f(c64 (&v)[16], const c64* w, const FftConsts& kc) {
+    c64 a[2][8];
+#pragma unroll
+    for (int n1 = 0; n1 < 2; n1++) {
+        c64 t[8], wt[8];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) { t[n2] = v[n1 + 2 * n2]; wt[n2] = TW ? w[n1 + 2 * n2] : 0ull; }
+        if constexpr (!TW) dft8_tw<0, 0>(t, nullptr, kc);
+        else if (n1 == 0) dft8_tw<1, 0>(t, wt, kc);
+        else dft8_tw<3, 0>(t, wt, kc);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) a[n1][k2] = t[k2];
+    }
+    dft16_cols<0>(a, v, kc);
 }
 
 template <int SKEW>
@@ -720,8 +781,19 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
             }
             if (FIRST && GEN && !SPLIT) v[r] = cconj_if(v[r], imsgn);    // inverse = conj(FFT(conj x))
         }
-        if (TW2L) {
-            // applied inside dft64_f<1> below
+        // radix 32 with plain per-input twiddles: the FMA-form DFT folds them into its first level
+        // (radix 16 measured 2 % slower in this form at n = 256 and stays on dft_small<16>)
+        constexpr bool FMAF = QPSK_FFT_FMA_SMALL && R == 32 && !FACT && !FACT64;
+        c64 wf[FMAF ? R : 1];
+        if (FMAF && NS > 1 && !PRETW) {
+#pragma unroll
+            for (int m = 1; m < R; m++) {
+                if (PRELOAD) wf[m] = tw[m - 1];
+                else wf[m] = Cfg::TW_SMEM ? twp[(m - 1) * KTE + (PERBF ? t * TPF : 0)] : __ldg(twp + (m - 1) * KTE + (PERBF ? t * TPF : 0));
+            }
+        }
+        if (TW2L || FMAF) {
+            // applied inside the DFT below
         } else if (NS > 1 && !PRETW) {
 #pragma unroll
             for (int m = 1; m < R; m++) {
@@ -767,6 +839,12 @@ __device__ __forceinline__ void fft_stage(c64 (&pts)[FftCfg<LOG2N>::P], c64* sda
             } else {
                 dft64_f<0>(v, kc, nullptr, nullptr, nullptr);
             }
+        } else if constexpr (FMAF && R == 32) {
+            if constexpr (NS > 1 && !PRETW) dft32_f<true>(v, wf, kc);
+            else dft32_f<false>(v, nullptr, kc);
+        } else if constexpr (FMAF && R == 16) {
+            if constexpr (NS > 1 && !PRETW) dft16_f<true>(v, wf, kc);
+            else dft16_f<false>(v, nullptr, kc);
         } else {
             dft_small<R>(v, kc);
         }

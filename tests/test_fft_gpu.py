@@ -79,6 +79,36 @@ def test_argmax_first_strict_maximum_on_ties():
     f.close()
 
 
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("nb", [1, 5, 37])
+def test_argmax_exact_ties_pick_the_lowest_bin_at_every_size(n, nb):
+    """An impulse at sample 0 has a perfectly flat spectrum in any arithmetic (every butterfly adds zeros), so all n bins tie
+    exactly: the estimator must return bin 0 -- across the threads of a warp, the warps of a transform and the two halves of
+    the split 8192-point kernel (whose even and odd bins live in different warps) -- with |X|^2 = (a / n)^2; an all-zero
+    burst gives (0, 0).  Burst counts that do not fill the last pass of a CTA exercise the masked slots."""
+    import qpsk_b200
+    f = qpsk_b200.Fft(n)
+    amp = np.float32(1.0) + np.arange(nb, dtype=np.float32)
+    x = np.zeros((nb, n), np.complex64)
+    x[:, 0] = amp
+    x[nb // 2] = 0
+    b, m = f.argmax(x)
+    want = (amp / np.float32(n)) ** 2
+    want[nb // 2] = 0
+    assert np.array_equal(b, np.zeros(nb, np.int32))
+    assert np.allclose(m, want, rtol=1e-6, atol=0)
+    # a single bin raised by one ulp-sized step above a flat spectrum must win wherever it sits (every thread / warp / half)
+    rng = np.random.default_rng(n + nb)
+    for k in rng.integers(0, n, 6):
+        t = np.arange(n)
+        y = np.zeros((1, n), np.complex64)
+        y[0, 0] = n
+        y[0] += (0.01 * np.exp(2j * np.pi * k * t / n)).astype(np.complex64)
+        bb, _ = f.argmax(y)
+        assert bb[0] == k, (n, k, bb[0])
+    f.close()
+
+
 @pytest.mark.parametrize("n", [16384, 65536, 1 << 19])
 def test_long_transforms_four_step(oracle_lib, n):
     """fftn / ifftn of the reference take any power of two (fft.c:110-136); beyond 8192 points the library runs a four-step
