@@ -174,7 +174,10 @@ struct FftCfg {
     // stride across lanes, so it needs no skew, and overwrites it in the skewed layout afterwards.  The copy is issued
     // as soon as the previous burst's last stage has read the buffer, so it runs under that stage's arithmetic and the
     // epilogue, and no thread ever waits for HBM with its registers full.
-    static constexpr bool TMA_IN = (P >= 64);
+#ifndef QPSK_FFT_TMA_MINP
+#define QPSK_FFT_TMA_MINP 64
+#endif
+    static constexpr bool TMA_IN = (P >= QPSK_FFT_TMA_MINP);
     static constexpr int TW = qpsk_fft_tw_count(N);
     static constexpr bool LIN = (N >= 256);                        // linear skew offsets (static_asserted per stage)
     // resident CTAs per SM the register allocation is capped for
