@@ -11,6 +11,7 @@
 #include "../host/host_design.h"
 #include "common.cuh"
 #include "rx_front.cuh"
+#include "rx_front2.cuh"
 #include "channel.cuh"
 #include "rx_costas.cuh"
 #include "fir.cuh"
@@ -95,6 +96,8 @@ struct qpsk_b200_rx {
     cudaEvent_t ev_fr[2 * QPSK_MAX_CHUNKS], ev_lp[2 * QPSK_MAX_CHUNKS];   // around K1 / K3 of every frame chunk of the last call
     int timed_chunks;  bool timed_loop;
     bool timed, last_fused, no_fuse;
+    int dephase_cycles;     // see rx_front_kernel
+    bool front_v1;          // rx_front_kernel (default) or, with QPSK_B200_FRONT=2 in the environment, rx_front2_kernel
     long long launches;
     // device state
     int16_t* d_pcm_tail;    // [Cpad][128]
@@ -216,7 +219,7 @@ static cudaError_t launch_front(const RxFrontArgs& a, const float* taps, int gri
     cudaLaunchAttribute attr[1];
     int nattr = 0;
     if (persist_bytes > 0 && a.scratch != nullptr) {
-        const size_t live = (size_t)a.scratch_nslots * 512 * 2 * QPSK_GROUP * sizeof(float);      // the shared slots, not the fallback regions
+        const size_t live = (size_t)a.scratch_nslots * QPSK_SCRATCH_REGION_FLOATS * sizeof(float);      // the shared slots, not the fallback regions
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
         attr[0].val.accessPolicyWindow.base_ptr = a.scratch;
         attr[0].val.accessPolicyWindow.num_bytes = live < persist_window ? live : persist_window;
@@ -227,6 +230,48 @@ static cudaError_t launch_front(const RxFrontArgs& a, const float* taps, int gri
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
     return cudaLaunchKernelEx(&cfg, rx_front_kernel<NTAPS, SPS, MODE>, a, tap_bank<NTAPS>(taps));
+}
+
+#ifdef QPSK_FRONT_PROF
+extern "C" int qpsk_b200_debug_front_trace(long long* trace, unsigned long long* hdr, int* count) {
+    if (cudaMemcpyFromSymbol(trace, g_front_trace, sizeof(long long) * QPSK_FRONT_TRACE_SLOTS * 256 * 10 * 2) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(hdr, g_front_trace_hdr, sizeof(unsigned long long) * QPSK_FRONT_TRACE_SLOTS * 4) != cudaSuccess) return -1;
+    return cudaMemcpyFromSymbol(count, g_front_trace_count, sizeof(int)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int qpsk_b200_debug_front_prof(unsigned long long* dst) {
+    return cudaMemcpyFromSymbol(dst, g_front_prof, sizeof(unsigned long long) * QPSK_FRONT_PROF_ROWS * 48) == cudaSuccess ? 0 : -1;
+}
+#endif
+
+// the second-generation front end (rx_front2.cuh); same arguments, same outputs
+template <int NTAPS, int SPS, int MODE>
+static cudaError_t launch_front2(const RxFrontArgs& a, const float* taps, int grid, cudaStream_t s, size_t persist_bytes, size_t persist_window) {
+    const size_t smem = sizeof(RxFront2Smem);
+    cudaError_t e = cudaFuncSetAttribute(rx_front2_kernel<NTAPS, SPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(rx_front2_kernel<NTAPS, SPS, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(QPSK_F2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    int nattr = 0;
+    if (persist_bytes > 0 && a.scratch != nullptr) {
+        const size_t live = (size_t)a.scratch_nslots * QPSK_SCRATCH_REGION_FLOATS * sizeof(float);      // the shared slots, not the fallback regions
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = a.scratch;
+        attr[0].val.accessPolicyWindow.num_bytes = live < persist_window ? live : persist_window;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        nattr = 1;
+    }
+    cfg.attrs = attr; cfg.numAttrs = nattr;
+    TapBank2 tb;
+    for (int i = 0; i < 127; i++) tb.t[i] = make_float2(taps[i], taps[i]);
+    tb.t[127] = make_float2(0.0f, 0.0f);
+    tb.one = make_float2(1.0f, 1.0f);
+    return cudaLaunchKernelEx(&cfg, rx_front2_kernel<NTAPS, SPS, MODE>, a, tb);
 }
 
 extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, int max_frames, qpsk_b200_rx** out) {
@@ -252,6 +297,12 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     memset(rx, 0, sizeof *rx);
     rx->cfg = *cfg;
     rx->no_fuse = (cfg->flags & QPSK_B200_NO_FUSE) != 0;
+    rx->dephase_cycles = 0;
+    if (const char* dp = getenv("QPSK_B200_DEPHASE")) rx->dephase_cycles = atoi(dp);
+    // QPSK_B200_FRONT=2 selects the barrier-free front end (rx_front2.cuh): same results bit for bit, within 1 % of the same speed
+    // (profiles/r02_notes.md, "front-end timeline"); the default stays the kernel every round-1 and round-2 number was taken with
+    rx->front_v1 = true;
+    if (const char* fv = getenv("QPSK_B200_FRONT")) rx->front_v1 = atoi(fv) != 2;
     rx->no_chunk = (cfg->flags & QPSK_B200_NO_CHUNK) != 0;
     rx->nsm = prop.multiProcessorCount;
     rx->sm_clock_khz = 0;
@@ -262,7 +313,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         int max_persist = 0, max_window = 0;
         cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device);
         cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, cfg->device);
-        size_t want = (size_t)2 * rx->nsm * 512 * 2 * QPSK_GROUP * sizeof(float);
+        size_t want = (size_t)2 * rx->nsm * QPSK_SCRATCH_REGION_FLOATS * sizeof(float);
         if ((size_t)max_persist < want) want = (size_t)max_persist;
         if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             rx->l2_persist_bytes = want;
@@ -310,10 +361,10 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         long long ctas = (long long)(rx->Cpad / QPSK_GROUP) * max_frames;
         const long long cap = (long long)(rx->Cpad / QPSK_GROUP) > 16LL * rx->nsm ? (long long)(rx->Cpad / QPSK_GROUP) : 16LL * rx->nsm;
         if (ctas > cap) ctas = cap;
-        rx->front_scratch_bytes = (size_t)(ctas + (long long)rx->nsm * QPSK_SCRATCH_SLOTS) * 512 * 2 * QPSK_GROUP * sizeof(float);
+        rx->front_scratch_bytes = (size_t)(ctas + (long long)rx->nsm * QPSK_SCRATCH_SLOTS) * QPSK_SCRATCH_REGION_FLOATS * sizeof(float);
         e = cudaMalloc((void**)&rx->d_front_scratch, rx->front_scratch_bytes);
         if (e != cudaSuccess) rx->front_scratch_bytes = 0;
-        if (e == cudaSuccess) e = cudaMalloc((void**)&rx->d_scratch_slots, (size_t)rx->nsm * QPSK_SCRATCH_SLOTS * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&rx->d_scratch_slots, (size_t)rx->nsm * (QPSK_SCRATCH_SLOTS + 1) * sizeof(int));   // + the first wave's arrival counters
     }
     alloc((void**)&rx->d_dec_ring, (F + 1) * S * Cp * sizeof(float2));
     alloc((void**)&rx->d_index_t, F * Cp * sizeof(int));
@@ -498,7 +549,7 @@ static int rx_ensure_front_scratch(qpsk_b200_rx* rx, int grid) {
     // per-CTA frame scratch (512 samples x 2 components x 32 lanes of float); rewritten every frame, so it lives in L2.
     // Sized once for the largest grid any call can ask for (every channel group x every frame), so no allocation ever
     // happens in the middle of a stream-ordered call.
-    const size_t need = (size_t)(grid + rx->nsm * QPSK_SCRATCH_SLOTS) * 512 * 2 * QPSK_GROUP * sizeof(float);
+    const size_t need = (size_t)(grid + rx->nsm * QPSK_SCRATCH_SLOTS) * QPSK_SCRATCH_REGION_FLOATS * sizeof(float);
     if (rx->front_scratch_bytes >= need) return 0;
     CU(cudaDeviceSynchronize());
     if (rx->d_front_scratch) { cudaFree(rx->d_front_scratch); rx->d_front_scratch = nullptr; rx->front_scratch_bytes = 0; }
@@ -547,6 +598,9 @@ static int rx_launch_front(qpsk_b200_rx* rx, const RxJob& j, bool loop_overlappe
     fa.scratch = rx->d_front_scratch;
     fa.scratch_slots = rx->d_scratch_slots;
     fa.scratch_nslots = rx->nsm * QPSK_SCRATCH_SLOTS;
+    fa.dephase_counters = rx->d_scratch_slots + rx->nsm * QPSK_SCRATCH_SLOTS;
+    fa.dephase_cycles = rx->dephase_cycles;
+    if (fa.dephase_cycles > 0) CU(cudaMemsetAsync(fa.dephase_counters, 0, (size_t)rx->nsm * sizeof(int), s));
     const bool fused = (fblocks == 1) && !rx->no_fuse;
     fa.fuse_costas = fused ? 1 : 0;
     fa.costas = rx_costas_args(rx, j);
@@ -554,8 +608,13 @@ static int rx_launch_front(qpsk_b200_rx* rx, const RxJob& j, bool loop_overlappe
     const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
     if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_fr[2 * timed_chunk], s));
     const size_t pb = rx->l2_persist_bytes, pw = rx->l2_window_bytes;
-    if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, rx->taps, grid, s, pb, pw) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, rx->taps, grid, s, pb, pw);
-    else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, rx->taps, grid, s, pb, pw) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, rx->taps, grid, s, pb, pw);
+    if (rx->front_v1) {
+        if (rx->sps == 4) e = fast ? launch_front<127, 4, QPSK_MODE_FAST>(fa, rx->taps, grid, s, pb, pw) : launch_front<127, 4, QPSK_MODE_EXACT>(fa, rx->taps, grid, s, pb, pw);
+        else              e = fast ? launch_front<127, 8, QPSK_MODE_FAST>(fa, rx->taps, grid, s, pb, pw) : launch_front<127, 8, QPSK_MODE_EXACT>(fa, rx->taps, grid, s, pb, pw);
+    } else {
+        if (rx->sps == 4) e = fast ? launch_front2<127, 4, QPSK_MODE_FAST>(fa, rx->taps, grid, s, pb, pw) : launch_front2<127, 4, QPSK_MODE_EXACT>(fa, rx->taps, grid, s, pb, pw);
+        else              e = fast ? launch_front2<127, 8, QPSK_MODE_FAST>(fa, rx->taps, grid, s, pb, pw) : launch_front2<127, 8, QPSK_MODE_EXACT>(fa, rx->taps, grid, s, pb, pw);
+    }
     if (e != cudaSuccess) return fail(QPSK_B200_ERR_CUDA, "front-end kernel launch failed: %s", cudaGetErrorString(e));
     if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_fr[2 * timed_chunk + 1], s));
     // carry the last 128 PCM samples of every channel (the next chunk's filter history)

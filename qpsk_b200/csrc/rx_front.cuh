@@ -123,6 +123,17 @@ __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, const float
     }
 }
 
+#ifdef QPSK_FRONT_PROF
+// instrumented build (tools/front_prof.py): per CTA, global-timer stamps of the roles and cycle sums of the filter warps' phases
+#define QPSK_FRONT_PROF_ROWS 4096
+__device__ unsigned long long g_front_prof[QPSK_FRONT_PROF_ROWS][48];
+// per-tile trace of the CTAs that ran on SM 0 and SM 77: [slot][tile][warp 0..9][start, end] in SM cycles, + a header row per slot
+#define QPSK_FRONT_TRACE_SLOTS 128
+__device__ long long g_front_trace[QPSK_FRONT_TRACE_SLOTS][256][10][2];
+__device__ unsigned long long g_front_trace_hdr[QPSK_FRONT_TRACE_SLOTS][4];
+__device__ int g_front_trace_count;
+#endif
+
 struct RxFrontArgs {
     const int16_t* pcm;        // [C][pcm_row] s16 PCM, channel-major; the F*N samples of this launch start each row
     size_t pcm_row;            // row stride in samples (>= F*N: a frame chunk of a longer call, or a staged slice)
@@ -143,6 +154,8 @@ struct RxFrontArgs {
     int slot_base, nslots;     // frame f goes to ring slot (slot_base + 1 + f) % nslots
     int ub_mode;
     int fuse_costas;           // 1: this CTA owns every frame of its channels, so its Costas warp runs the loop too
+    int*    dephase_counters;  // [nsm] zeroed before the launch: arrival order of the first wave's CTAs on each SM
+    int     dephase_cycles;    // the first-wave CTA that arrives second on its SM starts this many cycles late (see rx_front_kernel)
     CostasArgs costas;         // used when fuse_costas
 };
 
@@ -277,6 +290,9 @@ enum { BAR_ROWS = 1,      // FIR warps: sample rows of the tile are in shared me
 #define QPSK_AUX_THREADS 64
 #define QPSK_FRONT_THREADS 352   // 8 FIR warps + 2 timing/decimation warps + 1 Costas warp
 #define QPSK_SCRATCH_SLOTS 2     // resident CTAs per SM (__launch_bounds__ below)
+// one scratch region: 48 chunks x 16 samples x 32 lanes of raw (I, Q) sums = 6 tiles (rx_front2_kernel); the round-1 kernel keeps one
+// frame of gained samples (512 x 2 x 32 floats) in the first two thirds of it
+#define QPSK_SCRATCH_REGION_FLOATS (48 * 16 * QPSK_GROUP * 2)
 
 // Warp-specialised front end, two CTAs per SM.  Warps 0-7 mix and filter (the FP32-pipe-bound part) and hand
 // each tile's raw sums to warps 8-9 through a single-tile shared-memory buffer (named barriers BAR_FULL /
@@ -306,6 +322,42 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
     constexpr int tiles_per_frame = 512 / QPSK_CHUNK;
     const int nframes = f1 - f0;
     if (threadIdx.x == 0) sm.frames_decimated = 0;
+#ifdef QPSK_FRONT_PROF
+    unsigned long long g_entry;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
+    unsigned long long* prof_row = g_front_prof[blockIdx.x % QPSK_FRONT_PROF_ROWS];
+    __shared__ int trace_slot_s;
+    if (threadIdx.x == 0) {
+        unsigned smid_; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_)); prof_row[0] = g_entry; prof_row[1] = smid_;
+        int ts = -1;
+        if (smid_ == 0 || smid_ == 77) {
+            ts = atomicAdd(&g_front_trace_count, 1) % QPSK_FRONT_TRACE_SLOTS;
+            g_front_trace_hdr[ts][0] = g_entry; g_front_trace_hdr[ts][1] = smid_; g_front_trace_hdr[ts][2] = blockIdx.x; g_front_trace_hdr[ts][3] = clock64();
+        }
+        trace_slot_s = ts;
+    }
+    __syncthreads();
+    const int trace_slot = trace_slot_s;
+#define PROF_TRACE(tile, wi, se, val) do { if (trace_slot >= 0 && lane == 0 && (tile) < 256) g_front_trace[trace_slot][tile][wi][se] = (val); } while (0)
+#define PROF_ROLE_END(slot) do { if (lane == 0) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); prof_row[slot] = g_; } } while (0)
+#else
+#define PROF_ROLE_END(slot) do { } while (0)
+#endif
+    // Two CTAs share an SM and take the same time per tile, so the pair launched together by the first wave would walk
+    // through its fill phases (no FP32 work) in lock-step for the whole launch, and every later pair inherits the phase of
+    // the pair it replaces.  The first-wave CTA that finds itself second on its SM starts half a tile late instead, so one
+    // CTA's fill phase lies under the other one's filter.
+    if (a.dephase_cycles > 0 && blockIdx.x < gridDim.x && (int)blockIdx.x < a.scratch_nslots && a.dephase_counters != nullptr) {
+        if (threadIdx.x == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const int order = atomicAdd(&a.dephase_counters[smid], 1);
+            if (order & 1) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < a.dephase_cycles) __nanosleep(500);
+            }
+        }
+    }
     __syncthreads();
 
     if (w < 8) {
@@ -341,8 +393,16 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
         cp_async_wait_all();
         bar_sync(BAR_FIR_DONE, QPSK_FIR_THREADS);
 
+#ifdef QPSK_FRONT_PROF
+        long long pc_fill = 0, pc_strip = 0, pc_empty = 0, pc_post = 0, pt, pt2;
+        unsigned long long g64 = 0, g65 = 0;
+        const long long pstart = clock64();
+#endif
         for (int k = 0; k < ntiles; k++) {
             const size_t tbase = s0 + (size_t)k * QPSK_CHUNK;   // first sample of this tile in the launch
+#ifdef QPSK_FRONT_PROF
+            pt = clock64();
+#endif
             // shift own strip: current -> halo, then mix the staged PCM in as the new current tile
 #pragma unroll
             for (int e = 0; e < R; e++) xrow[strip + e] = xcur[e];
@@ -362,9 +422,22 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
 
             // matched filter: rrc_fir.c:22-28
             u64 acc[R];
+#ifdef QPSK_FRONT_PROF
+            pt2 = clock64(); pc_fill += pt2 - pt; pt = pt2;
+            PROF_TRACE(k, w, 0, pt2);
+            if (k == 64) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g64));
+            if (k == 65) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g65));
+#endif
             fir_strip<NTAPS, R, MODE>(xcur - (NTAPS - 1), tb.t, acc);
+#ifdef QPSK_FRONT_PROF
+            pt2 = clock64(); pc_strip += pt2 - pt; pt = pt2;
+            PROF_TRACE(k, w, 1, pt2);
+#endif
             // sm.out is a single tile: wait until the timing warps have taken the previous one
             if (k > 0) bar_sync(BAR_EMPTY, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+#ifdef QPSK_FRONT_PROF
+            pt2 = clock64(); pc_empty += pt2 - pt; pt = pt2;
+#endif
             // raw sums go to shared memory; the output gain (a double multiply behind two conversions on the
             // narrow XU pipe) is applied by the timing warps, off the filter's critical path
             u64* orow = &sm.out[lane][strip];
@@ -373,7 +446,18 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
             bar_arrive(BAR_FULL, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
             cp_async_wait_all();                       // next tile's PCM and phasors have landed
             bar_sync(BAR_FIR_DONE, QPSK_FIR_THREADS);
+#ifdef QPSK_FRONT_PROF
+            pt2 = clock64(); pc_post += pt2 - pt;
+#endif
         }
+#ifdef QPSK_FRONT_PROF
+        if (lane == 0) {
+            prof_row[8 + w] = pc_strip; prof_row[16 + w] = pc_post; prof_row[24 + w] = pc_fill; prof_row[32 + w] = pc_empty;
+            if (w == 0) { prof_row[6] = clock64() - pstart; prof_row[7] = g64; prof_row[40] = g65; }
+        }
+#endif
+        if (w == 0) PROF_ROLE_END(2);
+        if (w == 7) PROF_ROLE_END(3);
     } else if (w < 10) {
         // ============================ timing + decimation warps ============================
         // warp 8 = I, warp 9 = Q, lane = channel: amplitude histograms of qpsk.c:131-167, one tile behind the filter
@@ -397,7 +481,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
         bar_sync(BAR_AUX, QPSK_AUX_THREADS);
         const int scr_slot = sm.scr_slot;
         const u64 keep_policy = l2_evict_last_policy();
-        float* scr = a.scratch + (size_t)(scr_slot >= 0 ? scr_slot : a.scratch_nslots + (int)blockIdx.x) * (512 * 2 * QPSK_GROUP);
+        float* scr = a.scratch + (size_t)(scr_slot >= 0 ? scr_slot : a.scratch_nslots + (int)blockIdx.x) * (size_t)QPSK_SCRATCH_REGION_FLOATS;
         auto scr_at = [&](int n, int c) -> const float* {         // sample n of the frame, component c, this lane
             return scr + ((size_t)((n / SPS) * 2 + c) * QPSK_GROUP + lane) * SPS + (n % SPS);
         };
@@ -412,6 +496,9 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
             float sre = 0.0f, sim = 0.0f;
             for (int t = 0; t < tiles_per_frame; t++) {
                 bar_sync(BAR_FULL, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
+#ifdef QPSK_FRONT_PROF
+                PROF_TRACE(fr * tiles_per_frame + t, w, 0, clock64());
+#endif
                 const float* ow = reinterpret_cast<const float*>(&sm.out[lane][0]) + comp;
 #pragma unroll 2
                 for (int s = 0; s < TILE_SYMS; s++) {
@@ -441,6 +528,9 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
                     const int bin = (lo + (p1 ? 0 : 1)) & 7;                    // 7 + 1 -> 0: no edge reached
                     hist += 1ull << (8 * bin);                     // byte 0 collects "no bin"; counts <= 128 fit a byte
                 }
+#ifdef QPSK_FRONT_PROF
+                PROF_TRACE(fr * tiles_per_frame + t, w, 1, clock64());
+#endif
                 if (fr * tiles_per_frame + t + 1 < ntiles) bar_arrive(BAR_EMPTY, QPSK_FIR_THREADS + QPSK_AUX_THREADS);
             }
             sm.hist[comp][lane] = hist;
@@ -505,6 +595,7 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
             __threadfence();
             atomicExch(&a.scratch_slots[scr_slot], 0);
         }
+        if (w == 8) PROF_ROLE_END(4);
     } else {
         // ================================== Costas warp ==================================
         if (!a.fuse_costas || !live) return;
@@ -521,5 +612,6 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
             costas_discard_slot(a.costas, f0 + fr, ch - lane, lane);
         }
         a.costas.loop_state[ch] = make_float2(phase, freq);
+        PROF_ROLE_END(5);
     }
 }
