@@ -2085,17 +2085,15 @@ extern "C" int qpsk_b200_probe_fp32(int device, int fused, double* tap_updates_p
     if (rc) return rc;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
-    const int threads = 256, grid = prop.multiProcessorCount * 4, iters = 2000;
+    const int threads = 256, grid = prop.multiProcessorCount * 4, iters = 4000;      // 8 warps per scheduler, ~3.5 ms per timed launch
     float2 hx[1024];
-    float ht[QPSK_PROBE_TAPS];
+    ProbeTaps ht;
     for (int i = 0; i < 1024; i++) hx[i] = make_float2(0.001f * (i % 97) - 0.04f, 0.002f * (i % 89) - 0.08f);
-    for (int i = 0; i < QPSK_PROBE_TAPS; i++) ht[i] = 0.01f * (i % 13) - 0.05f;
-    DevBuf x, t, o;
+    for (int i = 0; i < 128 + 2 * QPSK_PROBE_R; i++) ht.t[i] = make_float2(0.01f * (i % 13) - 0.05f, 0.01f * (i % 13) - 0.05f);
+    DevBuf x, o;
     CU(cudaMalloc(&x.p, sizeof hx));
-    CU(cudaMalloc(&t.p, sizeof ht));
     CU(cudaMalloc(&o.p, (size_t)grid * threads * QPSK_PROBE_R * sizeof(float2)));
     CU(cudaMemcpy(x.p, hx, sizeof hx, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(t.p, ht, sizeof ht, cudaMemcpyHostToDevice));
     cudaStream_t s;
     CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     cudaEvent_t e0, e1;
@@ -2105,8 +2103,8 @@ extern "C" int qpsk_b200_probe_fp32(int device, int fused, double* tap_updates_p
     cudaError_t e = cudaSuccess;
     for (int rep = 0; rep < 6 && e == cudaSuccess; rep++) {          // rep 0 is the warm-up
         cudaEventRecord(e0, s);
-        if (fused) fp32_pipe_probe_kernel<1><<<grid, threads, 0, s>>>((const float2*)x.p, (const float*)t.p, (float2*)o.p, rep ? iters : 10);
-        else       fp32_pipe_probe_kernel<0><<<grid, threads, 0, s>>>((const float2*)x.p, (const float*)t.p, (float2*)o.p, rep ? iters : 10);
+        if (fused) fp32_pipe_probe_kernel<1><<<grid, threads, 0, s>>>((const float2*)x.p, ht, (float2*)o.p, rep ? iters : 10);
+        else       fp32_pipe_probe_kernel<0><<<grid, threads, 0, s>>>((const float2*)x.p, ht, (float2*)o.p, rep ? iters : 10);
         e = cudaGetLastError();
         cudaEventRecord(e1, s);
         if (e == cudaSuccess) e = cudaEventSynchronize(e1);
