@@ -289,6 +289,9 @@ enum { BAR_ROWS = 1,      // FIR warps: sample rows of the tile are in shared me
 #define QPSK_FIR_THREADS 256
 #define QPSK_AUX_THREADS 64
 #define QPSK_FRONT_THREADS 352   // 8 FIR warps + 2 timing/decimation warps + 1 Costas warp
+#ifndef QPSK_COSTAS_POLL_NS
+#define QPSK_COSTAS_POLL_NS 2000
+#endif
 #define QPSK_SCRATCH_SLOTS 2     // resident CTAs per SM (__launch_bounds__ below)
 // one scratch region: 48 chunks x 16 samples x 32 lanes of raw (I, Q) sums = 6 tiles (rx_front2_kernel); the round-1 kernel keeps one
 // frame of gained samples (512 x 2 x 32 floats) in the first two thirds of it
@@ -605,7 +608,9 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
         for (int fr = 0; fr < nframes; fr++) {
             // call f consumes the frame decimated one call earlier (already in the ring) and patches the
             // frame produced by this call, so it must wait until that one has been decimated
-            while (sm.frames_decimated < fr + 1) __nanosleep(200);
+            // a frame takes ~70 us to arrive; every poll is four issue slots taken from the filter warps (profiles/r02_notes.md:
+            // the kernel is bound by the schedulers' issue ports), so the wait sleeps QPSK_COSTAS_POLL_NS between looks
+            while (sm.frames_decimated < fr + 1) __nanosleep(QPSK_COSTAS_POLL_NS);
             __threadfence();
             costas_run_frame<true, 1>(a.costas, p, f0 + fr, ch, phase, freq);
             __syncwarp(__activemask());                            // every lane has read the slot
