@@ -99,7 +99,11 @@ __device__ __forceinline__ void fir_strip(const u64* __restrict__ x, const float
 #pragma unroll
         for (int r = 0; r <= d; r++) fir_tap<MODE>(acc[r], xv, taps2, d - r, one);
     }
-#pragma unroll 1
+#ifndef QPSK_STRIP_UNROLL
+#define QPSK_STRIP_UNROLL 1
+#endif
+    constexpr int STRIP_UNROLL = QPSK_STRIP_UNROLL;
+#pragma unroll STRIP_UNROLL
     for (int m = 0; m < TRIPS; m++) {                // steady, rolled
         const int d0 = R - 1 + m * R;
 #pragma unroll
