@@ -135,7 +135,6 @@ struct qpsk_b200_rx {
     bool no_chunk;                          // QPSK_B200_NO_CHUNK
     bool prerotate, loop_seeded;            // QPSK_B200_PREROTATE_OFFSET; the first call after a reset has seeded the loop
     cudaStream_t s_loop;                    // the loop of frame chunk k runs here, under the front end of chunk k+1
-    int loop_excl_smem;                     // dynamic shared memory a loop CTA on s_loop asks for (and never touches), see rx_launch_loop_and_decode
     cudaEvent_t ev_front;
     int nsm, sm_clock_khz;                  // launch policy inputs, read from the device
     size_t l2_persist_bytes, l2_window_bytes;   // persisting-L2 carve-out set aside for the frame scratch, largest access-policy window
@@ -354,19 +353,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&rx->s_k0, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_k0_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_call_start, cudaEventDisableTiming);
-    if (e == cudaSuccess) {
-        // the loop stream outranks the front end's: its few CTAs should be placed the moment a chunk's symbols exist
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        e = cudaStreamCreateWithPriority(&rx->s_loop, cudaStreamNonBlocking, prio_hi);
-    }
-    rx->loop_excl_smem = 0;
-    if (e == cudaSuccess) {
-        int excl = 115 * 1024;
-        if (const char* ev = getenv("QPSK_B200_LOOP_EXCL_KB")) excl = atoi(ev) * 1024;
-        if (excl > 0 && cudaFuncSetAttribute(costas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, excl) == cudaSuccess) rx->loop_excl_smem = excl;
-        else cudaGetLastError();
-    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&rx->s_loop, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_front, cudaEventDisableTiming);
     // the front end's per-CTA frame scratch, for the largest grid a call can ask for (every group x every frame, capped
     // at eight waves: the policy never cuts finer than that), so nothing is allocated inside a stream-ordered call
@@ -646,16 +633,7 @@ static int rx_launch_loop_and_decode(qpsk_b200_rx* rx, const RxJob& j, bool fuse
     const int live = ca.c1 - j.c0;
     if (!fused) {
         if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_lp[2 * timed_chunk], s));
-        if (s == rx->s_loop && rx->loop_excl_smem > 0) {
-            // The loop of a frame chunk runs under the front end of the next chunk and is a pure latency chain: every instruction
-            // it issues queues behind the filter warps of the CTAs it shares an SM with.  One warp per CTA, spread over as many
-            // SMs as there are warps, each CTA asking for enough (unused) shared memory that only ONE front-end CTA fits beside
-            // it instead of two: half the competition for the loop, a few per cent of the machine for the front end, which has
-            // time to spare in this regime (it waits for the loop anyway).
-            costas_kernel<<<(live + 31) / 32, 32, rx->loop_excl_smem, s>>>(ca);
-        } else {
-            costas_kernel<<<(live + 127) / 128, 128, 0, s>>>(ca);
-        }
+        costas_kernel<<<(live + 127) / 128, 128, 0, s>>>(ca);
         CU(cudaGetLastError());
         if (timed_chunk >= 0) CU(cudaEventRecord(rx->ev_lp[2 * timed_chunk + 1], s));
         rx->launches += 1;

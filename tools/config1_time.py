@@ -1,5 +1,5 @@
 """configs[1] alone (1,024 x 1200-baud channels x 256 frames, device-resident): ms per call and the K1 / K3 sums.
-usage: [QPSK_B200_LOOP_EXCL_KB=0|115] python tools/config1_time.py"""
+usage: python tools/config1_time.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -19,5 +19,5 @@ for _ in range(30):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); rx.process_device(pcm.data_ptr(), F, st.cuda_stream); e1.record(); torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
-print("config1 excl_kb=%s ms median %.3f min %.3f  kernels (front sum, loop sum) %s  dibit checksum %d" % (
-    os.environ.get("QPSK_B200_LOOP_EXCL_KB", "default"), float(np.median(ms)), min(ms), rx.kernel_ms(), int(rx.dibits().astype(np.int64).sum())))
+print("config1 ms median %.3f min %.3f  kernels (front sum, loop sum) %s  dibit checksum %d" % (
+    float(np.median(ms)), min(ms), rx.kernel_ms(), int(rx.dibits().astype(np.int64).sum())))
