@@ -94,7 +94,7 @@ struct qpsk_b200_rx {
     qpsk_host_loop loop;
     cudaStream_t stream;
     cudaEvent_t ev_fr[2 * QPSK_MAX_CHUNKS], ev_lp[2 * QPSK_MAX_CHUNKS];   // around K1 / K3 of every frame chunk of the last call
-    int timed_chunks;  bool timed_loop;
+    int timed_chunks, timed_loop_chunks;  bool timed_loop;
     bool timed, last_fused, no_fuse;
     int dephase_cycles;     // see rx_front_kernel
     bool front_v1;          // rx_front_kernel (default) or, with QPSK_B200_FRONT=2 in the environment, rx_front2_kernel
@@ -135,6 +135,10 @@ struct qpsk_b200_rx {
     bool no_chunk;                          // QPSK_B200_NO_CHUNK
     bool prerotate, loop_seeded;            // QPSK_B200_PREROTATE_OFFSET; the first call after a reset has seeded the loop
     cudaStream_t s_loop;                    // the loop of frame chunk k runs here, under the front end of chunk k+1
+    int* d_chunk_flags;                     // [QPSK_MAX_CHUNKS] ticket of the last call whose chunk k has left the front end (costas_chase_kernel)
+    int chase_ticket;                       // tickets handed out so far
+    int chase_smem;                         // dynamic shared memory a chasing loop CTA asks for and never touches: keeps front-end CTAs off its SM
+    bool no_chase;                          // QPSK_B200_NO_CHASE=1 in the environment: one loop kernel per chunk, as in round 2's first sessions
     cudaEvent_t ev_front;
     int nsm, sm_clock_khz;                  // launch policy inputs, read from the device
     size_t l2_persist_bytes, l2_window_bytes;   // persisting-L2 carve-out set aside for the frame scratch, largest access-policy window
@@ -178,7 +182,7 @@ static int rx_free(qpsk_b200_rx* rx) {
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
                      rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, rx->d_est_bursts, rx->d_est_bins, rx->d_est_mag, rx->d_timing_t,
                      rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch,
-                     rx->d_scratch_slots };
+                     rx->d_scratch_slots, rx->d_chunk_flags };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev_fr) if (e) cudaEventDestroy(e);
     for (auto& e : rx->ev_lp) if (e) cudaEventDestroy(e);
@@ -354,6 +358,36 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_k0_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_call_start, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&rx->s_loop, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&rx->d_chunk_flags, (QPSK_MAX_CHUNKS + 1) * sizeof(int));      // + the chasing loop's watchdog word
+    if (e == cudaSuccess) e = cudaMemset(rx->d_chunk_flags, 0, (QPSK_MAX_CHUNKS + 1) * sizeof(int));
+    rx->chase_ticket = 0;
+    rx->no_chase = false;
+    if (e == cudaSuccess) {
+        // CUDA loads a kernel's code at its first launch, and that load can wait for the device to drain: a first launch made
+        // while the chasing loop spins for its result would never start.  Everything a chunked call launches is loaded here.
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, phasor_table_kernel);
+        cudaFuncGetAttributes(&fa, save_pcm_tail_kernel);
+        cudaFuncGetAttributes(&fa, chunk_signal_kernel);
+        cudaFuncGetAttributes(&fa, costas_chase_kernel);
+        cudaFuncGetAttributes(&fa, costas_kernel);
+        if (rx->sps == 4) {
+            cudaFuncGetAttributes(&fa, rx_front_kernel<127, 4, QPSK_MODE_EXACT>); cudaFuncGetAttributes(&fa, rx_front_kernel<127, 4, QPSK_MODE_FAST>);
+            cudaFuncGetAttributes(&fa, rx_front2_kernel<127, 4, QPSK_MODE_EXACT>); cudaFuncGetAttributes(&fa, rx_front2_kernel<127, 4, QPSK_MODE_FAST>);
+        } else {
+            cudaFuncGetAttributes(&fa, rx_front_kernel<127, 8, QPSK_MODE_EXACT>); cudaFuncGetAttributes(&fa, rx_front_kernel<127, 8, QPSK_MODE_FAST>);
+            cudaFuncGetAttributes(&fa, rx_front2_kernel<127, 8, QPSK_MODE_EXACT>); cudaFuncGetAttributes(&fa, rx_front2_kernel<127, 8, QPSK_MODE_FAST>);
+        }
+        cudaGetLastError();
+    }
+    rx->chase_smem = 0;
+    if (e == cudaSuccess) {
+        int kb = 120;                       // 228 KB per SM - 120 - 1 < 110 + 1: no room for a front-end CTA
+        if (const char* ck = getenv("QPSK_B200_CHASE_SMEM_KB")) kb = atoi(ck);
+        if (kb > 0 && cudaFuncSetAttribute(costas_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kb * 1024) == cudaSuccess) rx->chase_smem = kb * 1024;
+        else cudaGetLastError();
+    }
+    if (const char* nc = getenv("QPSK_B200_NO_CHASE")) rx->no_chase = atoi(nc) != 0;
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_front, cudaEventDisableTiming);
     // the front end's per-CTA frame scratch, for the largest grid a call can ask for (every group x every frame, capped
     // at eight waves: the policy never cuts finer than that), so nothing is allocated inside a stream-ordered call
@@ -717,18 +751,75 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
     const bool seeding = rx->prerotate && !rx->loop_seeded;
     const bool saved_no_fuse = rx->no_fuse;
     if (seeding) rx->no_fuse = true;
-    bool loop_stream_used = false;
+    // chunked call: ONE loop kernel chases the chunks through flags (costas_chase_kernel) when no chunk's front end would carry
+    // the loop itself; its arguments describe the whole call, taken before the chunks advance the ring
+    const int ngroups_all = (rx->C + QPSK_GROUP - 1) / QPSK_GROUP;
+    const int nchunks = (F + fc - 1) / fc;
+    const bool chase = chunked && !rx->no_chase && !seeding && nchunks <= QPSK_MAX_CHUNKS
+                       && rx_frame_blocks(rx, ngroups_all, rx->C, fc, true) > 1 && rx_frame_blocks(rx, ngroups_all, rx->C, F - (nchunks - 1) * fc, true) > 1;
+    RxJob whole;
+    whole.d_pcm = d_pcm; whole.pcm_row = pcm_row; whole.c0 = 0; whole.nc = rx->C; whole.F = F; whole.f_off = 0;
+    const CostasArgs chase_args = rx_costas_args(rx, whole);
+    const int ticket = chase ? ++rx->chase_ticket : 0;
+    bool loop_stream_used = false, chase_launched = false;
     int k = 0;
     rx->timed_loop = false;
+    // a chasing loop that is already running must not be left waiting for chunks that will never come
+    auto bail = [&](int rc) -> int {
+        rx->no_fuse = saved_no_fuse;
+        if (chase_launched) {
+            int tickets[QPSK_MAX_CHUNKS];
+            for (int i = 0; i < QPSK_MAX_CHUNKS; i++) tickets[i] = ticket;
+            cudaMemcpyAsync(rx->d_chunk_flags, tickets, sizeof tickets, cudaMemcpyHostToDevice, rx->s_k0);
+            cudaStreamSynchronize(rx->s_k0);
+            cudaStreamSynchronize(rx->s_loop);
+        }
+        return rc;
+    };
+    if (chase) {
+        // The chasing loop goes first: its few CTAs (128 streams each) are placed while the SMs are still empty and ask for so
+        // much (unused) shared memory that no front-end CTA fits beside them -- the loop is a dependency chain, every cycle it
+        // queues behind filter warps is a cycle of the call; the front end, which has time to spare here, runs on the other SMs.
+        // It starts behind whatever the caller's stream holds (the previous call's last reader of the loop state).
+        // Nothing between this launch and the last chunk's signal may synchronise with the device (the loop would wait for
+        // signals the host has not enqueued yet): the one such place, the growth of the frame scratch, is done first.
+        {
+            const int fb = rx_frame_blocks(rx, ngroups_all, rx->C, fc, true);
+            const int fpb = (fc + fb - 1) / fb;
+            int rc = rx_ensure_front_scratch(rx, ngroups_all * ((fc + fpb - 1) / fpb));
+            if (rc) return bail(rc);
+        }
+        cudaStream_t sl = rx->s_loop;
+        cudaError_t e = cudaEventRecord(rx->ev_front, s);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(sl, rx->ev_front, 0);
+        if (e == cudaSuccess) e = cudaEventRecord(rx->ev_lp[0], sl);
+        if (e != cudaSuccess) return bail(fail(QPSK_B200_ERR_CUDA, "loop stream setup failed: %s", cudaGetErrorString(e)));
+        const int live = chase_args.c1 - chase_args.c0;
+        // ... as long as that costs the front end no more than an eighth of the machine
+        const int loop_ctas = (live + 127) / 128;
+        costas_chase_kernel<<<loop_ctas, 128, loop_ctas * 8 <= rx->nsm ? rx->chase_smem : 0, sl>>>(chase_args, rx->d_chunk_flags, ticket, fc, QPSK_MAX_CHUNKS);
+        if (cudaGetLastError() != cudaSuccess) return bail(fail(QPSK_B200_ERR_CUDA, "loop kernel launch failed"));
+        chase_launched = true;
+        cudaEventRecord(rx->ev_lp[1], sl);
+        rx->launches += 1;
+    }
     for (int f0 = 0; f0 < F; f0 += fc, k++) {
         RxJob j;
         j.d_pcm = d_pcm + (size_t)f0 * rx->N; j.pcm_row = pcm_row; j.c0 = 0; j.nc = rx->C; j.F = (F - f0 < fc) ? F - f0 : fc; j.f_off = f0;
         int rc = rx_begin_chunk(rx, j.F, s);
-        if (rc) { rx->no_fuse = saved_no_fuse; return rc; }
+        if (rc) return bail(rc);
         bool fused = false;
         rc = rx_launch_front(rx, j, chunked, s, &fused, k);
         if (!rc && seeding) rc = rx_seed_loop(rx, 0, rx->C, F, first_slot, s);
-        if (rc) { rx->no_fuse = saved_no_fuse; return rc; }
+        if (rc) return bail(rc);
+        if (chase) {
+            if (fused) return bail(fail(QPSK_B200_ERR_STATE, "internal: a chunk of a chased call fused its loop"));
+            chunk_signal_kernel<<<1, 1, 0, s>>>(rx->d_chunk_flags + k, ticket);
+            if (cudaGetLastError() != cudaSuccess) return bail(fail(QPSK_B200_ERR_CUDA, "chunk signal launch failed"));
+            rx->launches += 1;
+            rx_end_chunk(rx, j.F);
+            continue;
+        }
         cudaStream_t sl = s;
         if (chunked && !fused) {
             sl = rx->s_loop;
@@ -742,6 +833,18 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
         rx_end_chunk(rx, j.F);
     }
     rx->timed_chunks = k;
+    if (chase) {
+        rx->timed_loop = true;
+        rx->timed_loop_chunks = 1;
+        if (rx->d_frames_t) {                                             // K4 over the whole call, behind the loop
+            int rc = launch_frame_decode(rx->nsym / 4, rx->d_dibits_t, rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, 0, chase_args.c1, rx->Cpad, F, rx->s_loop);
+            if (rc) return bail(rc);
+            rx->launches += 1;
+        }
+        loop_stream_used = true;
+    } else {
+        rx->timed_loop_chunks = k;
+    }
     if (loop_stream_used) {
         CU(cudaEventRecord(rx->ev_front, rx->s_loop));
         CU(cudaStreamWaitEvent(s, rx->ev_front, 0));
@@ -792,6 +895,9 @@ extern "C" int qpsk_b200_rx_sync(qpsk_b200_rx* rx) {
     if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
     CU(cudaSetDevice(rx->cfg.device));
     CU(cudaDeviceSynchronize());
+    int dog = 0;
+    CU(cudaMemcpy(&dog, rx->d_chunk_flags + QPSK_MAX_CHUNKS, sizeof dog, cudaMemcpyDeviceToHost));
+    if (dog != 0) return fail(QPSK_B200_ERR_STATE, "the chasing loop kernel of call ticket %d gave up waiting for a frame chunk: results of that call are incomplete", dog);
     return QPSK_B200_OK;
 }
 
@@ -806,7 +912,7 @@ extern "C" int qpsk_b200_rx_last_kernel_ms(qpsk_b200_rx* rx, float* front_ms, fl
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, rx->ev_fr[2 * k], rx->ev_fr[2 * k + 1]));
         fr += ms;
-        if (rx->timed_loop) { CU(cudaEventElapsedTime(&ms, rx->ev_lp[2 * k], rx->ev_lp[2 * k + 1])); lp += ms; }
+        if (rx->timed_loop && k < rx->timed_loop_chunks) { CU(cudaEventElapsedTime(&ms, rx->ev_lp[2 * k], rx->ev_lp[2 * k + 1])); lp += ms; }
     }
     if (front_ms) *front_ms = fr;
     if (costas_ms) *costas_ms = lp;

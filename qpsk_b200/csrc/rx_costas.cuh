@@ -138,6 +138,51 @@ __global__ void __launch_bounds__(128) costas_kernel(const CostasArgs a) {
     a.loop_state[c] = make_float2(phase, freq);
 }
 
+// The loop of a call whose front end runs as frame chunks, as ONE kernel that chases the chunks: chunk k's frames are
+// processed as soon as flags[k] carries this call's ticket (chunk_signal_kernel, enqueued behind chunk k's front end on the
+// front end's stream).  Saves the launch and the cold start of one loop kernel per chunk -- for 1,024 streams the loop is a
+// pure dependency chain and every chunk boundary was ~35 us of it.  The host launches this kernel behind chunk 0's front end;
+// should a later launch of the call fail, it writes the ticket into every flag itself (rx_run_call's bail), so the kernel
+// cannot outlive the call.  Symbols and indices are read past L1 (they are written while this kernel runs).
+__global__ void chunk_signal_kernel(int* flag, int ticket) {
+    __threadfence();
+    *reinterpret_cast<volatile int*>(flag) = ticket;
+}
+__global__ void __launch_bounds__(128) costas_chase_kernel(const CostasArgs a, int* __restrict__ flags, int ticket, int frames_per_chunk, int watchdog_slot) {
+    const int c = a.c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = c < a.c1;
+    const int cl = live ? c : a.c1 - 1;
+    const CostasParams p = costas_params(a);
+    const float2 st = a.loop_state[cl];
+    float phase = st.x, freq = st.y;
+    __shared__ int give_up;
+    if (threadIdx.x == 0) give_up = 0;
+    for (int f0 = 0, k = 0; f0 < a.F; f0 += frames_per_chunk, k++) {
+        if (threadIdx.x == 0) {
+            const volatile int* fl = flags + k;
+            unsigned long long t0 = 0;
+            // watchdog: a chunk that has not come after four seconds never will (a bug in the host's ordering); the kernel then
+            // says so in flags[watchdog_slot] and leaves instead of hanging the device -- the host reports it at its next sync
+            for (int spins = 0; *fl != ticket; spins++) {
+                __nanosleep(500);
+                if ((spins & 1023) == 1023) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    if (t0 == 0) t0 = t;
+                    else if (t - t0 > 4000000000ull) { give_up = 1; flags[watchdog_slot] = ticket; break; }
+                }
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (give_up) return;
+        const int f1 = min(a.F, f0 + frames_per_chunk);
+        if (live)
+            for (int f = f0; f < f1; f++) costas_run_frame<true, 4>(a, p, f, c, phase, freq);
+    }
+    if (live) a.loop_state[c] = make_float2(phase, freq);
+}
+
 // [rows][Cpad] channel-fastest -> [C][rows] channel-major (download layout), element = T
 template <typename T>
 __global__ void transpose_to_channel_major(const T* __restrict__ src, T* __restrict__ dst, int rows, int C, int Cpad) {

@@ -331,3 +331,38 @@ def test_front2_streaming_and_frame_split(front2, oracle_lib):
         f += nf
     assert np.array_equal(np.concatenate(parts, axis=1), want)
     rx.close()
+
+
+@pytest.mark.parametrize("no_chase", [False, True])
+def test_device_path_chunked_call_equals_oracle(monkeypatch, oracle_lib, no_chase):
+    """configs[1]'s regime on the device-resident entry point: few channels x many frames, so the call is cut into frame
+    chunks and ONE loop kernel chases them through flags on its own SMs (costas_chase_kernel); QPSK_B200_NO_CHASE=1 is the
+    per-chunk loop kernel it replaced.  Two calls back to back (state carries, tickets advance), every decision and the loop
+    tracks bit-exact against the oracle, and every frame counted by the decode stage."""
+    import torch
+    import qpsk_b200
+    from qpsk_b200 import capi
+    if no_chase:
+        monkeypatch.setenv("QPSK_B200_NO_CHASE", "1")
+    rs, C, F = 1200.0, 96, 80                      # 80 frames: chunks of 8 frames (the last one ragged on the second call)
+    o = oracle_lib.Oracle(rs=rs)
+    pcm, _ = make_pcm(C, F + 37, rs=rs, seed=77, esn0_db=15.0, oracle=o)
+    want = o.rx_run(pcm, want=("dibit", "phase", "freq"))
+    d = torch.from_numpy(pcm).cuda()
+    rx = qpsk_b200.Receiver(C, F, rs=rs, decode_frames=True)
+    st = torch.cuda.Stream()
+    a = d[:, :F * 512].contiguous(); b = d[:, F * 512:].contiguous()
+    rx.process_device(a.data_ptr(), F, st.cuda_stream)
+    rx.sync()
+    got1 = rx.dibits(); tr1 = rx.read(capi.OUT_TRACK)
+    rx.process_device(b.data_ptr(), 37, st.cuda_stream)
+    rx.sync()
+    got2 = rx.dibits(); tr2 = rx.read(capi.OUT_TRACK)
+    nsym = 64
+    assert np.array_equal(got1, want["dibit"][:, :F * nsym])
+    assert np.array_equal(got2[:, :37 * nsym], want["dibit"][:, F * nsym:])
+    assert bits_equal(tr1[..., 0], want["phase"][:, :F]) and bits_equal(tr1[..., 1], want["freq"][:, :F])
+    assert bits_equal(tr2[:, :37, 0], want["phase"][:, F:]) and bits_equal(tr2[:, :37, 1], want["freq"][:, F:])
+    n, _ = rx.crc_counters()
+    assert n == C * (F + 37)
+    rx.close()
