@@ -74,6 +74,7 @@ struct DevBuf {      // scoped device allocation for the one-shot entry points
     ~DevBuf() { if (p) cudaFree(p); }
 };
 #define QPSK_MAX_CHUNKS 16      // frame chunks per call (rx_plan_chunks)
+#define QPSK_FOLLOW_WARPS_PER_SM 4   // costas_follow_kernel: one-warp CTAs of 64 registers that fit beside two front-end CTAs (9,216 free registers / 2,048)
 
 // the taps of a context as the kernels take them: a __grid_constant__ parameter (see TapBank, rx_front.cuh)
 template <int NTAPS>
@@ -137,6 +138,13 @@ struct qpsk_b200_rx {
     cudaStream_t s_loop;                    // the loop of frame chunk k runs here, under the front end of chunk k+1
     int* d_chunk_flags;                     // [QPSK_MAX_CHUNKS] ticket of the last call whose chunk k has left the front end (costas_chase_kernel)
     int chase_ticket;                       // tickets handed out so far
+    unsigned long long* d_block_progress;   // [front-end CTAs] progress words of a followed call (costas_follow_kernel)
+    size_t block_progress_n;
+    bool follow_now;                        // rx_launch_front: publish progress words for this launch
+    int follow_fblocks;                     // ... and split the frames into this many blocks (decided by rx_run_call)
+    int follow_mode;                        // QPSK_B200_FOLLOW in the environment: 0 = never (default: measured slower, profiles/r02_notes.md), 1 = when the cost model says so
+    int follow_fb_forced;                   // QPSK_B200_FOLLOW_FB=n: follow every eligible call with n frame blocks (tests, sweeps)
+    int relay_mode;                         // QPSK_B200_RELAY in the environment: 0 = never, 1 = when the cost model says so (default), n > 1 = n frame blocks whenever legal
     int chase_smem;                         // dynamic shared memory a chasing loop CTA asks for and never touches: keeps front-end CTAs off its SM
     bool no_chase;                          // QPSK_B200_NO_CHASE=1 in the environment: one loop kernel per chunk, as in round 2's first sessions
     cudaEvent_t ev_front;
@@ -182,7 +190,7 @@ static int rx_free(qpsk_b200_rx* rx) {
                      rx->d_loop_state, rx->d_dibits_t, rx->d_track_t, rx->d_fir_dbg, rx->d_costas_dbg,
                      rx->d_frames_t, rx->d_crc_ok_t, rx->d_rotation_t, rx->d_counters, rx->d_est_bursts, rx->d_est_bins, rx->d_est_mag, rx->d_timing_t,
                      rx->d_pcm_stage2[0], rx->d_pcm_stage2[1], rx->d_out_stage2[0], rx->d_out_stage2[1], rx->d_scratch, rx->d_front_scratch,
-                     rx->d_scratch_slots, rx->d_chunk_flags };
+                     rx->d_scratch_slots, rx->d_chunk_flags, rx->d_block_progress };
     for (void* p : ptrs) if (p) cudaFree(p);
     for (auto& e : rx->ev_fr) if (e) cudaEventDestroy(e);
     for (auto& e : rx->ev_lp) if (e) cudaEventDestroy(e);
@@ -370,6 +378,8 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         cudaFuncGetAttributes(&fa, save_pcm_tail_kernel);
         cudaFuncGetAttributes(&fa, chunk_signal_kernel);
         cudaFuncGetAttributes(&fa, costas_chase_kernel);
+        cudaFuncGetAttributes(&fa, costas_follow_kernel);
+        cudaFuncSetAttribute(costas_follow_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncGetAttributes(&fa, costas_kernel);
         if (rx->sps == 4) {
             cudaFuncGetAttributes(&fa, rx_front_kernel<127, 4, QPSK_MODE_EXACT>); cudaFuncGetAttributes(&fa, rx_front_kernel<127, 4, QPSK_MODE_FAST>);
@@ -388,6 +398,11 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         else cudaGetLastError();
     }
     if (const char* nc = getenv("QPSK_B200_NO_CHASE")) rx->no_chase = atoi(nc) != 0;
+    rx->follow_now = false; rx->follow_fblocks = 0; rx->follow_mode = 0; rx->follow_fb_forced = 0;
+    if (const char* fo = getenv("QPSK_B200_FOLLOW")) rx->follow_mode = atoi(fo) != 0;
+    if (const char* fo = getenv("QPSK_B200_FOLLOW_FB")) rx->follow_fb_forced = atoi(fo);
+    rx->relay_mode = 1;
+    if (const char* re = getenv("QPSK_B200_RELAY")) rx->relay_mode = atoi(re);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_front, cudaEventDisableTiming);
     // the front end's per-CTA frame scratch, for the largest grid a call can ask for (every group x every frame, capped
     // at eight waves: the policy never cuts finer than that), so nothing is allocated inside a stream-ordered call
@@ -398,6 +413,11 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
         rx->front_scratch_bytes = (size_t)(ctas + (long long)rx->nsm * QPSK_SCRATCH_SLOTS) * QPSK_SCRATCH_REGION_FLOATS * sizeof(float);
         e = cudaMalloc((void**)&rx->d_front_scratch, rx->front_scratch_bytes);
         if (e != cudaSuccess) rx->front_scratch_bytes = 0;
+        if (e == cudaSuccess) {
+            rx->block_progress_n = (size_t)ctas + 1;
+            e = cudaMalloc((void**)&rx->d_block_progress, rx->block_progress_n * sizeof(unsigned long long));
+            if (e == cudaSuccess) e = cudaMemset(rx->d_block_progress, 0, rx->block_progress_n * sizeof(unsigned long long));
+        }
         if (e == cudaSuccess) e = cudaMalloc((void**)&rx->d_scratch_slots, (size_t)rx->nsm * (QPSK_SCRATCH_SLOTS + 1) * sizeof(int));   // + the first wave's arrival counters
     }
     alloc((void**)&rx->d_dec_ring, (F + 1) * S * Cp * sizeof(float2));
@@ -563,7 +583,7 @@ struct RxJob {
 // waves (16,384 channels = 512 CTAs = 1.73 waves of 2 x nsm), at the price of the loop as its own kernel: a block start
 // costs about a third of a frame, the front end without the loop runs ~3 % faster, the stand-alone loop needs
 // max(latency of one stream, its share of the machine).
-static int rx_frame_blocks(const qpsk_b200_rx* rx, int ngroups, int nc, int F, bool loop_overlapped) {
+static int rx_frame_blocks(const qpsk_b200_rx* rx, int ngroups, int nc, int F, bool loop_overlapped, double margin = 0.98) {
     const RxCostModel m = rx_cost_model(rx);
     int fblocks = 1;
     const double loop_units = loop_overlapped ? 0.0
@@ -573,8 +593,64 @@ static int rx_frame_blocks(const qpsk_b200_rx* rx, int ngroups, int nc, int F, b
         const int fpb = (F + fb - 1) / fb, nb = (F + fpb - 1) / fpb;
         if (nb != fb) continue;                                     // same split as a smaller fb
         const double waves = (double)(((long long)ngroups * nb + m.slots - 1) / m.slots);
-        const double t = waves * (fpb + 0.3) * 0.97 + loop_units;
-        if (t < best * 0.98) { best = t; fblocks = nb; }            // 2 % hysteresis in favour of fewer blocks
+        // (a front end without the loop warp runs ~3 % faster -- unless the loop runs beside it as its own kernel)
+        const double t = waves * (fpb + 0.3) * (loop_overlapped ? 1.0 : 0.97) + loop_units;
+        if (t < best * margin) { best = t; fblocks = nb; }          // hysteresis in favour of fewer blocks (2 % unless the caller asks for more)
+    }
+    return fblocks;
+}
+
+// Frame blocks of a RELAYED launch: the CTAs own frame blocks AND keep the loop in their spare warp; the loop state travels from
+// the CTA of block k to the CTA of block k + 1 of the same channels through a relay word (rx_front_kernel, fuse_costas == 2).
+// Same instructions as the fused kernel, but the machine fills evenly when the channel groups are an awkward number of waves
+// of whole-stream CTAs: 16,384 channels are 512 CTAs = 1.73 waves (the second leaves 80 SMs with one CTA), 8,192 are 0.86
+// (40 SMs with one CTA, and every CTA as long as the call).  Measured (tools/strong_time.py, 64 frames): 8,192 channels
+// 5.75 -> 4.89 ms, 16,384 11.06 -> 9.56 ms, 32,768 19.81 (frame chunks) -> 18.95 ms, 65,536 unchanged within 0.3 %.
+// Model, in frame units: whole-stream CTAs run in lock step, waves x F; blocks are short and numerous, so they cost their
+// total work over the resident CTAs plus half a block of tail, a block start costing ~0.15 frame; the relayed loop of one
+// channel group stays a serial chain (~0.9 unit per 128-symbol frame between the filter warps).  Few channels (under half a
+// wave of groups) are left to the frame-chunk plan, whose loop runs on SMs of its own.  0 = the plain fused kernel.
+static int rx_relay_blocks(const qpsk_b200_rx* rx, int ngroups, int F) {
+    if (rx->relay_mode == 0 || rx->no_fuse || !rx->front_v1 || !rx->d_block_progress || F < 2) return 0;
+    const RxCostModel m = rx_cost_model(rx);
+    if ((size_t)(rx->Cpad / QPSK_GROUP) > rx->block_progress_n) return 0;
+    if (rx->relay_mode > 1) {                                                  // forced (tests, sweeps): legal for any shape, only not fast
+        const int fpb = (F + rx->relay_mode - 1) / rx->relay_mode;
+        const int nb = (F + fpb - 1) / fpb;
+        return nb > 1 ? nb : 0;
+    }
+    if (2 * ngroups < m.slots) return 0;
+    const double chain = 0.9 * F * rx->nsym / 128.0;
+    double best = (double)((ngroups + m.slots - 1) / m.slots) * F * 0.95;      // 5 % in favour of whole-stream CTAs
+    int fblocks = 0;
+    for (int fb = 2; fb <= F; fb++) {
+        const int fpb = (F + fb - 1) / fb, nb = (F + fpb - 1) / fpb;
+        if (nb != fb) continue;
+        const double t = fmax((double)ngroups * nb * (fpb + 0.15) / m.slots + 0.5 * fpb, chain);
+        if (t < best) { best = t * 0.99; fblocks = nb; }                       // 1 % in favour of fewer blocks
+    }
+    return fblocks;
+}
+
+// Frame blocks of a FOLLOWED call (the loop beside the front end, costas_follow_kernel), 0 = the fused kernel is the better
+// plan.  The front end is waves x (frames per block + a third of a frame per block start); the loop is one dependency chain
+// per channel group that, issued between the filter warps of two co-resident front-end CTAs, takes ~1.27 front-end frame
+// units per frame (measured: 6.7 ms for 64 frames beside a 4.5 ms front end; the ratio is clock-independent), on
+// QPSK_FOLLOW_WARPS_PER_SM x nsm warps.  8,192 channels (256 groups) are bound by that chain and stay fused; 16,384 and
+// 32,768 are 1.73 and 3.46 waves as whole streams, 6.92 and 6.92 as blocks of 16 and 32 frames.
+static int rx_follow_blocks(const qpsk_b200_rx* rx, int ngroups, int F) {
+    const RxCostModel m = rx_cost_model(rx);
+    const double warps = (double)QPSK_FOLLOW_WARPS_PER_SM * rx->nsm;
+    const double loop_floor = 1.27 * F * ceil(ngroups / warps);     // the busiest warp: its groups one after the other, every frame block
+    const double fused = (double)((ngroups + m.slots - 1) / m.slots) * F;
+    double best = fused * 0.95;                                      // 5 % in favour of the fused kernel
+    int fblocks = 0;
+    for (int fb = 2; fb <= F; fb++) {
+        const int fpb = (F + fb - 1) / fb, nb = (F + fpb - 1) / fpb;
+        if (nb != fb) continue;
+        const double waves = (double)(((long long)ngroups * nb + m.slots - 1) / m.slots);
+        const double t = fmax(waves * (fpb + 0.3), loop_floor);
+        if (t < best) { best = t; fblocks = nb; }
     }
     return fblocks;
 }
@@ -623,7 +699,8 @@ static int rx_launch_front(qpsk_b200_rx* rx, const RxJob& j, bool loop_overlappe
     fa.C = rx->C; fa.Cpad = rx->Cpad; fa.F = j.F; fa.N = N; fa.chan_base = j.c0; fa.chan_count = j.nc;
     fa.slot_base = rx->slot_base; fa.nslots = rx->nslots; fa.ub_mode = rx->cfg.ub_mode;
     const int ngroups = (j.nc + QPSK_GROUP - 1) / QPSK_GROUP;
-    int fblocks = rx_frame_blocks(rx, ngroups, j.nc, j.F, loop_overlapped);
+    const int relay_fb = (rx->follow_now || loop_overlapped) ? 0 : rx_relay_blocks(rx, ngroups, j.F);
+    int fblocks = rx->follow_now ? rx->follow_fblocks : relay_fb > 1 ? relay_fb : rx_frame_blocks(rx, ngroups, j.nc, j.F, loop_overlapped);
     fa.frames_per_block = (j.F + fblocks - 1) / fblocks;
     fblocks = (j.F + fa.frames_per_block - 1) / fa.frames_per_block;
     const int grid = ngroups * fblocks;
@@ -632,11 +709,24 @@ static int rx_launch_front(qpsk_b200_rx* rx, const RxJob& j, bool loop_overlappe
     fa.scratch = rx->d_front_scratch;
     fa.scratch_slots = rx->d_scratch_slots;
     fa.scratch_nslots = rx->nsm * QPSK_SCRATCH_SLOTS;
+    fa.block_progress = nullptr; fa.progress_ticket = 0;
+    if (rx->follow_now) {
+        if ((size_t)grid > rx->block_progress_n) return fail(QPSK_B200_ERR_STATE, "internal: a followed call with more CTAs than progress words");
+        fa.block_progress = rx->d_block_progress;
+        fa.progress_ticket = (unsigned long long)rx->chase_ticket << 32;
+    }
     fa.dephase_counters = rx->d_scratch_slots + rx->nsm * QPSK_SCRATCH_SLOTS;
     fa.dephase_cycles = rx->dephase_cycles;
     if (fa.dephase_cycles > 0) CU(cudaMemsetAsync(fa.dephase_counters, 0, (size_t)rx->nsm * sizeof(int), s));
-    const bool fused = (fblocks == 1) && !rx->no_fuse;
-    fa.fuse_costas = fused ? 1 : 0;
+    const bool relayed = relay_fb > 1 && fblocks > 1;
+    const bool fused = ((fblocks == 1) && !rx->no_fuse) || relayed;
+    fa.fuse_costas = relayed ? 2 : fused ? 1 : 0;
+    fa.relay_group_base = j.c0 / QPSK_GROUP; fa.relay_watchdog = rx->d_chunk_flags + QPSK_MAX_CHUNKS; fa.relay_ticket = 0;
+    if (relayed) {
+        fa.relay_ticket = ++rx->chase_ticket;
+        fa.block_progress = rx->d_block_progress;
+        fa.progress_ticket = (unsigned long long)fa.relay_ticket << 32;
+    }
     fa.costas = rx_costas_args(rx, j);
     cudaError_t e;
     const bool fast = rx->cfg.mode == QPSK_B200_MODE_FAST;
@@ -735,6 +825,7 @@ static int rx_plan_chunks(const qpsk_b200_rx* rx, int nc, int F) {
     if (rx->prerotate && !rx->loop_seeded) return F;                          // the seeding call: front end, estimator, then the loop
     const int ngroups = (nc + QPSK_GROUP - 1) / QPSK_GROUP;
     if (F < 32) return F;
+    if (rx_relay_blocks(rx, ngroups, F) > 1) return F;                        // frame blocks with the loop relayed from CTA to CTA
     if (rx_frame_blocks(rx, ngroups, nc, F, false) == 1) return F;            // the fused kernel is the better plan
     int fc = (F + 15) / 16;
     if (fc < 8) fc = 8;
@@ -755,12 +846,32 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
     // the loop itself; its arguments describe the whole call, taken before the chunks advance the ring
     const int ngroups_all = (rx->C + QPSK_GROUP - 1) / QPSK_GROUP;
     const int nchunks = (F + fc - 1) / fc;
-    const bool chase = chunked && !rx->no_chase && !seeding && nchunks <= QPSK_MAX_CHUNKS
+    // ... and only when its CTAs (128 streams each) get SMs of their own, an eighth of the machine at most: launched first, a
+    // loop CTA pins its SM's shared-memory carve-out at whatever it was placed with, and a chasing loop on EVERY SM (32,768
+    // channels x 64 frames, the 2-GPU strong-scaling shape, planned as chunks) left no SM a 110 KB front-end CTA could start
+    // on: the loop waited for a front end that waited for the loop, until the watchdog.  More channels than that run the
+    // per-chunk loop kernels, which wait for nothing.
+    const bool chase = chunked && !rx->no_chase && !seeding && nchunks <= QPSK_MAX_CHUNKS && rx->chase_smem > 0
+                       && ((rx->C + 127) / 128) * 8 <= rx->nsm
                        && rx_frame_blocks(rx, ngroups_all, rx->C, fc, true) > 1 && rx_frame_blocks(rx, ngroups_all, rx->C, F - (nchunks - 1) * fc, true) > 1;
     RxJob whole;
     whole.d_pcm = d_pcm; whole.pcm_row = pcm_row; whole.c0 = 0; whole.nc = rx->C; whole.F = F; whole.f_off = 0;
     const CostasArgs chase_args = rx_costas_args(rx, whole);
-    const int ticket = chase ? ++rx->chase_ticket : 0;
+    // A call that is neither chunked nor worth chunking would run as whole-stream CTAs with the loop fused.  When its channel
+    // groups are an awkward number of waves (16,384 channels = 1.73, 8,192 = 0.86 of 2 x nsm resident CTAs) the frames are cut
+    // into blocks all the same, and the loop runs beside the front end as costas_follow_kernel: one warp per resident
+    // front-end CTA, following its channel groups frame by frame through the progress words the front-end CTAs publish.
+    int follow_fb = 0;
+    if (!chunked && !seeding && (rx->follow_mode != 0 || rx->follow_fb_forced > 0) && !rx->no_fuse && !rx->d_fir_dbg && !rx->d_costas_dbg && rx->d_block_progress && F >= 2) {
+        follow_fb = rx->follow_fb_forced > 0 ? (rx->follow_fb_forced < F ? rx->follow_fb_forced : F)
+                                             : rx_follow_blocks(rx, ngroups_all, F);
+        if (follow_fb > 1) {
+            const int fpb = (F + follow_fb - 1) / follow_fb;
+            follow_fb = (F + fpb - 1) / fpb;
+        }
+        if (follow_fb <= 1 || (size_t)ngroups_all * follow_fb > rx->block_progress_n) follow_fb = 0;
+    }
+    const int ticket = (chase || follow_fb) ? ++rx->chase_ticket : 0;
     bool loop_stream_used = false, chase_launched = false;
     int k = 0;
     rx->timed_loop = false;
@@ -797,7 +908,7 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
         const int live = chase_args.c1 - chase_args.c0;
         // ... as long as that costs the front end no more than an eighth of the machine
         const int loop_ctas = (live + 127) / 128;
-        costas_chase_kernel<<<loop_ctas, 128, loop_ctas * 8 <= rx->nsm ? rx->chase_smem : 0, sl>>>(chase_args, rx->d_chunk_flags, ticket, fc, QPSK_MAX_CHUNKS);
+        costas_chase_kernel<<<loop_ctas, 128, rx->chase_smem, sl>>>(chase_args, rx->d_chunk_flags, ticket, fc, QPSK_MAX_CHUNKS);
         if (cudaGetLastError() != cudaSuccess) return bail(fail(QPSK_B200_ERR_CUDA, "loop kernel launch failed"));
         chase_launched = true;
         cudaEventRecord(rx->ev_lp[1], sl);
@@ -809,9 +920,41 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
         int rc = rx_begin_chunk(rx, j.F, s);
         if (rc) return bail(rc);
         bool fused = false;
-        rc = rx_launch_front(rx, j, chunked, s, &fused, k);
+        if (follow_fb) {
+            int rc2 = rx_ensure_front_scratch(rx, ngroups_all * follow_fb);
+            if (rc2) return bail(rc2);
+            // the loop starts behind everything the caller's stream holds up to here (the previous call's readers of the loop state)
+            cudaError_t e = cudaEventRecord(rx->ev_front, s);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(rx->s_loop, rx->ev_front, 0);
+            if (e != cudaSuccess) return bail(fail(QPSK_B200_ERR_CUDA, "loop stream setup failed: %s", cudaGetErrorString(e)));
+            rx->follow_now = true; rx->follow_fblocks = follow_fb;
+        }
+        rc = rx_launch_front(rx, j, chunked || follow_fb > 0, s, &fused, k);
+        rx->follow_now = false;
         if (!rc && seeding) rc = rx_seed_loop(rx, 0, rx->C, F, first_slot, s);
         if (rc) return bail(rc);
+        if (follow_fb && !fused) {
+            // The following loop is launched AFTER the front end it follows: the front end never waits for the loop, so whatever
+            // the block scheduler does with the loop's one-warp CTAs (two per SM fit beside two front-end CTAs: 2,560 registers
+            // and 1 KB of shared memory each) the call cannot deadlock.  (Launched first, its CTAs pinned every SM's shared-memory
+            // carve-out at the small setting they were placed with, and no 110 KB front-end CTA could start: measured, a
+            // watchdog exit.)  Same carve-out preference as the front end for the same reason.
+            const int fpb = (F + follow_fb - 1) / follow_fb;
+            cudaStream_t sl = rx->s_loop;
+            cudaError_t e = cudaEventRecord(rx->ev_lp[0], sl);
+            if (e != cudaSuccess) return bail(fail(QPSK_B200_ERR_CUDA, "loop stream setup failed: %s", cudaGetErrorString(e)));
+            const int loop_ctas = ngroups_all < QPSK_FOLLOW_WARPS_PER_SM * rx->nsm ? ngroups_all : QPSK_FOLLOW_WARPS_PER_SM * rx->nsm;
+            costas_follow_kernel<<<loop_ctas, 32, 0, sl>>>(chase_args, rx->d_block_progress, (unsigned long long)ticket << 32, ngroups_all, fpb,
+                                                           rx->d_chunk_flags + QPSK_MAX_CHUNKS, ticket);
+            if (cudaGetLastError() != cudaSuccess) return bail(fail(QPSK_B200_ERR_CUDA, "loop kernel launch failed"));
+            cudaEventRecord(rx->ev_lp[1], sl);
+            rx->launches += 1;
+        }
+        if (follow_fb) {
+            if (fused) return bail(fail(QPSK_B200_ERR_STATE, "internal: a followed call fused its loop"));
+            rx_end_chunk(rx, j.F);
+            continue;
+        }
         if (chase) {
             if (fused) return bail(fail(QPSK_B200_ERR_STATE, "internal: a chunk of a chased call fused its loop"));
             chunk_signal_kernel<<<1, 1, 0, s>>>(rx->d_chunk_flags + k, ticket);
@@ -833,7 +976,7 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
         rx_end_chunk(rx, j.F);
     }
     rx->timed_chunks = k;
-    if (chase) {
+    if (chase || follow_fb) {
         rx->timed_loop = true;
         rx->timed_loop_chunks = 1;
         if (rx->d_frames_t) {                                             // K4 over the whole call, behind the loop

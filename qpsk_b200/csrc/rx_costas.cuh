@@ -183,6 +183,52 @@ __global__ void __launch_bounds__(128) costas_chase_kernel(const CostasArgs a, i
     if (live) a.loop_state[c] = make_float2(phase, freq);
 }
 
+// The loop beside a front end whose CTAs own frame BLOCKS (channel counts that are an awkward number of waves of whole-stream
+// CTAs: 16,384 channels are 1.73 waves, as frame blocks they are 6.92): a persistent grid of one-warp CTAs, warp w following
+// channel groups w, w + gridDim, ... frame by frame through the progress words the front-end CTAs publish
+// (progress[fb * ngroups + g] = ticket << 32 | frames done).  Block order = the front end's launch order (all groups of frame
+// block 0, then block 1, ...), and with gridDim = the number of resident front-end CTAs a warp's groups sit in different
+// waves, so it is never more than a frame behind.  Loop state travels through loop_state between blocks.
+__global__ void __launch_bounds__(32, 32) costas_follow_kernel(const CostasArgs a, const unsigned long long* __restrict__ progress, unsigned long long ticket_hi,
+                                                           int ngroups, int frames_per_block, int* __restrict__ watchdog, int ticket) {
+    const int lane = threadIdx.x;
+    const CostasParams p = costas_params(a);
+    const int nfb = (a.F + frames_per_block - 1) / frames_per_block;
+    for (int fb = 0; fb < nfb; fb++) {
+        const int f0 = fb * frames_per_block, f1 = min(a.F, f0 + frames_per_block);
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            const int c = a.c0 + g * 32 + lane;
+            const bool live = c < a.c1;
+            float phase = 0.0f, freq = 0.0f;
+            if (live) { const float2 st = a.loop_state[c]; phase = st.x; freq = st.y; }
+            const volatile unsigned long long* pw = progress + (size_t)fb * ngroups + g;
+            for (int f = f0; f < f1; f++) {
+                int gave_up = 0;
+                if (lane == 0) {
+                    const unsigned long long want = ticket_hi | (unsigned)(f - f0 + 1);
+                    unsigned long long t0 = 0;
+                    for (int spins = 0; *pw < want; spins++) {
+                        __nanosleep(1000);
+                        if ((spins & 1023) == 1023) {                      // watchdog, see costas_chase_kernel
+                            unsigned long long t;
+                            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                            if (t0 == 0) t0 = t;
+                            else if (t - t0 > 4000000000ull) { gave_up = 1; *watchdog = ticket; break; }
+                        }
+                    }
+                    __threadfence();
+                }
+                gave_up = __shfl_sync(0xffffffffu, gave_up, 0);
+                if (gave_up) return;
+                if (live) costas_run_frame<true, 1>(a, p, f, c, phase, freq);
+                __syncwarp();                                              // every lane has read the slot
+                costas_discard_slot(a, f, c - lane, lane);
+            }
+            if (live) a.loop_state[c] = make_float2(phase, freq);
+        }
+    }
+}
+
 // [rows][Cpad] channel-fastest -> [C][rows] channel-major (download layout), element = T
 template <typename T>
 __global__ void transpose_to_channel_major(const T* __restrict__ src, T* __restrict__ dst, int rows, int C, int Cpad) {

@@ -158,6 +158,13 @@ struct RxFrontArgs {
     int slot_base, nslots;     // frame f goes to ring slot (slot_base + 1 + f) % nslots
     int ub_mode;
     int fuse_costas;           // 1: this CTA owns every frame of its channels, so its Costas warp runs the loop too
+                               // 2: this CTA owns a frame BLOCK and its Costas warp still runs the loop: it takes the loop state
+                               //    from the CTA of the previous block (relay word of the channel group in block_progress)
+    int relay_group_base;      // fuse_costas == 2: relay word of this CTA's group = block_progress[relay_group_base + g]
+    int* relay_watchdog;       // ... where a relay wait that gave up leaves relay_ticket (reported by qpsk_b200_rx_sync)
+    int relay_ticket;
+    unsigned long long* block_progress;  // optional [grid]: (ticket << 32 | frames of this CTA whose symbols are in the ring), for costas_follow_kernel
+    unsigned long long progress_ticket;   // ticket << 32 of this launch
     int*    dephase_counters;  // [nsm] zeroed before the launch: arrival order of the first wave's CTAs on each SM
     int     dephase_cycles;    // the first-wave CTA that arrives second on its SM starts this many cycles late (see rx_front_kernel)
     CostasArgs costas;         // used when fuse_costas
@@ -593,7 +600,10 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
                 bar_sync(BAR_AUX, QPSK_AUX_THREADS);
                 if (threadIdx.x == 8 * 32) sm.frames_decimated = fr + 1;
             } else {
+                if (a.block_progress != nullptr) __threadfence();  // ring + index writes before the progress word
                 bar_sync(BAR_AUX, QPSK_AUX_THREADS);               // sm.hist is rewritten next frame
+                if (a.block_progress != nullptr && threadIdx.x == 8 * 32)
+                    *reinterpret_cast<volatile unsigned long long*>(a.block_progress + blockIdx.x) = a.progress_ticket | (unsigned)(fr + 1);
             }
         }
         // both timing warps are done with the scratch: the slot goes back to the SM
@@ -607,7 +617,39 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
         // ================================== Costas warp ==================================
         if (!a.fuse_costas || !live) return;
         const CostasParams p = costas_params(a.costas);
-        const float2 st = a.costas.loop_state[ch];
+        float2 st;
+        if (a.fuse_costas == 2 && fb > 0) {
+            const unsigned amask = __activemask();                     // the live lanes; lane 0 is always one of them
+            volatile unsigned long long* relay = a.block_progress + a.relay_group_base + g;
+            // The loop state comes from the CTA that runs the previous frame block of these channels.  That CTA has a lower block
+            // index (blocks are numbered frame block by frame block), so it was dispatched earlier -- a whole wave earlier when a
+            // frame block is a wave of CTAs, and then this wait is over before it begins; with fewer channel groups the blocks of
+            // a group sit on the machine together and the loop warps take turns while the filter warps of all of them run.  A CTA
+            // never waits for a later one, so the chain always ends at block 0.  Same four-second watchdog as the chasing loop.
+            int gave_up = 0;
+            if (lane == 0) {
+                const unsigned long long want = a.progress_ticket | (unsigned)f0;
+                unsigned long long t0 = 0;
+                for (int spins = 0; *relay < want; spins++) {
+                    __nanosleep(QPSK_COSTAS_POLL_NS);
+                    if ((spins & 1023) == 1023) {
+                        unsigned long long t;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                        if (t0 == 0) t0 = t;
+                        else if (t - t0 > 4000000000ull) { gave_up = 1; *a.relay_watchdog = a.relay_ticket; break; }
+                    }
+                }
+                __threadfence();
+            }
+            gave_up = __shfl_sync(amask, gave_up, 0);
+            if (gave_up) {                                             // let the later blocks of the group through: the call is lost anyway
+                if (lane == 0) *relay = a.progress_ticket | (unsigned)f1;
+                return;
+            }
+            st = __ldcg(&a.costas.loop_state[ch]);                     // past L1: an earlier CTA of this SM may have read the line
+        } else {
+            st = a.costas.loop_state[ch];
+        }
         float phase = st.x, freq = st.y;
         for (int fr = 0; fr < nframes; fr++) {
             // call f consumes the frame decimated one call earlier (already in the ring) and patches the
@@ -621,6 +663,15 @@ __global__ void __launch_bounds__(QPSK_FRONT_THREADS, 2) rx_front_kernel(const _
             costas_discard_slot(a.costas, f0 + fr, ch - lane, lane);
         }
         a.costas.loop_state[ch] = make_float2(phase, freq);
+        if (a.fuse_costas == 2) {                                      // hand the loop over to the next frame block of these channels
+            __threadfence();                                           // (nothing of this lives in a register across the loop: the kernel sits at its 80)
+            __syncwarp(__activemask());
+            if (lane == 0) {
+                const int ng = (a.chan_count + QPSK_GROUP - 1) / QPSK_GROUP;
+                const int gg = blockIdx.x % ng, ff1 = min(a.F, (blockIdx.x / ng + 1) * a.frames_per_block);
+                *reinterpret_cast<volatile unsigned long long*>(a.block_progress + a.relay_group_base + gg) = a.progress_ticket | (unsigned)ff1;
+            }
+        }
         PROF_ROLE_END(5);
     }
 }

@@ -424,7 +424,10 @@ __global__ void __launch_bounds__(QPSK_F2_THREADS, 2) rx_front2_kernel(const __g
             }
             __threadfence();                                       // ring + index writes before the flag
             bar_sync(BAR_AUX, QPSK_AUX_THREADS);                   // both warps are done with the frame's raw chunks
-            if (w == 9 && lane == 0) sm.frames_decimated = fr + 1;
+            if (w == 9 && lane == 0) {
+                sm.frames_decimated = fr + 1;
+                if (a.block_progress != nullptr) *reinterpret_cast<volatile unsigned long long*>(a.block_progress + blockIdx.x) = a.progress_ticket | (unsigned)(fr + 1);
+            }
 #ifdef QPSK_FRONT_PROF
             tw_dec += clock64() - td0;
 #endif

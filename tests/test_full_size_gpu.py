@@ -49,6 +49,42 @@ def test_config2_size_replicated_channels(oracle_lib):
     rx.close()
 
 
+@pytest.mark.parametrize("C", [8192, 16384, 32768])
+def test_strong_scaling_shapes_replicated_channels(oracle_lib, C):
+    """The shapes one rank sees when 65,536 channels are split over 8 / 4 / 2 GPUs, 64 frames per call as in the bench, two
+    calls back to back on the device-resident entry point.  Each shape takes a different plan (one wave of whole-stream CTAs
+    with the loop fused; 1.73 waves; frame chunks with the loop of chunk k under the front end of chunk k+1 -- the plan whose
+    chasing loop once occupied every SM and starved its own front end until the watchdog): every replica of a base channel
+    must decide exactly like the oracle, and the call must end without a watchdog report."""
+    import torch
+    import qpsk_b200
+    from qpsk_b200 import capi
+    from synth import make_pcm
+    o = oracle_lib.Oracle()
+    F, NB = 64, 32
+    base, _ = make_pcm(NB, 2 * F, seed=4096 + C, esn0_db=18.0, oracle=o)
+    want = o.rx_run(base, want=("dibit", "phase", "freq"))
+    rng = np.random.default_rng(C)
+    which = rng.integers(0, NB, C)
+    which[:NB] = np.arange(NB)
+    d_base = torch.from_numpy(base).cuda()
+    idx = torch.from_numpy(which).cuda()
+    rx = qpsk_b200.Receiver(C, F, decode_frames=True, transient_symbols=True)
+    for call in range(2):
+        d_pcm = d_base[:, call * F * 512:(call + 1) * F * 512][idx].contiguous()
+        rx.process_device(d_pcm.data_ptr(), F)
+        rx.sync()                                                           # raises on a watchdog exit
+        got = qpsk_b200.unpack_dibits(rx.read(capi.OUT_DIBITS))
+        track = rx.read(capi.OUT_TRACK)
+        w = want["dibit"][:, call * F * 128:(call + 1) * F * 128]
+        assert np.array_equal(got, w[which])
+        assert np.array_equal(track[..., 0], want["phase"][which, call * F:(call + 1) * F])
+        assert np.array_equal(track[..., 1], want["freq"][which, call * F:(call + 1) * F])
+    n, _ = rx.crc_counters()
+    assert n == C * 2 * F
+    rx.close()
+
+
 def test_config3_size_fir_scaling_property(oracle_lib):
     import torch
     import qpsk_b200

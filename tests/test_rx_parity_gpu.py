@@ -366,3 +366,51 @@ def test_device_path_chunked_call_equals_oracle(monkeypatch, oracle_lib, no_chas
     n, _ = rx.crc_counters()
     assert n == C * (F + 37)
     rx.close()
+
+
+@pytest.mark.parametrize("follow", ["model", "fb3", "fb7", "off", "relay3", "relay7", "relay20"])
+@pytest.mark.parametrize("rs", [2400.0, 1200.0])
+def test_device_path_followed_call_equals_oracle(monkeypatch, oracle_lib, follow, rs):
+    """The strong-scaling regime on the device-resident entry point: a call that is not worth chunking but whose channel groups
+    fill the machine badly is cut into frame blocks, and the loop runs BESIDE the front end (costas_follow_kernel: one warp per
+    resident front-end CTA, following the progress words the front-end CTAs publish).  Forced block counts (3: ragged last
+    block; 7), the cost model's own choice and QPSK_B200_FOLLOW=0 (fused / stand-alone loop) all decide exactly like the
+    oracle over two calls back to back (loop state carried between blocks and between calls, tickets advance), ragged
+    channel count, transient symbols on."""
+    import torch
+    import qpsk_b200
+    from qpsk_b200 import capi
+    if follow.startswith("relay"):
+        # frame blocks with the loop still in the front-end CTAs, its state relayed from the CTA of block k to that of block k + 1
+        # (rx_front_kernel, fuse_costas == 2): forced here, the cost model only picks it for >= 9,472 channels
+        monkeypatch.setenv("QPSK_B200_RELAY", follow[5:])
+    elif follow == "off":
+        monkeypatch.setenv("QPSK_B200_FOLLOW", "0")
+        monkeypatch.setenv("QPSK_B200_RELAY", "0")
+    elif follow == "model":
+        monkeypatch.setenv("QPSK_B200_FOLLOW", "1")
+    else:
+        monkeypatch.setenv("QPSK_B200_FOLLOW_FB", follow[2:])
+    C, F, F2 = 300, 20, 11
+    nsym = 128 if rs == 2400.0 else 64
+    o = oracle_lib.Oracle(rs=rs)
+    pcm, _ = make_pcm(C, F + F2, rs=rs, seed=123, esn0_db=15.0, oracle=o)
+    want = o.rx_run(pcm, want=("dibit", "phase", "freq", "index"))
+    d = torch.from_numpy(pcm).cuda()
+    rx = qpsk_b200.Receiver(C, F, rs=rs, decode_frames=True, transient_symbols=True)
+    st = torch.cuda.Stream()
+    a = d[:, :F * 512].contiguous(); b = d[:, F * 512:].contiguous()
+    rx.process_device(a.data_ptr(), F, st.cuda_stream)
+    rx.sync()
+    got1 = rx.dibits(); tr1 = rx.read(capi.OUT_TRACK); ix1 = rx.read(capi.OUT_INDEX)
+    rx.process_device(b.data_ptr(), F2, st.cuda_stream)
+    rx.sync()
+    got2 = rx.dibits(); tr2 = rx.read(capi.OUT_TRACK); ix2 = rx.read(capi.OUT_INDEX)
+    assert np.array_equal(ix1[:, :F], want["index"][:, :F]) and np.array_equal(ix2[:, :F2], want["index"][:, F:])
+    assert np.array_equal(got1, want["dibit"][:, :F * nsym])
+    assert np.array_equal(got2[:, :F2 * nsym], want["dibit"][:, F * nsym:])
+    assert bits_equal(tr1[..., 0], want["phase"][:, :F]) and bits_equal(tr1[..., 1], want["freq"][:, :F])
+    assert bits_equal(tr2[:, :F2, 0], want["phase"][:, F:]) and bits_equal(tr2[:, :F2, 1], want["freq"][:, F:])
+    n, _ = rx.crc_counters()
+    assert n == C * (F + F2)
+    rx.close()
