@@ -793,9 +793,9 @@ def main():
         strong = {"channels_total": NCHAN, "channels_per_gpu": sc, "ms_per_step": sms, "value": NCHAN * nsamp / (sms * 1e-3) / 1e6, "unit": "Msamples/s",
                   "speedup_vs_one_gpu_weak_step": ms_per_step / sms, "ideal": world,
                   "efficiency": ms_per_step / sms / world,
-                  "note": "one set of 65,536 channels split over the ranks; fewer channels per GPU are fewer waves of the fused kernel "
-                          "(32,768 channels = 3.46 waves of 2 CTAs x 148 SMs, run as frame chunks; 16,384 = 1.73; 8,192 = 0.86), so the "
-                          "split is not even; profiles/r02_notes.md has the per-shape table and the measured alternative"}
+                  "note": "one set of 65,536 channels split over the ranks; fewer channels per GPU are an awkward number of waves of "
+                          "whole-stream CTAs (32,768 channels = 3.46 waves of 2 CTAs x 148 SMs, 16,384 = 1.73, 8,192 = 0.86), so the launch "
+                          "policy cuts the frames into blocks and relays the loop state from CTA to CTA (profiles/r02_notes.md, last section)"}
         rxs.close()
 
     # ---- statistics gather (the only collective): symbols decided + mean |freq| per GPU
