@@ -144,6 +144,7 @@ struct qpsk_b200_rx {
     int follow_fblocks;                     // ... and split the frames into this many blocks (decided by rx_run_call)
     int follow_mode;                        // QPSK_B200_FOLLOW in the environment: 0 = never (default: measured slower, profiles/r02_notes.md), 1 = when the cost model says so
     int follow_fb_forced;                   // QPSK_B200_FOLLOW_FB=n: follow every eligible call with n frame blocks (tests, sweeps)
+    int host_tail_chunks;                   // QPSK_B200_HOST_CHUNKS=n: frame chunks per multi-slice host call (default 4; 1 = whole calls per slice)
     int relay_mode;                         // QPSK_B200_RELAY in the environment: 0 = never, 1 = when the cost model says so (default), n > 1 = n frame blocks whenever legal
     int chase_smem;                         // dynamic shared memory a chasing loop CTA asks for and never touches: keeps front-end CTAs off its SM
     bool no_chase;                          // QPSK_B200_NO_CHASE=1 in the environment: one loop kernel per chunk, as in round 2's first sessions
@@ -402,6 +403,8 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (const char* fo = getenv("QPSK_B200_FOLLOW")) rx->follow_mode = atoi(fo) != 0;
     if (const char* fo = getenv("QPSK_B200_FOLLOW_FB")) rx->follow_fb_forced = atoi(fo);
     rx->relay_mode = 1;
+    rx->host_tail_chunks = 4;
+    if (const char* hc = getenv("QPSK_B200_HOST_CHUNKS")) rx->host_tail_chunks = atoi(hc);
     if (const char* re = getenv("QPSK_B200_RELAY")) rx->relay_mode = atoi(re);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_front, cudaEventDisableTiming);
     // the front end's per-CTA frame scratch, for the largest grid a call can ask for (every group x every frame, capped
@@ -1248,8 +1251,16 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
     if (slice < slice_floor) slice = slice_floor;
     if (slice > C) slice = C;
     const int nslices = (C + slice - 1) / slice;
-    const int fc = nslices == 1 ? rx_plan_chunks(rx, C, F) : F;
+    // Frame chunks.  One slice (few channels): the device-resident plan, the loop of chunk k apart from and under the front end
+    // of chunk k + 1.  Several slices: the call is bound by the PCM arriving, and what it adds to the last byte's arrival is the
+    // compute of the LAST job -- a quarter of the frames per job makes that job a quarter as long (65,536 channels x 64 frames:
+    // 5.5 ms of whole-stream CTAs behind the last copy become 1.4 ms); the loop stays fused, state carries as between calls.
+    int fc = F;
+    if (nslices == 1) fc = rx_plan_chunks(rx, C, F);
+    else if (rx->host_tail_chunks > 1 && F >= 32 && !rx->d_fir_dbg && !rx->d_costas_dbg && !rx->no_chunk && !(rx->prerotate && !rx->loop_seeded))
+        fc = (F + rx->host_tail_chunks - 1) / rx->host_tail_chunks;
     const bool chunked = fc < F;
+    const bool loop_apart = chunked && nslices == 1;
     // staging for one job: slice x fc frames of PCM in, slice x fc frames of packed dibits out
     const size_t pcm_job = (size_t)slice * fc * N * sizeof(int16_t), out_job = (size_t)slice * fc * W * sizeof(unsigned);
     if (rx->stage_pcm_bytes < pcm_job || rx->stage_out_bytes < out_job) {
@@ -1270,7 +1281,7 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
     const bool seeding = rx->prerotate && !rx->loop_seeded && !copy_only;      // see rx_run_call
     const bool saved_no_fuse = rx->no_fuse;
     if (seeding) rx->no_fuse = true;
-    bool loop_stream_used = false;
+    bool loop_stream_used = false, est_done = false;
     for (int f0 = 0; f0 < F; f0 += fc) {
         const int Fj = (F - f0 < fc) ? F - f0 : fc;
         if (!copy_only) {
@@ -1294,11 +1305,11 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
             cudaStream_t sr = sc;                               // the stream the job's results appear on
             if (!copy_only) {
                 bool fused = false;
-                rc = rx_launch_front(rx, j, chunked, sc, &fused);
+                rc = rx_launch_front(rx, j, loop_apart, sc, &fused);
                 if (!rc && seeding) rc = rx_seed_loop(rx, c0, (c0 + nc < C) ? c0 + nc : C, F, first_slot, sc);
                 if (rc) { rx->no_fuse = saved_no_fuse; return rx_host_abort(rx, rc); }
                 CU(cudaEventRecord(rx->ev_cmp[b], sc));         // the PCM staging buffer is free again
-                if (chunked && !fused) {
+                if (loop_apart && !fused) {
                     sr = rx->s_loop;
                     CU(cudaStreamWaitEvent(sr, rx->ev_cmp[b], 0));
                     loop_stream_used = true;
@@ -1328,13 +1339,21 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
             }
         }
         if (!copy_only) rx_end_chunk(rx, Fj);
+        // the estimator reads the call's first symbols only: in a multi-slice call it runs as soon as the chunk that holds them
+        // is through (every slice's loop included: fused, same stream), not behind the last copy where the caller waits for it
+        if (rx->est_on && !copy_only && !seeding && !est_done && chunked && !loop_apart
+            && (long long)(f0 + Fj) * rx->nsym >= est_burst_length(rx, F) + rx->nsym) {
+            rc = rx_launch_estimator(rx, 0, C, F, first_slot, sc);
+            if (rc) return rx_host_abort(rx, rc);
+            est_done = true;
+        }
     }
     if (loop_stream_used) {                                     // the compute stream joins the loop stream at the end of the call
         CU(cudaEventRecord(rx->ev_front, rx->s_loop));
         CU(cudaStreamWaitEvent(sc, rx->ev_front, 0));
     }
     if (seeding) { rx->no_fuse = saved_no_fuse; rx->loop_seeded = true; }
-    if (rx->est_on && !copy_only && !seeding) {
+    if (rx->est_on && !copy_only && !seeding && !est_done) {
         rc = rx_launch_estimator(rx, 0, C, F, first_slot, sc);
         if (rc) return rx_host_abort(rx, rc);
     }

@@ -85,6 +85,39 @@ def test_strong_scaling_shapes_replicated_channels(oracle_lib, C):
     rx.close()
 
 
+@pytest.mark.parametrize("host_chunks", [None, "1", "3"])
+def test_multi_slice_host_call_in_frame_chunks(oracle_lib, monkeypatch, host_chunks):
+    """The host-buffer entry point with more channels than one slice (> 18,944) and >= 32 frames per call: the call runs as
+    channel slices x frame chunks (a quarter of the frames per job by default, so that the job behind the last copy is short),
+    loop fused, state carried from chunk to chunk.  Two calls (40 and 33 frames: ragged chunks), replicated base channels,
+    every decision equal to the oracle's; QPSK_B200_HOST_CHUNKS=1 is whole calls per slice, 3 a ragged split."""
+    import qpsk_b200
+    from synth import make_pcm
+    if host_chunks is not None:
+        monkeypatch.setenv("QPSK_B200_HOST_CHUNKS", host_chunks)
+    o = oracle_lib.Oracle()
+    F1, F2, NB, C = 40, 33, 16, 19200 + 7
+    base, _ = make_pcm(NB, F1 + F2, seed=77, esn0_db=18.0, oracle=o)
+    want = o.rx_run(base, want=("dibit",))["dibit"]
+    rng = np.random.default_rng(5)
+    which = rng.integers(0, NB, C)
+    which[:NB] = np.arange(NB)
+    from qpsk_b200 import capi
+    rx = qpsk_b200.Receiver(C, F1, decode_frames=True, transient_symbols=True, estimate_offset=True)
+    got1 = qpsk_b200.unpack_dibits(rx.rx_frames(np.ascontiguousarray(base[which, :F1 * 512])))
+    assert np.array_equal(got1, want[which, :F1 * 128])
+    # the in-call estimator runs behind the first frame chunk here, not at the end of the call: same bins as a small receiver's
+    small = qpsk_b200.Receiver(NB, F1, estimate_offset=True, transient_symbols=True)
+    small.rx_frames(np.ascontiguousarray(base[:, :F1 * 512]))
+    assert np.array_equal(rx.read(capi.OUT_OFFSET_BIN), small.read(capi.OUT_OFFSET_BIN)[which])
+    small.close()
+    got2 = qpsk_b200.unpack_dibits(rx.rx_frames(np.ascontiguousarray(base[which, F1 * 512:])))
+    assert np.array_equal(got2[:, :F2 * 128], want[which, F1 * 128:])
+    n, _ = rx.crc_counters()
+    assert n == C * (F1 + F2)
+    rx.close()
+
+
 def test_config3_size_fir_scaling_property(oracle_lib):
     import torch
     import qpsk_b200
