@@ -196,6 +196,14 @@ int qpsk_b200_rx_device_dibits(qpsk_b200_rx *rx, const uint32_t **d_ptr, int *cp
 long long qpsk_b200_rx_launch_count(const qpsk_b200_rx *rx);
 /* device milliseconds of the front-end kernel in the most recent call (CUDA events on its stream) */
 int qpsk_b200_rx_last_kernel_ms(qpsk_b200_rx *rx, float *front_ms, float *costas_ms);
+/* the launch plan the most recent device-resident call (or the last job of a host call) ran under: frame chunks of the call,
+ * frame blocks per channel group of its last front-end launch, and where the Costas loop (qpsk.c:196-212) ran */
+#define QPSK_B200_LOOP_STANDALONE 0   /* costas_kernel behind the front end (per call or per chunk) */
+#define QPSK_B200_LOOP_FUSED      1   /* in the spare warp of whole-stream front-end CTAs */
+#define QPSK_B200_LOOP_RELAYED    2   /* in the front-end CTAs of frame blocks, state relayed from block to block */
+#define QPSK_B200_LOOP_CHASING    3   /* one kernel on SMs of its own that chases the frame chunks */
+#define QPSK_B200_LOOP_FOLLOWING  4   /* one-warp CTAs beside a frame-blocked front end (QPSK_B200_FOLLOW=1) */
+int qpsk_b200_rx_last_plan(const qpsk_b200_rx *rx, int *frame_chunks, int *frame_blocks, int *loop_mode);
 
 /* ------------------------------------------------------------------------------------------
  * Channel-batched rrc_fir()/rrc_make()  (rrc_fir.h:16-17, rrc_fir.c:17-76)

@@ -30,6 +30,7 @@ STREAM_SINK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(
 MODE_EXACT, MODE_FAST = 0, 1
 UB_ALIAS, UB_CLAMP, UB_PHASE, UB_TAU = 0, 1, 2, 3
 KEEP_FIR, KEEP_SYMBOLS, DECODE_FRAMES, NO_FUSE, RESOLVE_ROTATION, SLICE_DIAGONAL, ESTIMATE_OFFSET, ESTIMATE_TIMING, NO_CHUNK, PREROTATE_OFFSET, TRANSIENT_SYMBOLS = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
+LOOP_STANDALONE, LOOP_FUSED, LOOP_RELAYED, LOOP_CHASING, LOOP_FOLLOWING = range(5)
 OUT_DIBITS, OUT_INDEX, OUT_TRACK, OUT_DEC, OUT_SYMBOLS, OUT_FIR, OUT_TAPS, OUT_FRAMES, OUT_CRC_OK, OUT_ROTATION, OUT_OFFSET_BIN, OUT_OFFSET_HZ, OUT_TIMING_SUM, OUT_TIMING_TAU = range(14)
 
 _lib = None
@@ -69,6 +70,7 @@ def lib():
     L.qpsk_b200_rx_launch_count.argtypes = [C.c_void_p]
     L.qpsk_b200_rx_launch_count.restype = C.c_longlong
     L.qpsk_b200_rx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.qpsk_b200_rx_last_plan.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.qpsk_b200_rx_estimate_offset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.qpsk_b200_probe_fp32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     _bind_fir(L)

@@ -145,6 +145,7 @@ struct qpsk_b200_rx {
     int follow_mode;                        // QPSK_B200_FOLLOW in the environment: 0 = never (default: measured slower, profiles/r02_notes.md), 1 = when the cost model says so
     int follow_fb_forced;                   // QPSK_B200_FOLLOW_FB=n: follow every eligible call with n frame blocks (tests, sweeps)
     int host_tail_chunks;                   // QPSK_B200_HOST_CHUNKS=n: frame chunks per multi-slice host call (default 4; 1 = whole calls per slice)
+    int plan_chunks, plan_fblocks, plan_loop;   // qpsk_b200_rx_last_plan
     int relay_mode;                         // QPSK_B200_RELAY in the environment: 0 = never, 1 = when the cost model says so (default), n > 1 = n frame blocks whenever legal
     int chase_smem;                         // dynamic shared memory a chasing loop CTA asks for and never touches: keeps front-end CTAs off its SM
     bool no_chase;                          // QPSK_B200_NO_CHASE=1 in the environment: one loop kernel per chunk, as in round 2's first sessions
@@ -403,6 +404,7 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (const char* fo = getenv("QPSK_B200_FOLLOW")) rx->follow_mode = atoi(fo) != 0;
     if (const char* fo = getenv("QPSK_B200_FOLLOW_FB")) rx->follow_fb_forced = atoi(fo);
     rx->relay_mode = 1;
+    rx->plan_chunks = 0; rx->plan_fblocks = 0; rx->plan_loop = QPSK_B200_LOOP_STANDALONE;
     rx->host_tail_chunks = 4;
     if (const char* hc = getenv("QPSK_B200_HOST_CHUNKS")) rx->host_tail_chunks = atoi(hc);
     if (const char* re = getenv("QPSK_B200_RELAY")) rx->relay_mode = atoi(re);
@@ -750,6 +752,8 @@ static int rx_launch_front(qpsk_b200_rx* rx, const RxJob& j, bool loop_overlappe
     CU(cudaGetLastError());
     rx->launches += 2;
     rx->last_fused = fused;
+    rx->plan_chunks = 1; rx->plan_fblocks = fblocks;
+    rx->plan_loop = relayed ? QPSK_B200_LOOP_RELAYED : fused ? QPSK_B200_LOOP_FUSED : rx->follow_now ? QPSK_B200_LOOP_FOLLOWING : QPSK_B200_LOOP_STANDALONE;
     *fused_out = fused;
     return 0;
 }
@@ -1002,7 +1006,17 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
     }
     rx->lastF = F;
     rx->timed = true;
+    rx->plan_chunks = k;
+    if (chase) rx->plan_loop = QPSK_B200_LOOP_CHASING;
     return 0;
+}
+
+extern "C" int qpsk_b200_rx_last_plan(const qpsk_b200_rx* rx, int* frame_chunks, int* frame_blocks, int* loop_mode) {
+    if (!rx) return fail(QPSK_B200_ERR_ARG, "null receiver");
+    if (frame_chunks) *frame_chunks = rx->plan_chunks;
+    if (frame_blocks) *frame_blocks = rx->plan_fblocks;
+    if (loop_mode) *loop_mode = rx->plan_loop;
+    return QPSK_B200_OK;
 }
 
 extern "C" int qpsk_b200_rx_process_device(qpsk_b200_rx* rx, const int16_t* d_pcm, int nframes, void* cuda_stream) {

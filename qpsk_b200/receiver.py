@@ -134,6 +134,12 @@ class Receiver:
         capi.check(self.L.qpsk_b200_rx_last_kernel_ms(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def last_plan(self):
+        """(frame chunks, frame blocks per channel group, loop mode = capi.LOOP_*) of the most recent call."""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        capi.check(self.L.qpsk_b200_rx_last_plan(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def launch_count(self):
         return int(self.L.qpsk_b200_rx_launch_count(self.h))
 

@@ -74,6 +74,8 @@ def test_strong_scaling_shapes_replicated_channels(oracle_lib, C):
         d_pcm = d_base[:, call * F * 512:(call + 1) * F * 512][idx].contiguous()
         rx.process_device(d_pcm.data_ptr(), F)
         rx.sync()                                                           # raises on a watchdog exit
+        chunks, blocks, mode = rx.last_plan()
+        assert (chunks, mode) == (1, capi.LOOP_RELAYED) and blocks > 1      # the launch policy relays all three shapes
         got = qpsk_b200.unpack_dibits(rx.read(capi.OUT_DIBITS))
         track = rx.read(capi.OUT_TRACK)
         w = want["dibit"][:, call * F * 128:(call + 1) * F * 128]

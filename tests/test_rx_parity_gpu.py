@@ -355,6 +355,8 @@ def test_device_path_chunked_call_equals_oracle(monkeypatch, oracle_lib, no_chas
     rx.process_device(a.data_ptr(), F, st.cuda_stream)
     rx.sync()
     got1 = rx.dibits(); tr1 = rx.read(capi.OUT_TRACK)
+    chunks, _, mode = rx.last_plan()
+    assert chunks == 10 and mode == (capi.LOOP_STANDALONE if no_chase else capi.LOOP_CHASING)
     rx.process_device(b.data_ptr(), 37, st.cuda_stream)
     rx.sync()
     got2 = rx.dibits(); tr2 = rx.read(capi.OUT_TRACK)
@@ -403,6 +405,15 @@ def test_device_path_followed_call_equals_oracle(monkeypatch, oracle_lib, follow
     rx.process_device(a.data_ptr(), F, st.cuda_stream)
     rx.sync()
     got1 = rx.dibits(); tr1 = rx.read(capi.OUT_TRACK); ix1 = rx.read(capi.OUT_INDEX)
+    chunks, blocks, mode = rx.last_plan()
+    if follow.startswith("relay"):
+        assert mode == capi.LOOP_RELAYED and blocks == {"relay3": 3, "relay7": 7, "relay20": 20}[follow]
+    elif follow.startswith("fb"):
+        assert mode == capi.LOOP_FOLLOWING and blocks == {"fb3": 3, "fb7": 7}[follow]
+    elif follow == "model":
+        pass                                   # QPSK_B200_FOLLOW=1 leaves it to the cost model, which keeps this small shape fused
+    else:
+        assert mode in (capi.LOOP_FUSED, capi.LOOP_STANDALONE)
     rx.process_device(b.data_ptr(), F2, st.cuda_stream)
     rx.sync()
     got2 = rx.dibits(); tr2 = rx.read(capi.OUT_TRACK); ix2 = rx.read(capi.OUT_INDEX)
