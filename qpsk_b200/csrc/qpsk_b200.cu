@@ -73,7 +73,7 @@ struct DevBuf {      // scoped device allocation for the one-shot entry points
     void* p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
 };
-#define QPSK_MAX_CHUNKS 16      // frame chunks per call (rx_plan_chunks)
+#define QPSK_MAX_CHUNKS 32      // frame chunks per call (rx_plan_chunks)
 #define QPSK_FOLLOW_WARPS_PER_SM 4   // costas_follow_kernel: one-warp CTAs of 64 registers that fit beside two front-end CTAs (9,216 free registers / 2,048)
 
 // the taps of a context as the kernels take them: a __grid_constant__ parameter (see TapBank, rx_front.cuh)
@@ -145,6 +145,7 @@ struct qpsk_b200_rx {
     int follow_mode;                        // QPSK_B200_FOLLOW in the environment: 0 = never (default: measured slower, profiles/r02_notes.md), 1 = when the cost model says so
     int follow_fb_forced;                   // QPSK_B200_FOLLOW_FB=n: follow every eligible call with n frame blocks (tests, sweeps)
     int host_tail_chunks;                   // QPSK_B200_HOST_CHUNKS=n: frame chunks per multi-slice host call (default 4; 1 = whole calls per slice)
+    int chunk_div;                          // a chunked call is cut into this many frame chunks of at least 8 frames (QPSK_B200_CHUNK_DIV, <= QPSK_MAX_CHUNKS)
     int plan_chunks, plan_fblocks, plan_loop;   // qpsk_b200_rx_last_plan
     int relay_mode;                         // QPSK_B200_RELAY in the environment: 0 = never, 1 = when the cost model says so (default), n > 1 = n frame blocks whenever legal
     int chase_smem;                         // dynamic shared memory a chasing loop CTA asks for and never touches: keeps front-end CTAs off its SM
@@ -404,6 +405,8 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (const char* fo = getenv("QPSK_B200_FOLLOW")) rx->follow_mode = atoi(fo) != 0;
     if (const char* fo = getenv("QPSK_B200_FOLLOW_FB")) rx->follow_fb_forced = atoi(fo);
     rx->relay_mode = 1;
+    rx->chunk_div = QPSK_MAX_CHUNKS;
+    if (const char* cd = getenv("QPSK_B200_CHUNK_DIV")) { const int v = atoi(cd); if (v >= 1 && v <= QPSK_MAX_CHUNKS) rx->chunk_div = v; }
     rx->plan_chunks = 0; rx->plan_fblocks = 0; rx->plan_loop = QPSK_B200_LOOP_STANDALONE;
     rx->host_tail_chunks = 4;
     if (const char* hc = getenv("QPSK_B200_HOST_CHUNKS")) rx->host_tail_chunks = atoi(hc);
@@ -834,7 +837,7 @@ static int rx_plan_chunks(const qpsk_b200_rx* rx, int nc, int F) {
     if (F < 32) return F;
     if (rx_relay_blocks(rx, ngroups, F) > 1) return F;                        // frame blocks with the loop relayed from CTA to CTA
     if (rx_frame_blocks(rx, ngroups, nc, F, false) == 1) return F;            // the fused kernel is the better plan
-    int fc = (F + 15) / 16;
+    int fc = (F + rx->chunk_div - 1) / rx->chunk_div;
     if (fc < 8) fc = 8;
     return fc;
 }
