@@ -144,6 +144,7 @@ struct qpsk_b200_rx {
     int follow_fblocks;                     // ... and split the frames into this many blocks (decided by rx_run_call)
     int follow_mode;                        // QPSK_B200_FOLLOW in the environment: 0 = never (default: measured slower, profiles/r02_notes.md), 1 = when the cost model says so
     int follow_fb_forced;                   // QPSK_B200_FOLLOW_FB=n: follow every eligible call with n frame blocks (tests, sweeps)
+    int host_slice_halfwaves;               // QPSK_B200_HOST_SLICE_HALFWAVES: channel slice of a frame-chunked host call, in half waves of front-end CTAs (default 1 = one CTA per SM)
     int host_tail_chunks;                   // QPSK_B200_HOST_CHUNKS=n: frame chunks per multi-slice host call (default 4; 1 = whole calls per slice)
     int chunk_div;                          // a chunked call is cut into this many frame chunks of at least 8 frames (QPSK_B200_CHUNK_DIV, <= QPSK_MAX_CHUNKS)
     int plan_chunks, plan_fblocks, plan_loop;   // qpsk_b200_rx_last_plan
@@ -409,6 +410,8 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     if (const char* cd = getenv("QPSK_B200_CHUNK_DIV")) { const int v = atoi(cd); if (v >= 1 && v <= QPSK_MAX_CHUNKS) rx->chunk_div = v; }
     rx->plan_chunks = 0; rx->plan_fblocks = 0; rx->plan_loop = QPSK_B200_LOOP_STANDALONE;
     rx->host_tail_chunks = 4;
+    rx->host_slice_halfwaves = 1;
+    if (const char* hw = getenv("QPSK_B200_HOST_SLICE_HALFWAVES")) { const int v = atoi(hw); if (v >= 1 && v <= 64) rx->host_slice_halfwaves = v; }
     if (const char* hc = getenv("QPSK_B200_HOST_CHUNKS")) rx->host_tail_chunks = atoi(hc);
     if (const char* re = getenv("QPSK_B200_RELAY")) rx->relay_mode = atoi(re);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rx->ev_front, cudaEventDisableTiming);
@@ -1263,8 +1266,12 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
     const int F = nframes, N = rx->N, C = rx->C, W = rx->nsym / 16;
     const size_t row_bytes = (size_t)F * N * sizeof(int16_t);
     // channel slices: ~256 MiB of PCM, whole 32-channel groups, at least 4 waves of fused CTAs (2 per SM) when possible
+    // (4 half waves = 2 waves of whole-call CTAs; when the call will also be cut into frame chunks, below, HALF a wave per job:
+    // one CTA per SM runs a frame in ~50 us instead of 83, a job's compute always fits under the next job's copy, and nothing
+    // queues up behind the last copy but the last, small job itself -- 80.26 / 79.44 / 79.14 ms per step for 4 / 2 / 1 half waves)
+    const bool chunk_ok = rx->host_tail_chunks > 1 && F >= 32 && !rx->d_fir_dbg && !rx->d_costas_dbg && !rx->no_chunk && !(rx->prerotate && !rx->loop_seeded);
     int slice = (int)((256ull << 20) / row_bytes) / QPSK_GROUP * QPSK_GROUP;
-    const int slice_floor = 4 * 2 * rx->nsm * QPSK_GROUP / 2;
+    const int slice_floor = (chunk_ok ? rx->host_slice_halfwaves : 4) * 2 * rx->nsm * QPSK_GROUP / 2;
     if (slice < slice_floor) slice = slice_floor;
     if (slice > C) slice = C;
     const int nslices = (C + slice - 1) / slice;
@@ -1274,7 +1281,7 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
     // 5.5 ms of whole-stream CTAs behind the last copy become 1.4 ms); the loop stays fused, state carries as between calls.
     int fc = F;
     if (nslices == 1) fc = rx_plan_chunks(rx, C, F);
-    else if (rx->host_tail_chunks > 1 && F >= 32 && !rx->d_fir_dbg && !rx->d_costas_dbg && !rx->no_chunk && !(rx->prerotate && !rx->loop_seeded))
+    else if (chunk_ok)
         fc = (F + rx->host_tail_chunks - 1) / rx->host_tail_chunks;
     const bool chunked = fc < F;
     const bool loop_apart = chunked && nslices == 1;
