@@ -833,14 +833,15 @@ static int rx_seed_loop(qpsk_b200_rx* rx, int c0, int c1, int F, int first_slot,
 // 1,024 streams x 16,384 symbols x ~540 cycles = 4.7 ms behind a 2.3 ms front end.  Cutting the call into frame chunks
 // lets the loop of chunk k run on a second stream under the front end of chunks k+1.., and lets the host path copy
 // chunk k+1 in and chunk k-1 out meanwhile.  State carries between chunks exactly as between calls.
-static int rx_plan_chunks(const qpsk_b200_rx* rx, int nc, int F) {
+static int rx_plan_chunks(const qpsk_b200_rx* rx, int nc, int F, int div = 0) {
+    if (div <= 0) div = rx->chunk_div;
     if (rx->d_fir_dbg || rx->d_costas_dbg || rx->no_chunk) return F;         // debug taps are indexed by the call's frames
     if (rx->prerotate && !rx->loop_seeded) return F;                          // the seeding call: front end, estimator, then the loop
     const int ngroups = (nc + QPSK_GROUP - 1) / QPSK_GROUP;
     if (F < 32) return F;
     if (rx_relay_blocks(rx, ngroups, F) > 1) return F;                        // frame blocks with the loop relayed from CTA to CTA
     if (rx_frame_blocks(rx, ngroups, nc, F, false) == 1) return F;            // the fused kernel is the better plan
-    int fc = (F + rx->chunk_div - 1) / rx->chunk_div;
+    int fc = (F + div - 1) / div;
     if (fc < 8) fc = 8;
     return fc;
 }
@@ -1280,7 +1281,8 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
     // compute of the LAST job -- a quarter of the frames per job makes that job a quarter as long (65,536 channels x 64 frames:
     // 5.5 ms of whole-stream CTAs behind the last copy become 1.4 ms); the loop stays fused, state carries as between calls.
     int fc = F;
-    if (nslices == 1) fc = rx_plan_chunks(rx, C, F);
+    // (a host call's chunks are copies too: 16 at most -- with 32, configs[1]'s 8 KB / 128 B rows in and out cost 0.3 ms of 6.0)
+    if (nslices == 1) fc = rx_plan_chunks(rx, C, F, rx->chunk_div < 16 ? rx->chunk_div : 16);
     else if (chunk_ok)
         fc = (F + rx->host_tail_chunks - 1) / rx->host_tail_chunks;
     const bool chunked = fc < F;
