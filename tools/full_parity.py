@@ -56,17 +56,24 @@ def main():
     got = rx.read(capi.OUT_DIBITS)
     idx = rx.read(capi.OUT_INDEX)
     track = rx.read(capi.OUT_TRACK)
+    # the host-buffer entry point on the same PCM (channel slices x frame chunks, copies overlapped): the same bytes
+    host_pcm = pcm.cpu().numpy()
+    del pcm
+    rx.reset()
+    host_got = rx.rx_frames(host_pcm)
+    host_bad = int((host_got != got).sum())
+    del host_got
     rx.close()
     SHM = _scratch_path(nchan * nsamp * 2)
     host = np.memmap(SHM, dtype=np.int16, mode="w+", shape=(nchan, nsamp))
-    host[:] = pcm.cpu().numpy()
+    host[:] = host_pcm
     host.flush()
-    del pcm
+    del host_pcm
     cores = os.cpu_count() or 1
     step = max(32, nchan // (cores * 8))
     jobs = [(SHM, c, min(nchan, c + step), nsamp) for c in range(0, nchan, step)]
     t0 = time.time()
-    bad = {"dibit_bytes": 0, "index": 0, "phase": 0, "freq": 0}
+    bad = {"dibit_bytes": 0, "index": 0, "phase": 0, "freq": 0, "host_path_dibit_bytes": host_bad}
     try:
         with mp.get_context("spawn").Pool(cores) as pool:
             for c0, packed, windex, wphase, wfreq in pool.imap_unordered(_worker, jobs):
