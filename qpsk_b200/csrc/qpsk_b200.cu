@@ -147,6 +147,8 @@ struct qpsk_b200_rx {
     int host_slice_halfwaves;               // QPSK_B200_HOST_SLICE_HALFWAVES: channel slice of a frame-chunked host call, in half waves of front-end CTAs (default 1 = one CTA per SM)
     int host_tail_chunks;                   // QPSK_B200_HOST_CHUNKS=n: frame chunks per multi-slice host call (default 4; 1 = whole calls per slice)
     int chunk_div;                          // a chunked call is cut into this many frame chunks of at least 8 frames (QPSK_B200_CHUNK_DIV, <= QPSK_MAX_CHUNKS)
+    bool no_est_emit;                       // QPSK_B200_NO_EST_EMIT=1: always the separate pass (A/B measurements)
+    bool est_emit; int est_emit_n;          // this call's loop launches leave the estimator's 4th-power bursts behind (costas_emit_power4)
     int plan_chunks, plan_fblocks, plan_loop;   // qpsk_b200_rx_last_plan
     int relay_mode;                         // QPSK_B200_RELAY in the environment: 0 = never, 1 = when the cost model says so (default), n > 1 = n frame blocks whenever legal
     int chase_smem;                         // dynamic shared memory a chasing loop CTA asks for and never touches: keeps front-end CTAs off its SM
@@ -408,6 +410,8 @@ extern "C" int qpsk_b200_rx_create(const qpsk_b200_rx_config* cfg, int nchan, in
     rx->relay_mode = 1;
     rx->chunk_div = QPSK_MAX_CHUNKS;
     if (const char* cd = getenv("QPSK_B200_CHUNK_DIV")) { const int v = atoi(cd); if (v >= 1 && v <= QPSK_MAX_CHUNKS) rx->chunk_div = v; }
+    rx->est_emit = false; rx->est_emit_n = 0; rx->no_est_emit = false;
+    if (const char* ne = getenv("QPSK_B200_NO_EST_EMIT")) rx->no_est_emit = atoi(ne) != 0;
     rx->plan_chunks = 0; rx->plan_fblocks = 0; rx->plan_loop = QPSK_B200_LOOP_STANDALONE;
     rx->host_tail_chunks = 4;
     rx->host_slice_halfwaves = 1;
@@ -679,6 +683,16 @@ static int rx_ensure_front_scratch(qpsk_b200_rx* rx, int grid) {
     return 0;
 }
 
+// The in-call estimator's bursts (4th power of the call's first n symbols) are left behind by the loop itself when every one
+// of those symbols is consumed within the call: frame m of the call is consumed by loop frame m + 1, so n symbols need
+// n / nsym + 1 frames.  Otherwise (short calls; the seeding call, whose loop runs after the estimate) symbol_power4_kernel
+// makes a pass over the ring as before.
+static void rx_plan_est_emit(qpsk_b200_rx* rx, int F, bool seeding) {
+    const int n = est_burst_length(rx, F);
+    rx->est_emit = rx->est_on && !seeding && rx->d_est_bursts != nullptr && !rx->no_est_emit && n % rx->nsym == 0 && n / rx->nsym + 1 <= F;
+    rx->est_emit_n = rx->est_emit ? n : 0;
+}
+
 static CostasArgs rx_costas_args(const qpsk_b200_rx* rx, const RxJob& j) {
     const size_t Cp = rx->Cpad, S = rx->nsym, fo = j.f_off;
     CostasArgs ca;
@@ -690,6 +704,7 @@ static CostasArgs rx_costas_args(const qpsk_b200_rx* rx, const RxJob& j) {
     ca.c0 = j.c0; ca.c1 = (j.c0 + j.nc < rx->C) ? j.c0 + j.nc : rx->C;
     ca.slot_base = rx->slot_base; ca.nslots = rx->nslots; ca.ub_mode = rx->cfg.ub_mode;
     // TRANSIENT_SYMBOLS: the estimator reads the call's first symbols after the kernel, those slots stay
+    ca.est_bursts = rx->est_emit ? rx->d_est_bursts : nullptr; ca.est_n = rx->est_emit_n; ca.est_f_off = (int)fo;
     ca.discard_from = -1;
     if (rx->cfg.flags & QPSK_B200_TRANSIENT_SYMBOLS)
         ca.discard_from = rx->est_on ? (est_burst_length(rx, j.F + j.f_off) + rx->nsym - 1) / rx->nsym + 1 - j.f_off : 1;
@@ -795,13 +810,16 @@ static int rx_launch_estimator(qpsk_b200_rx* rx, int c0, int c1, int F, int firs
         rx->est_fft_n = n;
     }
     rx->est_call_n = n;
-    dim3 grid((c1 - c0 + 31) / 32, (n + 31) / 32), block(32, 8);
-    symbol_power4_kernel<<<grid, block, 0, s>>>(rx->d_dec_ring, rx->d_est_bursts, c0, c1, rx->Cpad, rx->nsym, rx->nslots, first_slot, n);
-    CU(cudaGetLastError());
+    if (!(rx->est_emit && rx->est_emit_n == n)) {          // the loop has not left the bursts behind: one pass over the ring
+        dim3 grid((c1 - c0 + 31) / 32, (n + 31) / 32), block(32, 8);
+        symbol_power4_kernel<<<grid, block, 0, s>>>(rx->d_dec_ring, rx->d_est_bursts, c0, c1, rx->Cpad, rx->nsym, rx->nslots, first_slot, n);
+        CU(cudaGetLastError());
+        rx->launches += 1;
+    }
     int rc = qpsk_b200_fft_argmax_device(rx->est_fft, reinterpret_cast<const float*>(rx->d_est_bursts + (size_t)c0 * n), c1 - c0,
                                          rx->d_est_bins + c0, rx->d_est_mag + c0, s);
     if (rc) return rc;
-    rx->launches += 2;
+    rx->launches += 1;
     return 0;
 }
 
@@ -854,6 +872,7 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
     const int first_slot = (rx->slot_base + 1) % rx->nslots;
     // PREROTATE_OFFSET, first call after a reset: the loop runs as its own kernel, after the estimator has seeded it
     const bool seeding = rx->prerotate && !rx->loop_seeded;
+    rx_plan_est_emit(rx, F, seeding);
     const bool saved_no_fuse = rx->no_fuse;
     if (seeding) rx->no_fuse = true;
     // chunked call: ONE loop kernel chases the chunks through flags (costas_chase_kernel) when no chunk's front end would carry
@@ -1305,6 +1324,7 @@ static int rx_submit_host(qpsk_b200_rx* rx, const int16_t* h_pcm, int nframes, u
     cudaStream_t sc = rx->stream;
     const int first_slot = (rx->slot_base + 1) % rx->nslots;
     const bool seeding = rx->prerotate && !rx->loop_seeded && !copy_only;      // see rx_run_call
+    if (!copy_only) rx_plan_est_emit(rx, F, seeding);
     const bool saved_no_fuse = rx->no_fuse;
     if (seeding) rx->no_fuse = true;
     bool loop_stream_used = false, est_done = false;
@@ -2317,9 +2337,7 @@ __global__ void symbol_power4_kernel(const float2* __restrict__ ring, float2* __
         const int k = k0 + j, c = c0 + threadIdx.x;
         if (k < n && c < C) {
             const int slot = (first_slot + k / nsym) % nslots;
-            const float2 z = ring[((size_t)slot * nsym + (k % nsym)) * Cpad + c];
-            const float2 z2 = make_float2(z.x * z.x - z.y * z.y, 2.0f * z.x * z.y);
-            tile[j][threadIdx.x] = make_float2(z2.x * z2.x - z2.y * z2.y, 2.0f * z2.x * z2.y);
+            tile[j][threadIdx.x] = power4_exact(ring[((size_t)slot * nsym + (k % nsym)) * Cpad + c]);
         }
     }
     __syncthreads();

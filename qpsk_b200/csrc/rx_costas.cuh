@@ -19,6 +19,8 @@ struct CostasArgs {
     int C, Cpad, F, nsym, sps, N;
     int c0, c1;              // channels [c0, c1) are processed by the standalone kernel launch
     int slot_base, nslots, ub_mode;
+    float2* est_bursts;      // optional [C][est_n]: the loop leaves the 4th power of the call's first est_n symbols here (the estimator's
+    int est_n, est_f_off;    // input) as it consumes them; est_f_off = position of this launch's frame 0 in the call
     int discard_from;        // QPSK_B200_TRANSIENT_SYMBOLS: ring slots consumed by frame 0 and by frames >= discard_from are dropped from L2
                              // without write-back once the loop has read them (-1: every slot is kept, OUT_DEC stays readable)
     float alpha, beta, max_freq, min_freq;
@@ -51,6 +53,27 @@ __device__ __forceinline__ unsigned costas_symbol(const float2 d, float& phase, 
     else if (freq < p.min_freq) freq = p.min_freq;
     const float2 r = cmul_exact_packed(y, p.rot45);            // qpsk.c:74-79
     return (r.x < 0.0f ? 1u : 0u) | (r.y < 0.0f ? 2u : 0u);
+}
+
+// z^4 as the frequency estimator wants it (QPSK on the axes raised to the 4th power is a tone at 4 x offset); one definition
+// for the loop's own emission and for symbol_power4_kernel, so both give the same bits
+__device__ __forceinline__ float2 power4_exact(const float2 z) {
+    const float2 z2 = make_float2(__fsub_rn(__fmul_rn(z.x, z.x), __fmul_rn(z.y, z.y)), __fmul_rn(__fmul_rn(2.0f, z.x), z.y));
+    return make_float2(__fsub_rn(__fmul_rn(z2.x, z2.x), __fmul_rn(z2.y, z2.y)), __fmul_rn(__fmul_rn(2.0f, z2.x), z2.y));
+}
+
+// The ring slot frame f has just consumed holds frame m = (call frame of f) - 1 of this call; if it belongs to the estimator's
+// burst, its 4th powers go to est_bursts[c][m * nsym ...] now, while the slot is hot in L2 -- instead of a pass over the ring
+// after the kernel (0.31 ms and 0.5 GB of reads per 65,536-channel call).  Off the loop's path on purpose (a call, no inlining):
+// it runs for 8 of 64 frames and must not cost the frame loop a register.
+__device__ __noinline__ void costas_emit_power4(const float2* __restrict__ cur, float2* __restrict__ dst, int nsym, int Cpad) {
+    for (int k = 0; k < nsym; k += 4) {
+        float2 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) w[i] = power4_exact(__ldcg(cur + (size_t)(k + i) * Cpad));
+        reinterpret_cast<float4*>(dst + k)[0] = make_float4(w[0].x, w[0].y, w[1].x, w[1].y);
+        reinterpret_cast<float4*>(dst + k)[1] = make_float4(w[2].x, w[2].y, w[3].x, w[3].y);
+    }
 }
 
 // One rx_frame call's worth of loop iterations for channel c (qpsk.c:196-212): consumes ring slot
@@ -108,6 +131,10 @@ __device__ __forceinline__ void costas_run_frame(const CostasArgs& a, const Cost
         }
     }
     a.track_t[(size_t)f * a.Cpad + c] = make_float2(phase, freq);
+    if (a.est_bursts != nullptr) {
+        const int m = f + a.est_f_off - 1;
+        if (m >= 0 && m * a.nsym < a.est_n) costas_emit_power4(cur, a.est_bursts + (size_t)c * a.est_n + (size_t)m * a.nsym, a.nsym, a.Cpad);
+    }
 }
 
 // The ring slot frame f has just consumed is dead (nobody reads it again: the next reader of that slot is a later call's frame
