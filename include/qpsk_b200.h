@@ -204,6 +204,9 @@ int qpsk_b200_rx_last_kernel_ms(qpsk_b200_rx *rx, float *front_ms, float *costas
 #define QPSK_B200_LOOP_CHASING    3   /* one kernel on SMs of its own that chases the frame chunks */
 #define QPSK_B200_LOOP_FOLLOWING  4   /* one-warp CTAs beside a frame-blocked front end (QPSK_B200_FOLLOW=1) */
 int qpsk_b200_rx_last_plan(const qpsk_b200_rx *rx, int *frame_chunks, int *frame_blocks, int *loop_mode);
+/* the launch policy alone (no device touched): the plan of a device-resident call of nchan channels x nframes frames at symbol
+ * rate rs (2400 or 1200) on a GPU of nsm SMs, default configuration; sm_clock_khz <= 0 = 1,965,000 */
+int qpsk_b200_debug_plan(int nsm, int sm_clock_khz, int nchan, int nframes, double rs, int *frame_chunks, int *frame_blocks, int *loop_mode);
 
 /* ------------------------------------------------------------------------------------------
  * Channel-batched rrc_fir()/rrc_make()  (rrc_fir.h:16-17, rrc_fir.c:17-76)

@@ -71,6 +71,7 @@ def lib():
     L.qpsk_b200_rx_launch_count.restype = C.c_longlong
     L.qpsk_b200_rx_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.qpsk_b200_rx_last_plan.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.qpsk_b200_debug_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.qpsk_b200_rx_estimate_offset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.qpsk_b200_probe_fp32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     _bind_fir(L)

@@ -864,6 +864,15 @@ static int rx_plan_chunks(const qpsk_b200_rx* rx, int nc, int F, int div = 0) {
     return fc;
 }
 
+// Is the loop of a chunked call (fc < F frames per chunk) ONE kernel that chases the chunks?  (the reasons are with its use in rx_run_call)
+static bool rx_chase_plan(const qpsk_b200_rx* rx, int F, int fc, bool seeding) {
+    const int ngroups_all = (rx->C + QPSK_GROUP - 1) / QPSK_GROUP;
+    const int nchunks = (F + fc - 1) / fc;
+    return fc < F && !rx->no_chase && !seeding && nchunks <= QPSK_MAX_CHUNKS && rx->chase_smem > 0
+           && ((rx->C + 127) / 128) * 8 <= rx->nsm
+           && rx_frame_blocks(rx, ngroups_all, rx->C, fc, true) > 1 && rx_frame_blocks(rx, ngroups_all, rx->C, F - (nchunks - 1) * fc, true) > 1;
+}
+
 // The device-resident call: frame chunks on `s`, the loop of a chunked call on the loop stream.  CUDA events bracket K1
 // and K3 of every chunk (qpsk_b200_rx_last_kernel_ms sums them).
 static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, int F, cudaStream_t s) {
@@ -884,9 +893,7 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
     // channels x 64 frames, the 2-GPU strong-scaling shape, planned as chunks) left no SM a 110 KB front-end CTA could start
     // on: the loop waited for a front end that waited for the loop, until the watchdog.  More channels than that run the
     // per-chunk loop kernels, which wait for nothing.
-    const bool chase = chunked && !rx->no_chase && !seeding && nchunks <= QPSK_MAX_CHUNKS && rx->chase_smem > 0
-                       && ((rx->C + 127) / 128) * 8 <= rx->nsm
-                       && rx_frame_blocks(rx, ngroups_all, rx->C, fc, true) > 1 && rx_frame_blocks(rx, ngroups_all, rx->C, F - (nchunks - 1) * fc, true) > 1;
+    const bool chase = rx_chase_plan(rx, F, fc, seeding);
     RxJob whole;
     whole.d_pcm = d_pcm; whole.pcm_row = pcm_row; whole.c0 = 0; whole.nc = rx->C; whole.F = F; whole.f_off = 0;
     const CostasArgs chase_args = rx_costas_args(rx, whole);
@@ -1035,6 +1042,47 @@ static int rx_run_call(qpsk_b200_rx* rx, const int16_t* d_pcm, size_t pcm_row, i
     rx->plan_chunks = k;
     if (chase) rx->plan_loop = QPSK_B200_LOOP_CHASING;
     return 0;
+}
+
+// The launch policy alone, for a device it is told about: what qpsk_b200_rx_process_device would do with nchan channels x
+// nframes frames at symbol rate rs on a GPU of nsm SMs (default configuration, exact arithmetic).  Touches no device: the
+// host-side tests pin the policy's decisions for the BASELINE shapes with it.
+extern "C" int qpsk_b200_debug_plan(int nsm, int sm_clock_khz, int nchan, int nframes, double rs, int* frame_chunks, int* frame_blocks, int* loop_mode) {
+    if (nsm < 1 || nchan < 1 || nframes < 1) return fail(QPSK_B200_ERR_ARG, "nsm, nchan and nframes must be positive");
+    const int sps = (int)(9600.0 / rs);
+    if (sps != 4 && sps != 8) return fail(QPSK_B200_ERR_ARG, "samples/symbol %d unsupported (4 = 2400 baud, 8 = 1200 baud)", sps);
+    qpsk_b200_rx* rx = new (std::nothrow) qpsk_b200_rx();
+    if (!rx) return fail(QPSK_B200_ERR_ARG, "out of host memory");
+    memset(rx, 0, sizeof *rx);
+    rx->cfg.mode = QPSK_B200_MODE_EXACT;
+    rx->C = nchan; rx->Cpad = (nchan + QPSK_GROUP - 1) / QPSK_GROUP * QPSK_GROUP; rx->maxF = nframes; rx->N = 512; rx->sps = sps; rx->nsym = 512 / sps;
+    rx->nsm = nsm; rx->sm_clock_khz = sm_clock_khz > 0 ? sm_clock_khz : 1965000;
+    rx->front_v1 = true; rx->relay_mode = 1; rx->chunk_div = QPSK_MAX_CHUNKS; rx->chase_smem = 120 * 1024;
+    rx->block_progress_n = (size_t)(rx->Cpad / QPSK_GROUP) * nframes + 1;
+    rx->d_block_progress = reinterpret_cast<unsigned long long*>(rx);      // only ever tested against null here
+    const int ngroups = rx->Cpad / QPSK_GROUP, F = nframes;
+    const int fc = rx_plan_chunks(rx, nchan, F);
+    int chunks = 1, blocks = 1, mode = QPSK_B200_LOOP_FUSED;
+    if (fc < F) {
+        chunks = (F + fc - 1) / fc;
+        blocks = rx_frame_blocks(rx, ngroups, nchan, fc, true);
+        mode = rx_chase_plan(rx, F, fc, false) ? QPSK_B200_LOOP_CHASING : blocks == 1 ? QPSK_B200_LOOP_FUSED : QPSK_B200_LOOP_STANDALONE;
+    } else if (rx_relay_blocks(rx, ngroups, F) > 1) {
+        blocks = rx_relay_blocks(rx, ngroups, F);
+        const int fpb = (F + blocks - 1) / blocks;
+        blocks = (F + fpb - 1) / fpb;
+        mode = QPSK_B200_LOOP_RELAYED;
+    } else {
+        blocks = rx_frame_blocks(rx, ngroups, nchan, F, false);
+        const int fpb = (F + blocks - 1) / blocks;
+        blocks = (F + fpb - 1) / fpb;
+        mode = blocks == 1 ? QPSK_B200_LOOP_FUSED : QPSK_B200_LOOP_STANDALONE;
+    }
+    delete rx;
+    if (frame_chunks) *frame_chunks = chunks;
+    if (frame_blocks) *frame_blocks = blocks;
+    if (loop_mode) *loop_mode = mode;
+    return QPSK_B200_OK;
 }
 
 extern "C" int qpsk_b200_rx_last_plan(const qpsk_b200_rx* rx, int* frame_chunks, int* frame_blocks, int* loop_mode) {
